@@ -1,0 +1,163 @@
+/*
+ * wab_b200.h — C ABI of the B200-native batched Wolves-and-Bushes simulator.
+ *
+ * The reference (johnmatthewtennant/wab-gym) has no FFI / plugin layer: its only boundary is the
+ * Python gym surface of WolvesAndBushesEnv (/root/reference/wab_env.py:103-342). This header is the
+ * boundary a binding for that surface calls into; each entry point names the reference interface it
+ * replaces. Plain pointers and sizes only — no torch types. All `d_*` pointers are DEVICE pointers
+ * owned by the caller (16-byte aligned for `d_grids`), all work is enqueued on the caller's
+ * cudaStream_t (passed as void* so C callers need no CUDA headers), nothing synchronises unless
+ * stated. One handle <-> one device <-> one stream at a time; handles are independent.
+ *
+ * Return value of every int function: 0 on success, a WAB_E_* code otherwise; the message is
+ * available from wab_last_error() (thread-local).
+ */
+#ifndef WAB_B200_H
+#define WAB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WAB_ABI_VERSION 1
+#define WAB_MAX_ACTIONS 8
+
+enum {
+    WAB_OK = 0,
+    WAB_E_NULL = 1,        /* null pointer argument                                              */
+    WAB_E_CONFIG = 2,      /* invalid option values (reference: ValueError, wab_env.py:147-148)  */
+    WAB_E_UNSUPPORTED = 3, /* valid for the reference but outside what the kernels implement     */
+    WAB_E_CUDA = 4,        /* CUDA runtime error (message carries cudaGetErrorString)            */
+    WAB_E_NO_DEVICE = 5    /* no CUDA device: there is no CPU fallback                           */
+};
+
+/* Food arithmetic. The reference keeps food as float64 (wab_env.py:307-322, :452). WAB_FOOD_INT is
+ * an integer counter in units of 1/turns_to_empty_food, legal only when the host has proven it
+ * equivalent for every reachable state (wab_gym_b200/config.py: prove_integer_food). */
+enum { WAB_FOOD_F64 = 0, WAB_FOOD_INT = 1 };
+
+/* Rule constants — the POD image of `default_game_options` (wab_env.py:11-39) plus the action table
+ * (wab_env.py:149-182) and host-precomputed integer thresholds for the keyed draws. */
+typedef struct WabConfig {
+    int32_t abi_version;          /* WAB_ABI_VERSION                                               */
+    int32_t width, height;        /* viewport (odd; kernels implement 11x11)      wab_env.py:25-26 */
+    int32_t max_turns;            /*                                              wab_env.py:23    */
+    int32_t wolf_spawn_margin;    /* kernels implement 1                          wab_env.py:34    */
+    int32_t n_actions;            /* 5 or 6                                       wab_env.py:149-191 */
+    int8_t action_dx[WAB_MAX_ACTIONS];
+    int8_t action_dy[WAB_MAX_ACTIONS];
+    int8_t action_role[WAB_MAX_ACTIONS]; /* -1 = keep role (NaN in the reference) wab_env.py:257-258 */
+    uint8_t lookout_only;         /*                                              wab_env.py:19, :302 */
+    uint8_t restrict_view;        /*                                              wab_env.py:20, :351 */
+    uint8_t wolves;               /*                                              wab_env.py:37    */
+    uint8_t wolves_can_move;      /*                                              wab_env.py:38    */
+    uint8_t god_mode;             /*                                              wab_env.py:292   */
+    int8_t starting_role;         /* -1 = random                                  wab_env.py:598-599 */
+    uint8_t food_mode;            /* WAB_FOOD_F64 / WAB_FOOD_INT                                   */
+    uint8_t auto_reset;           /* 1: done envs are reset inside step() and their post-reset
+                                     observation is returned (VecEnv); 0: reference behaviour,
+                                     stepping after done keeps returning done     wab_env.py:328-340 */
+    int32_t food_int_start;       /* INT mode: starting_food * turns_to_empty_food                 */
+    int32_t food_int_inc;         /* INT mode: turns_to_empty_food / turns_to_fill_food            */
+    int32_t food_int_max;         /* INT mode: turns_to_empty_food (clip upper bound)              */
+    int32_t wolf_cap;             /* wolf slots per env (<= 15); overflow is counted, see stats    */
+    int32_t log_cap;              /* depletion-log slots per env (<= 255); overflow is counted     */
+    double food_start;            /* F64 mode: starting_food; < 0 = random        wab_env.py:596-597 */
+    double food_inc;              /* 1 / turns_to_fill_food                       wab_env.py:307-309 */
+    double food_dec;              /* 1 / turns_to_empty_food                      wab_env.py:316   */
+    double food_obs_scale;        /* turns_to_empty_food                          wab_env.py:452   */
+    uint32_t thr_spawn;           /* spawn  iff word <  thr  (U < chance/2)       wab_env.py:572-573 */
+    uint32_t thr_init;            /* init   iff word <  thr  (U < chance/2)       wab_env.py:589-590 */
+    uint64_t thr_keep;            /* wolf kept iff word >= thr (U > despawn)      wab_env.py:262-264 */
+    float reward_table[8];        /* [ate*4 + outcome], outcome 0 alive, 1 finished, 2 starved,
+                                     3 killed; the f32 image of the fp64 sums     wab_env.py:328-340 */
+    uint32_t mask_lookout[4];     /* 121-bit blind-spot masks, bit = i*11 + j     wab_env.py:109-139 */
+    uint32_t mask_gatherer[4];
+} WabConfig;
+
+/* Observation batch: the first six elements of the reference's tuple (wab_env.py:374-385) for N
+ * envs. The seventh (view_mask) is a function of role and options only. */
+typedef struct WabObs {
+    uint8_t *d_grids;  /* [N][3][11][11] u8: wolves, bushes, ostriches; cell [i][j] = [5-dx][5-dy] */
+    uint8_t *d_food;   /* [N] ceil(food * turns_to_empty_food)                     wab_env.py:452  */
+    uint8_t *d_role;   /* [N]                                                      wab_env.py:390  */
+    uint8_t *d_status; /* [N] 0 alive, 1 starved, 2 killed                         wab_env.py:387  */
+} WabObs;
+
+/* info byte written by step (optional): bits 0-1 outcome (index into reward_table), bit 2 ate,
+ * bit 3 invalid action, bits 4-5 status before auto-reset. */
+#define WAB_INFO_OUTCOME(b) ((b) & 3)
+#define WAB_INFO_ATE(b) (((b) >> 2) & 1)
+#define WAB_INFO_BAD_ACTION(b) (((b) >> 3) & 1)
+#define WAB_INFO_FINAL_STATUS(b) (((b) >> 4) & 3)
+
+/* indices into the int64[8] vector of wab_vec_stats */
+enum {
+    WAB_STAT_EPISODES = 0, WAB_STAT_STEPS = 1, WAB_STAT_FINISHED = 2, WAB_STAT_STARVED = 3,
+    WAB_STAT_KILLED = 4, WAB_STAT_EATS = 5, WAB_STAT_BAD_ACTIONS = 6, WAB_STAT_OVERFLOWS = 7
+};
+
+typedef struct WabVec WabVec;
+
+/* Replaces WolvesAndBushesEnv.__init__ (wab_env.py:106-186) for n_envs environments with global ids
+ * env_id_base .. env_id_base + n_envs - 1 (keys depend on the global id only, so results do not
+ * depend on how a batch is sharded over GPUs). bush_thr[k-1] = least 32-bit draw whose bush value
+ * round(U**bush_power * max_berries) is >= k (wab_env.py:631-635). Allocates state on `device`.
+ * Does NOT reset (the reference constructor does, :186): call wab_vec_reset. */
+int wab_vec_create(const WabConfig *cfg, const uint32_t *bush_thr, int32_t n_bush_thr, int64_t n_envs,
+                   uint64_t seed, uint64_t env_id_base, int32_t device, WabVec **out);
+
+/* Replaces reset() (wab_env.py:231-248). d_mask: NULL = all envs, else u8[N], nonzero = reset. Each
+ * reset env starts its next episode (first reset -> episode 0). Observations are written for EVERY
+ * env (unreset ones get their current state's fresh observation). */
+int wab_vec_reset(WabVec *h, const uint8_t *d_mask, WabObs obs, void *stream);
+
+/* Replaces step(action) (wab_env.py:250-342) for all envs. d_actions u8[N]; outputs: obs, d_reward
+ * f32[N], d_done u8[N], d_info u8[N] (may be NULL). */
+int wab_vec_step(WabVec *h, const uint8_t *d_actions, WabObs obs, float *d_reward, uint8_t *d_done,
+                 uint8_t *d_info, void *stream);
+
+/* T lockstep steps in ONE launch: d_actions u8[T][N]; every step's results are materialised:
+ * grids [T][N][3][11][11], food/role/status/done/info [T][N], reward [T][N] (info may be NULL). */
+int wab_vec_step_many(WabVec *h, int32_t n_steps, const uint8_t *d_actions, WabObs obs, float *d_reward,
+                      uint8_t *d_done, uint8_t *d_info, void *stream);
+
+/* Same contract as wab_vec_step with HOST buffers (pageable or pinned): copies actions in, steps,
+ * copies every output back, and synchronises the stream before returning. h_info may be NULL. */
+int wab_vec_step_host(WabVec *h, const uint8_t *h_actions, uint8_t *h_grids, uint8_t *h_food,
+                      uint8_t *h_role, uint8_t *h_status, float *h_reward, uint8_t *h_done,
+                      uint8_t *h_info, void *stream);
+int wab_vec_reset_host(WabVec *h, uint8_t *h_grids, uint8_t *h_food, uint8_t *h_role, uint8_t *h_status,
+                       void *stream);
+
+/* Episode statistics accumulated on the device since create (or the last call with clear != 0):
+ * copies int64[8] (WAB_STAT_*) to h_out8 and synchronises the stream. d_out8 variant: enqueue a
+ * device-to-device copy only (for an NCCL all-reduce by the caller), no sync. */
+int wab_vec_stats(WabVec *h, int64_t *h_out8, int32_t clear, void *stream);
+int wab_vec_stats_device(WabVec *h, int64_t *d_out8, void *stream);
+
+/* Hidden state for differential tests (synchronises). Any pointer may be NULL.
+ * x,y i32[N]; food f64[N] (INT mode: counter / turns_to_empty_food); role,status,turn i32[N];
+ * episode i64[N]; n_wolves i32[N]; wolves_xy i32[N][wolf_cap][2]; bush_mask u32[N][4];
+ * n_log i32[N]; log i32[N][log_cap][3] (x, y, eats). */
+int wab_vec_export_state(WabVec *h, int32_t *x, int32_t *y, double *food, int32_t *role, int32_t *status,
+                         int32_t *turn, int64_t *episode, int32_t *n_wolves, int32_t *wolves_xy,
+                         uint32_t *bush_mask, int32_t *n_log, int32_t *log_xyc, void *stream);
+
+int64_t wab_vec_num_envs(const WabVec *h);
+void wab_vec_destroy(WabVec *h);
+
+/* Raw Philox4x32-10 on the device for n counters (cross-checks the RNG contract). d_ctr u32[n][4],
+ * d_out u32[n][4]. */
+int wab_philox_device(const uint32_t *d_ctr, uint32_t key0, uint32_t key1, int64_t n, uint32_t *d_out,
+                      void *stream);
+
+const char *wab_last_error(void);
+int wab_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,133 @@
+// hostsim.cpp — TEST-ONLY host build of the kernel logic header wab_gym_b200/csrc/wab_core.cuh.
+//
+// Compiles the per-environment step / reset / observation-composition code that the CUDA kernels
+// run (the same header, the same Params builder) with g++, so that `-m "not gpu"` tests can compare
+// it with the oracle in a container without a GPU. It serialises what the kernel fans out over a
+// warp (36 bush blocks + 31 wolf-init groups of a reset; the 363-bit observation string of one env).
+// It is NOT a CPU fallback: nothing in the product package loads it.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../wab_gym_b200/csrc/wab_core.cuh"
+#include "../../wab_gym_b200/csrc/wab_params.h"
+
+using namespace wab;
+
+struct HostSim {
+    WabConfig cfg;
+    Params P;
+    std::vector<uint32_t> thr;
+    Env E;
+    std::vector<uint32_t> wolves, logcell;
+    std::vector<uint8_t> logcnt;
+    Slots S;
+    bool f64;
+};
+
+static void expand_obs(const HostSim* h, const uint32_t wm[4], const uint32_t bm[4], uint32_t role, uint8_t* grids) {
+    uint32_t B[12];
+    compose_obs(h->P, wm, bm, role, B);
+    B[11] = 0u;   // bits 352..362 (last ostrich row) are never set
+    for (int b = 0; b < OBS_BYTES; ++b) grids[b] = (uint8_t)((B[b >> 5] >> (b & 31)) & 1u);
+}
+
+extern "C" {
+
+HostSim* hostsim_create(const WabConfig* cfg, const uint32_t* bush_thr, int32_t n_bush_thr, uint64_t seed,
+                        uint64_t env_id, char* err, int errlen) {
+    std::string e;
+    if (validate_config(cfg, n_bush_thr, 1, e) != WAB_OK) {
+        if (err && errlen > 0) { strncpy(err, e.c_str(), errlen - 1); err[errlen - 1] = 0; }
+        return nullptr;
+    }
+    HostSim* h = new HostSim();
+    h->cfg = *cfg;
+    h->thr.assign(bush_thr, bush_thr + n_bush_thr);
+    params_from_config(*cfg, h->thr.data(), n_bush_thr, seed, 0, h->P);
+    h->P.bush_thr = h->thr.data();
+    h->f64 = cfg->food_mode == WAB_FOOD_F64;
+    memset(&h->E, 0, sizeof(h->E));
+    h->E.env_id = (uint32_t)env_id;
+    h->E.episode = 0xFFFFFFFFu;
+    h->wolves.assign(cfg->wolf_cap, 0); h->logcell.assign(cfg->log_cap, 0); h->logcnt.assign(cfg->log_cap, 0);
+    h->S.wolves = h->wolves.data(); h->S.wstride = 1;
+    h->S.logcell = h->logcell.data(); h->S.logcnt = h->logcnt.data(); h->S.lstride = 1;
+    return h;
+}
+void hostsim_destroy(HostSim* h) { delete h; }
+
+// returns overflow flag
+static uint32_t do_reset(HostSim* h, uint32_t wm[4], uint32_t bm[4]) {
+    uint32_t overflow = 0;
+    if (h->f64) reset_scalars<true>(h->P, h->E); else reset_scalars<false>(h->P, h->E);
+    uint32_t m[4] = {0, 0, 0, 0};
+    for (int blk = 0; blk < 36; ++blk) reset_bush_block(h->P, h->E.env_id, h->E.episode, blk, m);
+    for (int w = 0; w < 4; ++w) h->E.m[w] = m[w];
+    if (h->P.wolves)
+        for (int grp = 0; grp < 31; ++grp) {
+            uint32_t hits = reset_init_group(h->P, h->E.env_id, h->E.episode, grp);
+            for (int l = 0; l < 4; ++l)
+                if ((hits >> l) & 1u) {
+                    int c = 4 * grp + l;
+                    if (h->E.nw < (uint32_t)h->P.wolf_cap) {
+                        h->S.wolves[h->E.nw] = pack_xy(c / 11 - HALF, c % 11 - HALF);
+                        h->E.nw += 1;
+                    } else overflow = 1;
+                }
+        }
+    wolf_plane(h->E, h->S, wm);
+    for (int w = 0; w < 4; ++w) bm[w] = h->E.m[w];
+    return overflow;
+}
+
+void hostsim_reset(HostSim* h, uint8_t* grids, int32_t* food, int32_t* role, int32_t* status, int32_t* overflow) {
+    uint32_t wm[4], bm[4];
+    uint32_t ov = do_reset(h, wm, bm);
+    expand_obs(h, wm, bm, h->E.role, grids);
+    *food = (int32_t)food_observation(h->P, h->E, h->f64);
+    *role = (int32_t)h->E.role; *status = (int32_t)h->E.status;
+    if (overflow) *overflow = (int32_t)ov;
+}
+
+// One step with the kernel's semantics (auto-reset when configured: post-reset observation).
+void hostsim_step(HostSim* h, int32_t action, uint8_t* grids, int32_t* food, int32_t* role, int32_t* status,
+                  float* reward, int32_t* done, int32_t* info, int32_t* overflow) {
+    StepOut O;
+    memset(&O, 0, sizeof(O));
+    if (h->f64) env_step<true>(h->P, h->E, h->S, (uint32_t)action, O);
+    else env_step<false>(h->P, h->E, h->S, (uint32_t)action, O);
+    if (O.done && h->P.auto_reset) {
+        O.overflow |= do_reset(h, O.wm, O.bm);
+        O.food_obs = food_observation(h->P, h->E, h->f64);
+        O.role = h->E.role; O.status = h->E.status;
+    }
+    expand_obs(h, O.wm, O.bm, O.role, grids);
+    *food = (int32_t)O.food_obs; *role = (int32_t)O.role; *status = (int32_t)O.status;
+    *reward = O.reward; *done = (int32_t)O.done; *info = (int32_t)O.info;
+    if (overflow) *overflow = (int32_t)O.overflow;
+}
+
+// hidden state: x, y, food (as double), role, status, turn, episode, nw, nlog; wolves (2 ints each)
+void hostsim_state(const HostSim* h, int32_t* scal9, double* food, int32_t* wolves_xy, uint32_t* bush_mask) {
+    const Env& E = h->E;
+    scal9[0] = E.x; scal9[1] = E.y; scal9[2] = E.food_i; scal9[3] = (int32_t)E.role; scal9[4] = (int32_t)E.status;
+    scal9[5] = (int32_t)E.turn; scal9[6] = (int32_t)E.episode; scal9[7] = (int32_t)E.nw; scal9[8] = (int32_t)E.nlog;
+    *food = h->f64 ? E.food_f : (double)E.food_i / h->P.food_obs_scale;
+    for (uint32_t k = 0; k < E.nw; ++k) {
+        wolves_xy[2 * k] = unpack_x(h->S.wolves[k]); wolves_xy[2 * k + 1] = unpack_y(h->S.wolves[k]);
+    }
+    for (int w = 0; w < 4; ++w) bush_mask[w] = E.m[w];
+}
+
+void hostsim_philox(const uint32_t* ctr, uint32_t k0, uint32_t k1, uint32_t* out) {
+    Params P;
+    memset(&P, 0, sizeof(P));
+    fill_round_keys(P, k0, k1);
+    philox(P, ctr[0], ctr[1], ctr[2], ctr[3], out);
+}
+
+}  // extern "C"

@@ -1,0 +1,482 @@
+// wab_core.cuh — per-environment step logic of the B200 Wolves-and-Bushes simulator.
+//
+// Everything in this header is one environment's worth of work executed by ONE thread; it is
+// written `__host__ __device__` so that tests/hostsim can compile the very same logic with g++ and
+// compare it against the oracle without a GPU (a unit test of the kernel logic — the product has no
+// CPU path). Warp-cooperative pieces (reset fan-out, observation expansion, coalesced stores) live
+// in wab_kernels.cu.
+//
+// Behaviour follows /root/reference/wab_env.py:250-342 (step), :231-248 (reset), :359-452 (obs);
+// each block below cites the lines it implements. Data layout is NOT the reference's:
+//   * bushes  : a 121-bit occupancy mask of the 11x11 window (bit i*11+j, [i][j] = [5-dx][5-dy],
+//               wab_env.py:403-409) slides with the ostrich; bush values are procedural
+//               (food0 = f(keyed draw of the cell)) so only cells that were EATEN need state: a
+//               small depletion log (cell, eats). Replaces the ever-growing record frame (:613-629).
+//   * wolves  : up to wolf_cap packed (x:i16, y:i16) slots.
+//   * food    : integer counter when proven equivalent on the host, else the reference's fp64.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define WAB_HD __host__ __device__ __forceinline__
+#else
+#define WAB_HD static inline
+#endif
+
+namespace wab {
+
+constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
+constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
+enum : uint32_t { SITE_BUSH = 1, SITE_INIT = 2, SITE_SPAWN = 3, SITE_DESP = 4, SITE_START = 5 };
+
+constexpr int VIEW = 11, HALF = 5, CELLS = 121, RING = 48;
+constexpr int OBS_BYTES = 3 * CELLS;        // 363 bytes per env: wolves, bushes, ostriches
+constexpr uint32_t TOP_WORD_MASK = 0x01FFFFFFu;  // 121 = 3*32 + 25
+
+// bit c = 11*i + j.  Column j = 0 -> bits 0,11,...,110 ; column j = 10 -> bits 10,21,...,120
+constexpr uint32_t colmask_word(int j, int w) {
+    uint32_t m = 0;
+    for (int i = 0; i < VIEW; ++i) {
+        int c = 11 * i + j;
+        if ((c >> 5) == w) m |= 1u << (c & 31);
+    }
+    return m;
+}
+
+template <int J, int W> struct ColMask { static constexpr uint32_t v = colmask_word(J, W); };
+
+// Rule constants + RNG schedule, passed to kernels by value (constant bank).
+struct Params {
+    uint32_t rk0[10], rk1[10];     // Philox round keys (key is uniform: the seed)
+    uint32_t thr_bush1;            // food0 > 0  <=>  word >= thr_bush1   (bush_thr[0])
+    uint32_t thr_spawn, thr_init;  // event <=> word < thr
+    uint32_t n_bush_thr;
+    uint64_t thr_keep;             // kept <=> word >= thr_keep
+    const uint32_t* bush_thr;      // device table, n_bush_thr entries
+    uint64_t act_tbl;              // per action a, byte a: (dx+1) | (dy+1)<<2 | (role+1)<<4
+    int32_t n_actions, max_turns;
+    int32_t food_int_start, food_int_inc, food_int_max;
+    int32_t wolf_cap, log_cap;
+    uint8_t lookout_only, restrict_view, wolves, wolves_can_move, god_mode, auto_reset;
+    int8_t starting_role;
+    uint8_t food_random;           // starting_food is None
+    double food_start, food_inc, food_dec, food_obs_scale;
+    float reward_table[8];
+    uint32_t mask_look[4], mask_gath[4];
+    uint64_t env_id_base;
+};
+
+// Registers of one environment.
+struct Env {
+    int32_t x, y;
+    uint32_t turn, role, status, nw, nlog, episode, env_id;
+    uint32_t m[4];   // bush occupancy of the window (food > 0), current
+    int32_t food_i;  // INT mode
+    double food_f;   // F64 mode
+};
+
+// Per-env variable-length storage: element k of this env is base[k * stride].
+struct Slots {
+    uint32_t* wolves; int32_t wstride;
+    uint32_t* logcell; uint8_t* logcnt; int64_t lstride;
+};
+
+struct StepOut {
+    uint32_t wm[4];   // wolf plane of the observation
+    uint32_t bm[4];   // bush plane of the observation (snapshot before eating, wab_env.py:289 vs :312)
+    uint32_t food_obs, role, status, done, info;
+    float reward;
+    uint32_t ate, bad_action, overflow, outcome;
+};
+
+WAB_HD uint32_t pack_xy(int32_t x, int32_t y) { return ((uint32_t)x & 0xFFFFu) | ((uint32_t)y << 16); }
+WAB_HD int32_t unpack_x(uint32_t p) { return (int32_t)(int16_t)(p & 0xFFFFu); }
+WAB_HD int32_t unpack_y(uint32_t p) { return (int32_t)(int16_t)(p >> 16); }
+
+WAB_HD uint32_t fshl(uint32_t lo, uint32_t hi, uint32_t s) {  // upper word of (hi:lo) << s, 0 <= s < 32
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(lo, hi, s);
+#else
+    return s ? (hi << s) | (lo >> (32 - s)) : hi;
+#endif
+}
+WAB_HD uint32_t fshr(uint32_t lo, uint32_t hi, uint32_t s) {  // lower word of (hi:lo) >> s, 0 <= s < 32
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, s);
+#else
+    return s ? (lo >> s) | (hi << (32 - s)) : lo;
+#endif
+}
+WAB_HD void shl128(uint32_t* m, uint32_t s) {
+    m[3] = fshl(m[2], m[3], s); m[2] = fshl(m[1], m[2], s); m[1] = fshl(m[0], m[1], s); m[0] = m[0] << s;
+}
+WAB_HD void shr128(uint32_t* m, uint32_t s) {
+    m[0] = fshr(m[0], m[1], s); m[1] = fshr(m[1], m[2], s); m[2] = fshr(m[2], m[3], s); m[3] = m[3] >> s;
+}
+WAB_HD void setbit128(uint32_t* m, int pos, uint32_t on) {
+    uint32_t b = on << (pos & 31);
+    int w = pos >> 5;
+    m[0] |= (w == 0) ? b : 0u; m[1] |= (w == 1) ? b : 0u; m[2] |= (w == 2) ? b : 0u; m[3] |= (w == 3) ? b : 0u;
+}
+
+// Philox4x32-10 (Salmon et al. SC'11). Round keys come precomputed from Params.
+WAB_HD void philox(const Params& P, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)PHILOX_M0 * c0;
+        uint64_t p1 = (uint64_t)PHILOX_M1 * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ P.rk0[r];
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ P.rk1[r];
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+WAB_HD uint32_t ctr2(uint32_t site, uint32_t turn, uint32_t sub) { return (site << 28) | ((turn & 0xFFFFFu) << 8) | (sub & 0xFFu); }
+WAB_HD uint32_t pick4(const uint32_t w[4], uint32_t lane) {
+    uint32_t a = (lane & 1u) ? w[1] : w[0];
+    uint32_t b = (lane & 1u) ? w[3] : w[2];
+    return (lane & 2u) ? b : a;
+}
+
+// number of thresholds <= word  ==  round(U**power * max_berries)   (wab_env.py:631-635)
+WAB_HD int32_t bush_value(const Params& P, uint32_t word) {
+    int32_t lo = 0, hi = (int32_t)P.n_bush_thr;
+    while (lo < hi) {
+        int32_t mid = (lo + hi) >> 1;
+#if defined(__CUDA_ARCH__)
+        uint32_t t = __ldg(P.bush_thr + mid);
+#else
+        uint32_t t = P.bush_thr[mid];
+#endif
+        if (t <= word) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+WAB_HD uint32_t bush_word(const Params& P, const Env& E, int32_t x, int32_t y) {
+    uint32_t w[4];
+    philox(P, E.env_id, E.episode, ctr2(SITE_BUSH, 0, 0), pack_xy(x >> 1, y >> 1), w);
+    return pick4(w, ((uint32_t)x & 1u) | (((uint32_t)y & 1u) << 1));
+}
+// eats recorded for a cell, or -1
+WAB_HD int32_t log_find(const Env& E, const Slots& S, uint32_t cell) {
+    for (uint32_t l = 0; l < E.nlog; ++l)
+        if (S.logcell[(int64_t)l * S.lstride] == cell) return (int32_t)l;
+    return -1;
+}
+// bush at (x, y) still has food, given its first-reveal draw `word` (only called when word >= thr_bush1)
+WAB_HD uint32_t bush_alive(const Params& P, const Env& E, const Slots& S, int32_t x, int32_t y, uint32_t word) {
+    if (E.nlog == 0) return 1u;
+    int32_t l = log_find(E, S, pack_xy(x, y));
+    if (l < 0) return 1u;
+    return (int32_t)S.logcnt[(int64_t)l * S.lstride] < bush_value(P, word) ? 1u : 0u;
+}
+
+// 11-bit value with bit g at stride 11 (positions 11*g), as four words.
+WAB_HD void spread11(uint32_t v, uint32_t t[4]) {
+    t[0] = ((v & 7u) * 0x00100401u) & 0x00400801u;
+    t[1] = ((((v >> 3) & 7u) * 0x00100401u) & 0x00400801u) << 1;
+    t[2] = ((((v >> 6) & 7u) * 0x00100401u) & 0x00400801u) << 2;
+    t[3] = ((((v >> 9) & 3u) * 0x00100401u) & 0x00400801u) << 3;
+}
+
+// Slide the window after the ostrich moved by (dx, dy) (one of them non-zero) to (E.x, E.y) and
+// reveal the 11 new cells: generate_bushes, wab_env.py:613-629, for cells without a record; cells
+// seen before get the same draw (keys do not depend on the turn) minus what was eaten.
+WAB_HD void slide_window(const Params& P, Env& E, const Slots& S, int32_t dx, int32_t dy) {
+    // drop the column that would wrap into the neighbouring row, then shift by 11*dx + dy
+    if (dy > 0) {
+        E.m[0] &= ~ColMask<10, 0>::v; E.m[1] &= ~ColMask<10, 1>::v; E.m[2] &= ~ColMask<10, 2>::v; E.m[3] &= ~ColMask<10, 3>::v;
+    }
+    if (dy < 0) {
+        E.m[0] &= ~ColMask<0, 0>::v; E.m[1] &= ~ColMask<0, 1>::v; E.m[2] &= ~ColMask<0, 2>::v; E.m[3] &= ~ColMask<0, 3>::v;
+    }
+    int32_t s = 11 * dx + dy;
+    shl128(E.m, (uint32_t)(s > 0 ? s : 0));
+    shr128(E.m, (uint32_t)(s < 0 ? -s : 0));
+    E.m[3] &= TOP_WORD_MASK;
+
+    const bool along_y = (dx != 0);                       // new row (fixed x) or new column (fixed y)
+    const int32_t fixed = along_y ? E.x + HALF * dx : E.y + HALF * dy;
+    const int32_t vmax = (along_y ? E.y : E.x) + HALF;    // cell g of the line has coordinate vmax - g
+    const int32_t vb0 = (vmax - 10) >> 1;
+    const uint32_t fb = (uint32_t)fixed & 1u;
+    uint32_t line = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 3
+#endif
+    for (int b = 0; b < 6; ++b) {
+        const int32_t vb = vb0 + b;
+        uint32_t w[4];
+        const uint32_t payload = along_y ? pack_xy(fixed >> 1, vb) : pack_xy(vb, fixed >> 1);
+        philox(P, E.env_id, E.episode, ctr2(SITE_BUSH, 0, 0), payload, w);
+        // lane = (x&1) | (y&1)<<1 ; the two cells of this block on our line differ in the along bit
+        const uint32_t we0 = along_y ? (fb ? w[1] : w[0]) : (fb ? w[2] : w[0]);
+        const uint32_t we1 = along_y ? (fb ? w[3] : w[2]) : (fb ? w[3] : w[1]);
+        for (int e = 0; e < 2; ++e) {
+            const int32_t v = 2 * vb + e;
+            const int32_t g = vmax - v;
+            const uint32_t word = e ? we1 : we0;
+            uint32_t on = (g >= 0 && g <= 10 && word >= P.thr_bush1 && P.n_bush_thr > 0) ? 1u : 0u;
+            if (on && E.nlog)
+                on = along_y ? bush_alive(P, E, S, fixed, v, word) : bush_alive(P, E, S, v, fixed, word);
+            line |= on << (g & 15);
+        }
+    }
+    if (along_y) {                                // row i = 0 (dx > 0) or i = 10 (dx < 0): bits 11*i + g
+        E.m[0] |= (dx > 0) ? line : 0u;
+        E.m[3] |= (dx < 0) ? (line << 14) : 0u;   // 110 = 96 + 14
+    } else {                                      // column j = 0 (dy > 0) or j = 10 (dy < 0): bits 11*g + j
+        uint32_t t[4];
+        spread11(line, t);
+        shl128(t, dy < 0 ? 10u : 0u);
+        E.m[0] |= t[0]; E.m[1] |= t[1]; E.m[2] |= t[2]; E.m[3] |= t[3];
+    }
+}
+
+// ring cell j (oracle/keyed_rng.py ring_index) -> offset from the ostrich
+WAB_HD void ring_offset(int j, int32_t& dx, int32_t& dy) {
+    int bx, by;
+    if (j < 13) { bx = 0; by = j; }
+    else if (j < 35) { bx = 1 + ((j - 13) >> 1); by = ((j - 13) & 1) ? 12 : 0; }
+    else { bx = 12; by = j - 35; }
+    dx = bx - 6; dy = by - 6;
+}
+
+WAB_HD uint32_t food_observation(const Params& P, const Env& E, bool f64) {
+    if (!f64) return (uint32_t)E.food_i;
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)(int32_t)ceil(__dmul_rn(E.food_f, P.food_obs_scale));   // wab_env.py:452
+#else
+    return (uint32_t)(int32_t)__builtin_ceil(E.food_f * P.food_obs_scale);
+#endif
+}
+
+// wolf plane from the current wolf slots (wab_env.py:412-428)
+WAB_HD void wolf_plane(const Env& E, const Slots& S, uint32_t wm[4]) {
+    wm[0] = wm[1] = wm[2] = wm[3] = 0u;
+    for (uint32_t k = 0; k < E.nw; ++k) {
+        uint32_t p = S.wolves[(int32_t)k * S.wstride];
+        int32_t ddx = E.x - unpack_x(p), ddy = E.y - unpack_y(p);
+        if (ddx >= -HALF && ddx <= HALF && ddy >= -HALF && ddy <= HALF)
+            setbit128(wm, 11 * (ddx + HALF) + (ddy + HALF), 1u);
+    }
+}
+
+// One step of one environment: wab_env.py:250-342 up to (not including) auto-reset and the
+// observation stores. `F64` selects the reference's fp64 food arithmetic.
+template <bool F64>
+WAB_HD void env_step(const Params& P, Env& E, const Slots& S, uint32_t action, StepOut& O) {
+    // ---- :251-258 action
+    O.bad_action = (action >= (uint32_t)P.n_actions) ? 1u : 0u;
+    const uint32_t code = O.bad_action ? 0x05u /* dx=0, dy=0, keep */ : (uint32_t)(P.act_tbl >> (8 * action)) & 0xFFu;
+    const int32_t dx = (int32_t)(code & 3u) - 1, dy = (int32_t)((code >> 2) & 3u) - 1;
+    const int32_t nrole = (int32_t)((code >> 4) & 3u) - 1;
+    E.turn += 1;                                   // :252
+    E.x += dx; E.y += dy;                          // :255-256
+    if (nrole >= 0) E.role = (uint32_t)nrole;      // :257-258
+    O.overflow = 0;
+
+    // ---- :259 generate_bushes for the newly visible line
+    if (dx != 0 || dy != 0) slide_window(P, E, S, dx, dy);
+
+    // ---- :262-264 despawn (keep iff U > chance). rank = ordinal among earlier wolves on the cell.
+    if (E.nw) {
+        uint32_t kept = 0;
+        uint32_t keepmask = 0;
+        for (uint32_t k = 0; k < E.nw; ++k) {
+            const uint32_t p = S.wolves[(int32_t)k * S.wstride];
+            uint32_t rank = 0;
+            for (uint32_t q = 0; q < k; ++q) rank += (S.wolves[(int32_t)q * S.wstride] == p) ? 1u : 0u;
+            uint32_t w[4];
+            philox(P, E.env_id, E.episode, ctr2(SITE_DESP, E.turn, rank >> 2), p, w);
+            if ((uint64_t)pick4(w, rank & 3u) >= P.thr_keep) keepmask |= 1u << k;
+        }
+        for (uint32_t k = 0; k < E.nw; ++k)
+            if ((keepmask >> k) & 1u) {
+                S.wolves[(int32_t)kept * S.wstride] = S.wolves[(int32_t)k * S.wstride];
+                ++kept;
+            }
+        E.nw = kept;
+    }
+
+    // ---- :266 the frame the rest of the step reads: bushes with food > 0, ostrich status
+    O.bm[0] = E.m[0]; O.bm[1] = E.m[1]; O.bm[2] = E.m[2]; O.bm[3] = E.m[3];
+    const uint32_t status_pre = E.status;
+
+    // ---- :267-297 wolves chase (ties -> x axis), kill on contact; wolf plane after the move (:289)
+    O.wm[0] = O.wm[1] = O.wm[2] = O.wm[3] = 0u;
+    for (uint32_t k = 0; k < E.nw; ++k) {
+        const uint32_t p = S.wolves[(int32_t)k * S.wstride];
+        int32_t wx = unpack_x(p), wy = unpack_y(p);
+        int32_t ddx = E.x - wx, ddy = E.y - wy;                                  // :59-60
+        if (P.wolves_can_move) {
+            const int32_t ax = ddx < 0 ? -ddx : ddx, ay = ddy < 0 ? -ddy : ddy;
+            const int32_t sx = (ddx > 0) - (ddx < 0), sy = (ddy > 0) - (ddy < 0);
+            wx += (ax >= ay) ? sx : 0;                                           // :278-280
+            wy += (ax < ay) ? sy : 0;                                            // :281-283
+            S.wolves[(int32_t)k * S.wstride] = pack_xy(wx, wy);                  // :285-286
+            ddx = E.x - wx; ddy = E.y - wy;
+        }
+        if (ddx == 0 && ddy == 0 && !P.god_mode) E.status = 2u;                  // :292-297
+        if (ddx >= -HALF && ddx <= HALF && ddy >= -HALF && ddy <= HALF)          // :416-427
+            setbit128(O.wm, 11 * (ddx + HALF) + (ddy + HALF), 1u);
+    }
+
+    // ---- :300-313 eat (bush and status as of the frame above; role is fresh)
+    O.ate = 0;
+    if (((O.bm[1] >> 28) & 1u) && (E.role == 1u || P.lookout_only) && status_pre == 0u) {   // bit 60 = [5][5]
+        O.ate = 1u;
+        if (F64) {
+            double f = E.food_f + P.food_inc;                                    // :307-309
+            f = f < 0.0 ? 0.0 : f; f = f > 1.0 ? 1.0 : f;                        // :310
+            E.food_f = f;
+        } else {
+            int32_t f = E.food_i + P.food_int_inc;
+            E.food_i = f > P.food_int_max ? P.food_int_max : f;
+        }
+        // bush.food -= 1 (:312): count the eat; the cell disappears when eats == its first-reveal value
+        const uint32_t cell = pack_xy(E.x, E.y);
+        const int32_t food0 = bush_value(P, bush_word(P, E, E.x, E.y));
+        int32_t l = log_find(E, S, cell);
+        int32_t eats;
+        if (l >= 0) {
+            eats = (int32_t)S.logcnt[(int64_t)l * S.lstride] + 1;
+            S.logcnt[(int64_t)l * S.lstride] = (uint8_t)eats;
+        } else if (E.nlog < (uint32_t)P.log_cap) {
+            eats = 1;
+            S.logcell[(int64_t)E.nlog * S.lstride] = cell;
+            S.logcnt[(int64_t)E.nlog * S.lstride] = 1;
+            E.nlog += 1;
+        } else {
+            eats = 1; O.overflow = 1u;             // counted, never silent (WAB_STAT_OVERFLOWS)
+        }
+        if (eats >= food0) E.m[1] &= ~(1u << 28);
+    }
+
+    // ---- :316-322 hunger, starvation (overrides killed)
+    if (F64) {
+        E.food_f = E.food_f - P.food_dec;
+        if (E.food_f <= 0.0) { E.status = 1u; E.food_f = 0.0; }
+    } else {
+        E.food_i -= 1;
+        if (E.food_i <= 0) { E.status = 1u; E.food_i = 0; }
+    }
+
+    // ---- :325-326 spawn_wolves on the 48 ring cells around the moved ostrich
+    if (P.wolves) {
+        uint32_t hitgroups = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 4
+#endif
+        for (int grp = 0; grp < RING / 4; ++grp) {
+            uint32_t w[4];
+            philox(P, E.env_id, E.episode, ctr2(SITE_SPAWN, E.turn, 0), (uint32_t)grp, w);
+            uint32_t a = w[0] < w[1] ? w[0] : w[1], b = w[2] < w[3] ? w[2] : w[3];
+            a = a < b ? a : b;
+            hitgroups |= (a < P.thr_spawn ? 1u : 0u) << grp;
+        }
+        while (hitgroups) {                        // rare: recompute the groups that hit
+#if defined(__CUDA_ARCH__)
+            const int grp = __ffs((int)hitgroups) - 1;
+#else
+            const int grp = __builtin_ctz(hitgroups);
+#endif
+            hitgroups &= hitgroups - 1u;
+            uint32_t w[4];
+            philox(P, E.env_id, E.episode, ctr2(SITE_SPAWN, E.turn, 0), (uint32_t)grp, w);
+            for (int l = 0; l < 4; ++l)
+                if (w[l] < P.thr_spawn) {                                        // :571-574
+                    int32_t ox, oy;
+                    ring_offset(4 * grp + l, ox, oy);
+                    if (E.nw < (uint32_t)P.wolf_cap) {
+                        S.wolves[(int32_t)E.nw * S.wstride] = pack_xy(E.x + ox, E.y + oy);
+                        E.nw += 1;
+                    } else {
+                        O.overflow = 1u;
+                    }
+                }
+        }
+    }
+
+    // ---- :328-340 reward, done
+    uint32_t outcome;
+    if (E.status == 0u) outcome = (E.turn >= (uint32_t)P.max_turns) ? 1u : 0u;
+    else outcome = (E.status == 1u) ? 2u : 3u;
+    O.outcome = outcome;
+    O.done = outcome != 0u;
+    O.reward = P.reward_table[O.ate * 4u + outcome];
+    O.info = outcome | (O.ate << 2) | (O.bad_action << 3) | (E.status << 4);
+
+    // ---- :342, :387-391, :450-452 scalar observation (fresh)
+    O.food_obs = food_observation(P, E, F64);
+    O.role = E.role;
+    O.status = E.status;
+}
+
+// ------------------------------------------------------------------ reset pieces (wab_env.py:231-248)
+// The 36 bush blocks and 31 wolf-init groups of a reset are independent Philox calls; the kernels
+// fan them out over the lanes of a warp. These two helpers are one lane's share.
+
+// bush block blk (0..35) of the reset window -> occupancy bits (generate_bushes at reset, :244)
+WAB_HD void reset_bush_block(const Params& P, uint32_t env_id, uint32_t episode, int blk, uint32_t part[4]) {
+    const int32_t xb = blk / 6 - 3, yb = blk % 6 - 3;       // x >> 1 for x in [-5, 5] is [-3, 2]
+    uint32_t w[4];
+    philox(P, env_id, episode, ctr2(SITE_BUSH, 0, 0), pack_xy(xb, yb), w);
+    for (int l = 0; l < 4; ++l) {
+        const int32_t x = 2 * xb + (l & 1), y = 2 * yb + (l >> 1);
+        const uint32_t on = (x >= -HALF && x <= HALF && y >= -HALF && y <= HALF && P.n_bush_thr > 0 &&
+                             w[l] >= P.thr_bush1) ? 1u : 0u;
+        const int pos = 11 * (HALF - x) + (HALF - y);        // [i][j] = [5 - x][5 - y], ostrich at (0, 0)
+        setbit128(part, on ? pos : 0, on);
+    }
+}
+// wolf-init group grp (0..30): cells c = 4*grp .. 4*grp+3, c = (x+5)*11 + (y+5)  (:578-593) -> hit bits
+WAB_HD uint32_t reset_init_group(const Params& P, uint32_t env_id, uint32_t episode, int grp) {
+    uint32_t w[4];
+    philox(P, env_id, episode, ctr2(SITE_INIT, 0, 0), (uint32_t)grp, w);
+    uint32_t hits = 0;
+    for (int l = 0; l < 4; ++l)
+        hits |= ((4 * grp + l < CELLS && w[l] < P.thr_init) ? 1u : 0u) << l;
+    return hits;
+}
+// scalar part of a reset: spawn_ostriches (:595-611)
+template <bool F64>
+WAB_HD void reset_scalars(const Params& P, Env& E) {
+    E.episode += 1;                 // first reset -> episode 0 (state is created with 0xFFFFFFFF)
+    E.turn = 0; E.x = 0; E.y = 0; E.status = 0; E.nw = 0; E.nlog = 0;
+    E.role = (uint32_t)(P.starting_role < 0 ? 0 : P.starting_role);
+    E.food_i = P.food_int_start;
+    E.food_f = P.food_start;
+    if (P.starting_role < 0 || P.food_random) {
+        uint32_t w[4];
+        philox(P, E.env_id, E.episode, ctr2(SITE_START, 0, 0), 0u, w);
+        if (P.starting_role < 0) E.role = w[1] >> 31;                 // np.random.randint(2), :598-599
+        if (P.food_random) E.food_f = (double)w[0] * (1.0 / 4294967296.0);   // np.random.random(), :596-597
+    }
+    (void)F64;
+}
+
+// 363-bit observation string of one env as 11 words (bits 0..120 wolves, 121..241 bushes,
+// 242..362 ostriches; bit 302 = ostrich [5][5], never masked). mask_grid: wab_env.py:344-357.
+WAB_HD void compose_obs(const Params& P, const uint32_t wm_in[4], const uint32_t bm_in[4], uint32_t role,
+                        uint32_t B[11]) {
+    uint32_t wm[4], bm[4];
+    for (int w = 0; w < 4; ++w) {
+        uint32_t blind = P.restrict_view ? (role == 1u ? P.mask_gath[w] : P.mask_look[w]) : 0u;
+        wm[w] = wm_in[w] & ~blind;
+        bm[w] = bm_in[w] & ~blind;
+    }
+    B[0] = wm[0]; B[1] = wm[1]; B[2] = wm[2];
+    B[3] = wm[3] | (bm[0] << 25);                  // 121 = 3*32 + 25
+    B[4] = (bm[0] >> 7) | (bm[1] << 25);
+    B[5] = (bm[1] >> 7) | (bm[2] << 25);
+    B[6] = (bm[2] >> 7) | (bm[3] << 25);
+    B[7] = bm[3] >> 7;
+    B[8] = 0u;
+    B[9] = 1u << 14;                               // 242 + 60 = 302 = 9*32 + 14
+    B[10] = 0u;
+}
+
+}  // namespace wab

@@ -1,0 +1,621 @@
+// wab_kernels.cu — sm_100a kernels + the C ABI of include/wab_b200.h.
+//
+// Execution model (B200: 148 SMs, HBM-bound byte/integer work, no tensor cores on this path):
+//   * one THREAD per environment runs the scalar game rules of wab_core.cuh with its state in
+//     registers (struct-of-arrays in HBM, one coalesced load/store per field per launch — in the
+//     multi-step kernel the state never leaves registers between steps);
+//   * one WARP cooperates on the two pieces that are wide: (a) a reset fans its 36 + 31 independent
+//     Philox calls over the 32 lanes and OR-reduces the window with redux.sync; (b) the observation:
+//     each lane writes its env's 363-bit string into a shared-memory bit stream whose bit b is
+//     exactly byte b of the warp's contiguous 32 x [3][11][11] u8 output, then the warp expands the
+//     stream 16 bits -> 16 bytes per lane and issues fully coalesced 16-byte streaming stores.
+//   * per-(env, episode, turn, cell) Philox4x32-10 counters make every draw order-free
+//     (oracle/keyed_rng.py states the contract).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+
+#include "../../include/wab_b200.h"
+#include "wab_core.cuh"
+#include "wab_params.h"
+
+using namespace wab;
+
+namespace {
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr int STREAM_WORDS = 364;   // 32 envs * 363 bits = 363 words (+1 pad keeps rows 8-byte aligned)
+
+struct StatePtrs {
+    uint32_t* pos;       // [N]  x:i16 | y:i16 << 16
+    uint32_t* misc;      // [N]  food_i:8 | role:1 | status:2 | nw:4 | -:1 | turn:16
+    uint32_t* episode;   // [N]
+    uint4* bush;         // [N]  121-bit window occupancy
+    uint8_t* nlog;       // [N]
+    double* food;        // [N]  F64 mode only
+    uint32_t* wolves;    // [wolf_cap][N]
+    uint32_t* logcell;   // [log_cap][N]
+    uint8_t* logcnt;     // [log_cap][N]
+    unsigned long long* stats;  // [8]
+    int64_t n;
+};
+
+struct OutPtrs {
+    uint8_t* grids; uint8_t* food; uint8_t* role; uint8_t* status;
+    float* reward; uint8_t* done; uint8_t* info;
+};
+
+template <bool F64>
+__device__ __forceinline__ void load_env(const Params& P, const StatePtrs& st, int64_t idx, Env& E,
+                                         uint32_t* wolves_s, int bs) {
+    const uint32_t pos = st.pos[idx], misc = st.misc[idx];
+    E.x = unpack_x(pos); E.y = unpack_y(pos);
+    E.food_i = (int32_t)(misc & 0xFFu);
+    E.role = (misc >> 8) & 1u; E.status = (misc >> 9) & 3u; E.nw = (misc >> 11) & 15u; E.turn = misc >> 16;
+    E.episode = st.episode[idx];
+    const uint4 b = st.bush[idx];
+    E.m[0] = b.x; E.m[1] = b.y; E.m[2] = b.z; E.m[3] = b.w;
+    E.nlog = st.nlog[idx];
+    E.food_f = F64 ? st.food[idx] : 0.0;
+    E.env_id = (uint32_t)(P.env_id_base + (uint64_t)idx);
+    for (uint32_t k = 0; k < E.nw; ++k) wolves_s[k * bs] = st.wolves[(int64_t)k * st.n + idx];
+}
+
+template <bool F64>
+__device__ __forceinline__ void store_env(const StatePtrs& st, int64_t idx, const Env& E,
+                                          const uint32_t* wolves_s, int bs) {
+    st.pos[idx] = pack_xy(E.x, E.y);
+    st.misc[idx] = ((uint32_t)E.food_i & 0xFFu) | (E.role << 8) | (E.status << 9) | (E.nw << 11) | (E.turn << 16);
+    st.episode[idx] = E.episode;
+    st.bush[idx] = make_uint4(E.m[0], E.m[1], E.m[2], E.m[3]);
+    st.nlog[idx] = (uint8_t)E.nlog;
+    if (F64) st.food[idx] = E.food_f;
+    for (uint32_t k = 0; k < E.nw; ++k) st.wolves[(int64_t)k * st.n + idx] = wolves_s[k * bs];
+}
+
+// Reset every env of the warp whose `need` is set (wab_env.py:231-248). All 32 lanes must call.
+// On return lanes with `need` hold the fresh state and their observation planes.
+template <bool F64>
+__device__ __forceinline__ void warp_reset(const Params& P, Env& E, const Slots& S, bool need, int lane,
+                                           uint32_t wm[4], uint32_t bm[4], uint32_t& overflow) {
+    unsigned todo = __ballot_sync(FULL, need);
+    if (need) reset_scalars<F64>(P, E);
+    while (todo) {
+        const int r = __ffs((int)todo) - 1;
+        todo &= todo - 1u;
+        const uint32_t eid = __shfl_sync(FULL, E.env_id, r);
+        const uint32_t ep = __shfl_sync(FULL, E.episode, r);
+        uint32_t part[4] = {0u, 0u, 0u, 0u};
+        reset_bush_block(P, eid, ep, lane, part);                 // blocks 0..31
+        if (lane < 4) reset_bush_block(P, eid, ep, 32 + lane, part);   // blocks 32..35
+        const uint32_t m0 = __reduce_or_sync(FULL, part[0]);
+        const uint32_t m1 = __reduce_or_sync(FULL, part[1]);
+        const uint32_t m2 = __reduce_or_sync(FULL, part[2]);
+        const uint32_t m3 = __reduce_or_sync(FULL, part[3]);
+        const uint32_t hits = (P.wolves && lane < 31) ? reset_init_group(P, eid, ep, lane) : 0u;
+        unsigned hl = __ballot_sync(FULL, hits != 0u);
+        if (lane == r) { E.m[0] = m0; E.m[1] = m1; E.m[2] = m2; E.m[3] = m3; }
+        while (hl) {                                              // rare: p = 0.0005 per cell
+            const int src = __ffs((int)hl) - 1;
+            hl &= hl - 1u;
+            const uint32_t h = __shfl_sync(FULL, hits, src);
+            if (lane == r) {
+                for (int l = 0; l < 4; ++l)
+                    if ((h >> l) & 1u) {
+                        const int c = 4 * src + l;
+                        if (E.nw < (uint32_t)P.wolf_cap) {
+                            S.wolves[(int32_t)E.nw * S.wstride] = pack_xy(c / 11 - HALF, c % 11 - HALF);
+                            E.nw += 1;
+                        } else {
+                            overflow = 1u;
+                        }
+                    }
+            }
+        }
+    }
+    if (need) {
+        wolf_plane(E, S, wm);
+        bm[0] = E.m[0]; bm[1] = E.m[1]; bm[2] = E.m[2]; bm[3] = E.m[3];
+    }
+}
+
+__device__ __forceinline__ uint32_t nibble_to_bytes(uint32_t n) { return (n * 0x00204081u) & 0x01010101u; }
+
+// Write the warp's observations: 32 envs x 363 bytes, contiguous from `gbase` (16-byte aligned).
+// `stream` is this warp's STREAM_WORDS shared-memory words. n_valid = envs of this warp that exist.
+__device__ __forceinline__ void emit_obs(const Params& P, uint32_t* stream, const uint32_t wm[4],
+                                         const uint32_t bm[4], uint32_t role, bool active, int lane,
+                                         uint8_t* gbase, int n_valid) {
+    uint32_t B[11];
+    if (active) {
+        compose_obs(P, wm, bm, role, B);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 11; ++k) B[k] = 0u;
+    }
+    // env `lane` owns bits [363*lane, 363*lane + 363); its last 60 bits are always zero, so the word
+    // it shares with lane+1 is written by lane+1 alone: plain stores, no atomics.
+    const uint32_t sh = (11u * (uint32_t)lane) & 31u;            // 363 mod 32 = 11
+    const int fw = (OBS_BYTES * lane) >> 5;
+    const int nown = ((OBS_BYTES * (lane + 1)) >> 5) - fw;       // 11 or 12
+    stream[fw] = B[0] << sh;
+#pragma unroll
+    for (int k = 1; k < 11; ++k) stream[fw + k] = fshl(B[k - 1], B[k], sh);
+    if (nown == 12) stream[fw + 11] = fshl(B[10], 0u, sh);
+    __syncwarp();
+    const uint16_t* hs = reinterpret_cast<const uint16_t*>(stream);
+    const int nbytes = OBS_BYTES * n_valid;
+    const int nfull = nbytes >> 4;
+#pragma unroll 4
+    for (int c = lane; c < nfull; c += 32) {
+        const uint32_t h = hs[c];
+        uint4 v;
+        v.x = nibble_to_bytes(h & 15u);
+        v.y = nibble_to_bytes((h >> 4) & 15u);
+        v.z = nibble_to_bytes((h >> 8) & 15u);
+        v.w = nibble_to_bytes(h >> 12);
+        __stcs(reinterpret_cast<uint4*>(gbase) + c, v);
+    }
+    const int b = (nfull << 4) + lane;                            // ragged tail of a partial warp
+    if (lane < 16 && b < nbytes) gbase[b] = (uint8_t)((stream[b >> 5] >> (b & 31)) & 1u);
+    __syncwarp();
+}
+
+__device__ __forceinline__ void write_scalars(const OutPtrs& out, int64_t o, const StepOut& O) {
+    out.food[o] = (uint8_t)O.food_obs;
+    out.role[o] = (uint8_t)O.role;
+    out.status[o] = (uint8_t)O.status;
+    if (out.reward) out.reward[o] = O.reward;
+    if (out.done) out.done[o] = (uint8_t)O.done;
+    if (out.info) out.info[o] = (uint8_t)O.info;
+}
+
+__device__ __forceinline__ void flush_stats(unsigned long long* stats, const uint32_t c[8], uint32_t* block_s) {
+    // warp redux -> shared atomics -> 8 global atomics per block
+    if (threadIdx.x < 8) block_s[threadIdx.x] = 0u;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t s = __reduce_add_sync(FULL, c[k]);
+        if ((threadIdx.x & 31) == 0 && s) atomicAdd(&block_s[k], s);
+    }
+    __syncthreads();
+    if (threadIdx.x < 8 && block_s[threadIdx.x]) atomicAdd(&stats[threadIdx.x], (unsigned long long)block_s[threadIdx.x]);
+}
+
+// T lockstep steps of every env; observation, reward, done and info are written for every step.
+template <bool F64>
+__global__ void __launch_bounds__(128) wab_step_kernel(const __grid_constant__ Params P, const StatePtrs st,
+                                                       const uint8_t* __restrict__ actions, const int n_steps,
+                                                       const OutPtrs out) {
+    extern __shared__ uint32_t smem[];
+    const int bs = blockDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* wolves_s = smem + threadIdx.x;                                   // [wolf_cap][bs]
+    uint32_t* stream = smem + P.wolf_cap * bs + warp * STREAM_WORDS;
+    uint32_t* block_s = smem + P.wolf_cap * bs + (bs >> 5) * STREAM_WORDS;     // 8 words
+    const int64_t idx = (int64_t)blockIdx.x * bs + threadIdx.x;
+    const int64_t n = st.n;
+    const bool active = idx < n;
+    const int64_t warp_first = idx - lane;
+    const int n_valid = (int)((n - warp_first) < 32 ? (n - warp_first > 0 ? n - warp_first : 0) : 32);
+
+    Env E;
+    Slots S;
+    S.wolves = wolves_s; S.wstride = bs;
+    S.logcell = st.logcell + (active ? idx : 0); S.logcnt = st.logcnt + (active ? idx : 0); S.lstride = n;
+    if (active) load_env<F64>(P, st, idx, E, wolves_s, bs);
+    else { E = Env(); }
+
+    uint32_t cnt[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    for (int t = 0; t < n_steps; ++t) {
+        StepOut O;
+        bool need_reset = false;
+        if (active) {
+            const uint32_t a = actions[(int64_t)t * n + idx];
+            env_step<F64>(P, E, S, a, O);
+            need_reset = O.done && P.auto_reset;
+            cnt[WAB_STAT_EPISODES] += O.done;      // auto_reset = 0: every step that reports done counts
+            cnt[WAB_STAT_STEPS] += 1u;
+            cnt[WAB_STAT_FINISHED] += (O.outcome == 1u) ? 1u : 0u;
+            cnt[WAB_STAT_STARVED] += (O.outcome == 2u) ? 1u : 0u;
+            cnt[WAB_STAT_KILLED] += (O.outcome == 3u) ? 1u : 0u;
+            cnt[WAB_STAT_EATS] += O.ate;
+            cnt[WAB_STAT_BAD_ACTIONS] += O.bad_action;
+        } else {
+            O = StepOut();
+        }
+        if (__any_sync(FULL, need_reset)) {
+            warp_reset<F64>(P, E, S, need_reset, lane, O.wm, O.bm, O.overflow);
+            if (need_reset) {          // VecEnv semantics: the post-reset observation is returned
+                O.food_obs = food_observation(P, E, F64);
+                O.role = E.role; O.status = E.status;
+            }
+        }
+        if (active) {
+            cnt[WAB_STAT_OVERFLOWS] += O.overflow;
+            write_scalars(out, (int64_t)t * n + idx, O);
+        }
+        emit_obs(P, stream, O.wm, O.bm, O.role, active, lane,
+                 out.grids + ((int64_t)t * n + warp_first) * OBS_BYTES, n_valid);
+    }
+    if (active) store_env<F64>(st, idx, E, wolves_s, bs);
+    flush_stats(st.stats, cnt, block_s);
+}
+
+// reset(mask) + fresh observation of every env
+template <bool F64>
+__global__ void __launch_bounds__(128) wab_reset_kernel(const __grid_constant__ Params P, const StatePtrs st,
+                                                        const uint8_t* __restrict__ mask, const OutPtrs out) {
+    extern __shared__ uint32_t smem[];
+    const int bs = blockDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* wolves_s = smem + threadIdx.x;
+    uint32_t* stream = smem + P.wolf_cap * bs + warp * STREAM_WORDS;
+    uint32_t* block_s = smem + P.wolf_cap * bs + (bs >> 5) * STREAM_WORDS;
+    const int64_t idx = (int64_t)blockIdx.x * bs + threadIdx.x;
+    const int64_t n = st.n;
+    const bool active = idx < n;
+    const int64_t warp_first = idx - lane;
+    const int n_valid = (int)((n - warp_first) < 32 ? (n - warp_first > 0 ? n - warp_first : 0) : 32);
+    Env E;
+    Slots S;
+    S.wolves = wolves_s; S.wstride = bs;
+    S.logcell = st.logcell + (active ? idx : 0); S.logcnt = st.logcnt + (active ? idx : 0); S.lstride = n;
+    if (active) load_env<F64>(P, st, idx, E, wolves_s, bs);
+    else { E = Env(); }
+    const bool need = active && (mask == nullptr || mask[idx] != 0);
+    StepOut O = StepOut();
+    uint32_t cnt[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    if (active && !need) {
+        wolf_plane(E, S, O.wm);
+        O.bm[0] = E.m[0]; O.bm[1] = E.m[1]; O.bm[2] = E.m[2]; O.bm[3] = E.m[3];
+    }
+    warp_reset<F64>(P, E, S, need, lane, O.wm, O.bm, O.overflow);
+    if (active) {
+        O.food_obs = food_observation(P, E, F64);
+        O.role = E.role; O.status = E.status;
+        out.food[idx] = (uint8_t)O.food_obs; out.role[idx] = (uint8_t)O.role; out.status[idx] = (uint8_t)O.status;
+        cnt[WAB_STAT_OVERFLOWS] += O.overflow;
+        store_env<F64>(st, idx, E, wolves_s, bs);
+    }
+    emit_obs(P, stream, O.wm, O.bm, O.role, active, lane, out.grids + warp_first * OBS_BYTES, n_valid);
+    flush_stats(st.stats, cnt, block_s);
+}
+
+__global__ void wab_philox_kernel(const __grid_constant__ Params P, const uint32_t* __restrict__ ctr, int64_t n,
+                                  uint32_t* __restrict__ outw) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w[4];
+    philox(P, ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], w);
+    outw[4 * i] = w[0]; outw[4 * i + 1] = w[1]; outw[4 * i + 2] = w[2]; outw[4 * i + 3] = w[3];
+}
+
+// ---------------------------------------------------------------------------------------- host
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(WAB_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define WAB_CUDA(call)                                         \
+    do {                                                       \
+        cudaError_t e__ = (call);                              \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call);  \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+struct WabVec {
+    WabConfig cfg;
+    Params P;
+    StatePtrs st;
+    int device;
+    int64_t n;
+    void* slab;
+    uint32_t* d_thr;
+    // device staging for the host-buffer entry points
+    uint8_t* stage;
+    size_t stage_bytes;
+};
+
+namespace {
+
+int block_size_for(int64_t n) {
+    int bs = 128;
+    while (bs > 32 && (n + bs - 1) / bs < 2 * 148) bs >>= 1;   // keep >= 2 CTAs per SM when the batch allows
+    return bs;
+}
+size_t smem_bytes(const WabVec* h, int bs) {
+    return sizeof(uint32_t) * ((size_t)h->P.wolf_cap * bs + (size_t)(bs / 32) * STREAM_WORDS + 8);
+}
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int check_ptr_align(const void* p, const char* name) {
+    if (((uintptr_t)p & 15u) != 0) return fail(WAB_E_CONFIG, std::string(name) + " must be 16-byte aligned");
+    return WAB_OK;
+}
+
+int launch_step(WabVec* h, int n_steps, const uint8_t* d_actions, const WabObs& obs, float* d_reward,
+                uint8_t* d_done, uint8_t* d_info, cudaStream_t s) {
+    OutPtrs out{obs.d_grids, obs.d_food, obs.d_role, obs.d_status, d_reward, d_done, d_info};
+    const int bs = block_size_for(h->n);
+    const unsigned grid = (unsigned)((h->n + bs - 1) / bs);
+    const size_t sm = smem_bytes(h, bs);
+    if (h->cfg.food_mode == WAB_FOOD_F64)
+        wab_step_kernel<true><<<grid, bs, sm, s>>>(h->P, h->st, d_actions, n_steps, out);
+    else
+        wab_step_kernel<false><<<grid, bs, sm, s>>>(h->P, h->st, d_actions, n_steps, out);
+    WAB_CUDA(cudaGetLastError());
+    return WAB_OK;
+}
+
+int ensure_stage(WabVec* h, size_t bytes) {
+    if (h->stage_bytes >= bytes) return WAB_OK;
+    if (h->stage) cudaFree(h->stage);
+    h->stage = nullptr; h->stage_bytes = 0;
+    WAB_CUDA(cudaMalloc(&h->stage, bytes));
+    h->stage_bytes = bytes;
+    return WAB_OK;
+}
+
+struct StageLayout { size_t actions, grids, food, role, status, reward, done, info, total; };
+StageLayout stage_layout(int64_t n) {
+    StageLayout L;
+    size_t o = 0;
+    L.actions = o; o = align_up(o + (size_t)n, 256);
+    L.grids = o; o = align_up(o + (size_t)n * OBS_BYTES, 256);
+    L.food = o; o = align_up(o + (size_t)n, 256);
+    L.role = o; o = align_up(o + (size_t)n, 256);
+    L.status = o; o = align_up(o + (size_t)n, 256);
+    L.reward = o; o = align_up(o + (size_t)n * 4, 256);
+    L.done = o; o = align_up(o + (size_t)n, 256);
+    L.info = o; o = align_up(o + (size_t)n, 256);
+    L.total = o;
+    return L;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* wab_last_error(void) { return g_err.c_str(); }
+int wab_abi_version(void) { return WAB_ABI_VERSION; }
+
+int wab_vec_create(const WabConfig* cfg, const uint32_t* bush_thr, int32_t n_bush_thr, int64_t n_envs,
+                   uint64_t seed, uint64_t env_id_base, int32_t device, WabVec** out) {
+    if (!cfg || !out || (n_bush_thr > 0 && !bush_thr)) return fail(WAB_E_NULL, "null argument");
+    *out = nullptr;
+    if (int rc = validate_config(cfg, n_bush_thr, n_envs, g_err)) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(WAB_E_NO_DEVICE, "no CUDA device: wab_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(WAB_E_CONFIG, "bad device ordinal");
+    DeviceGuard guard(device);
+
+    WabVec* h = new (std::nothrow) WabVec();
+    if (!h) return fail(WAB_E_CUDA, "out of host memory");
+    memset(h, 0, sizeof(*h));
+    h->cfg = *cfg; h->device = device; h->n = n_envs;
+
+    Params& P = h->P;
+    params_from_config(*cfg, bush_thr, n_bush_thr, seed, env_id_base, P);
+
+    // one slab, every array 256-byte aligned
+    const size_t n = (size_t)n_envs;
+    size_t o = 0;
+    const size_t o_pos = o; o = align_up(o + 4 * n, 256);
+    const size_t o_misc = o; o = align_up(o + 4 * n, 256);
+    const size_t o_ep = o; o = align_up(o + 4 * n, 256);
+    const size_t o_bush = o; o = align_up(o + 16 * n, 256);
+    const size_t o_nlog = o; o = align_up(o + n, 256);
+    const size_t o_food = o; o = align_up(o + 8 * n, 256);
+    const size_t o_wolves = o; o = align_up(o + 4 * n * (size_t)cfg->wolf_cap, 256);
+    const size_t o_lcell = o; o = align_up(o + 4 * n * (size_t)cfg->log_cap, 256);
+    const size_t o_lcnt = o; o = align_up(o + n * (size_t)cfg->log_cap, 256);
+    const size_t o_stats = o; o = align_up(o + 64, 256);
+    cudaError_t e = cudaMalloc(&h->slab, o);
+    if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaMalloc(state)"); }
+    uint8_t* base = (uint8_t*)h->slab;
+    e = cudaMemset(base, 0, o);
+    if (e == cudaSuccess) e = cudaMemset(base + o_ep, 0xFF, 4 * n);   // episode -1: first reset -> 0
+    if (e == cudaSuccess && n_bush_thr > 0) {
+        e = cudaMalloc(&h->d_thr, sizeof(uint32_t) * (size_t)n_bush_thr);
+        if (e == cudaSuccess)
+            e = cudaMemcpy(h->d_thr, bush_thr, sizeof(uint32_t) * (size_t)n_bush_thr, cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) { cudaFree(h->slab); if (h->d_thr) cudaFree(h->d_thr); delete h; return cuda_fail(e, "state init"); }
+    P.bush_thr = h->d_thr;
+    StatePtrs& st = h->st;
+    st.pos = (uint32_t*)(base + o_pos); st.misc = (uint32_t*)(base + o_misc); st.episode = (uint32_t*)(base + o_ep);
+    st.bush = (uint4*)(base + o_bush); st.nlog = base + o_nlog; st.food = (double*)(base + o_food);
+    st.wolves = (uint32_t*)(base + o_wolves); st.logcell = (uint32_t*)(base + o_lcell); st.logcnt = base + o_lcnt;
+    st.stats = (unsigned long long*)(base + o_stats); st.n = n_envs;
+    *out = h;
+    return WAB_OK;
+}
+
+void wab_vec_destroy(WabVec* h) {
+    if (!h) return;
+    DeviceGuard guard(h->device);
+    if (h->slab) cudaFree(h->slab);
+    if (h->d_thr) cudaFree(h->d_thr);
+    if (h->stage) cudaFree(h->stage);
+    delete h;
+}
+
+int64_t wab_vec_num_envs(const WabVec* h) { return h ? h->n : 0; }
+
+int wab_vec_reset(WabVec* h, const uint8_t* d_mask, WabObs obs, void* stream) {
+    if (!h || !obs.d_grids || !obs.d_food || !obs.d_role || !obs.d_status) return fail(WAB_E_NULL, "null argument");
+    if (int rc = check_ptr_align(obs.d_grids, "d_grids")) return rc;
+    DeviceGuard guard(h->device);
+    OutPtrs out{obs.d_grids, obs.d_food, obs.d_role, obs.d_status, nullptr, nullptr, nullptr};
+    const int bs = block_size_for(h->n);
+    const unsigned grid = (unsigned)((h->n + bs - 1) / bs);
+    const size_t sm = smem_bytes(h, bs);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (h->cfg.food_mode == WAB_FOOD_F64) wab_reset_kernel<true><<<grid, bs, sm, s>>>(h->P, h->st, d_mask, out);
+    else wab_reset_kernel<false><<<grid, bs, sm, s>>>(h->P, h->st, d_mask, out);
+    WAB_CUDA(cudaGetLastError());
+    return WAB_OK;
+}
+
+int wab_vec_step(WabVec* h, const uint8_t* d_actions, WabObs obs, float* d_reward, uint8_t* d_done,
+                 uint8_t* d_info, void* stream) {
+    if (!h || !d_actions || !obs.d_grids || !obs.d_food || !obs.d_role || !obs.d_status || !d_reward || !d_done)
+        return fail(WAB_E_NULL, "null argument");
+    if (int rc = check_ptr_align(obs.d_grids, "d_grids")) return rc;
+    DeviceGuard guard(h->device);
+    return launch_step(h, 1, d_actions, obs, d_reward, d_done, d_info, (cudaStream_t)stream);
+}
+
+int wab_vec_step_many(WabVec* h, int32_t n_steps, const uint8_t* d_actions, WabObs obs, float* d_reward,
+                      uint8_t* d_done, uint8_t* d_info, void* stream) {
+    if (!h || !d_actions || !obs.d_grids || !obs.d_food || !obs.d_role || !obs.d_status || !d_reward || !d_done)
+        return fail(WAB_E_NULL, "null argument");
+    if (n_steps < 1 || n_steps > 65535) return fail(WAB_E_CONFIG, "n_steps must be in [1, 65535]");
+    if (n_steps > 1 && (h->n % 16) != 0)
+        return fail(WAB_E_UNSUPPORTED, "step_many needs n_envs to be a multiple of 16 (16-byte aligned step slabs)");
+    if (int rc = check_ptr_align(obs.d_grids, "d_grids")) return rc;
+    DeviceGuard guard(h->device);
+    return launch_step(h, n_steps, d_actions, obs, d_reward, d_done, d_info, (cudaStream_t)stream);
+}
+
+int wab_vec_step_host(WabVec* h, const uint8_t* h_actions, uint8_t* h_grids, uint8_t* h_food, uint8_t* h_role,
+                      uint8_t* h_status, float* h_reward, uint8_t* h_done, uint8_t* h_info, void* stream) {
+    if (!h || !h_actions || !h_grids || !h_food || !h_role || !h_status || !h_reward || !h_done)
+        return fail(WAB_E_NULL, "null argument");
+    DeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const StageLayout L = stage_layout(h->n);
+    if (int rc = ensure_stage(h, L.total)) return rc;
+    uint8_t* b = h->stage;
+    const size_t n = (size_t)h->n;
+    WAB_CUDA(cudaMemcpyAsync(b + L.actions, h_actions, n, cudaMemcpyHostToDevice, s));
+    WabObs obs{b + L.grids, b + L.food, b + L.role, b + L.status};
+    if (int rc = launch_step(h, 1, b + L.actions, obs, (float*)(b + L.reward), b + L.done, b + L.info, s)) return rc;
+    WAB_CUDA(cudaMemcpyAsync(h_grids, b + L.grids, n * OBS_BYTES, cudaMemcpyDeviceToHost, s));
+    WAB_CUDA(cudaMemcpyAsync(h_food, b + L.food, n, cudaMemcpyDeviceToHost, s));
+    WAB_CUDA(cudaMemcpyAsync(h_role, b + L.role, n, cudaMemcpyDeviceToHost, s));
+    WAB_CUDA(cudaMemcpyAsync(h_status, b + L.status, n, cudaMemcpyDeviceToHost, s));
+    WAB_CUDA(cudaMemcpyAsync(h_reward, b + L.reward, n * 4, cudaMemcpyDeviceToHost, s));
+    WAB_CUDA(cudaMemcpyAsync(h_done, b + L.done, n, cudaMemcpyDeviceToHost, s));
+    if (h_info) WAB_CUDA(cudaMemcpyAsync(h_info, b + L.info, n, cudaMemcpyDeviceToHost, s));
+    WAB_CUDA(cudaStreamSynchronize(s));
+    return WAB_OK;
+}
+
+int wab_vec_reset_host(WabVec* h, uint8_t* h_grids, uint8_t* h_food, uint8_t* h_role, uint8_t* h_status,
+                       void* stream) {
+    if (!h || !h_grids || !h_food || !h_role || !h_status) return fail(WAB_E_NULL, "null argument");
+    DeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const StageLayout L = stage_layout(h->n);
+    if (int rc = ensure_stage(h, L.total)) return rc;
+    uint8_t* b = h->stage;
+    const size_t n = (size_t)h->n;
+    WabObs obs{b + L.grids, b + L.food, b + L.role, b + L.status};
+    if (int rc = wab_vec_reset(h, nullptr, obs, stream)) return rc;
+    WAB_CUDA(cudaMemcpyAsync(h_grids, b + L.grids, n * OBS_BYTES, cudaMemcpyDeviceToHost, s));
+    WAB_CUDA(cudaMemcpyAsync(h_food, b + L.food, n, cudaMemcpyDeviceToHost, s));
+    WAB_CUDA(cudaMemcpyAsync(h_role, b + L.role, n, cudaMemcpyDeviceToHost, s));
+    WAB_CUDA(cudaMemcpyAsync(h_status, b + L.status, n, cudaMemcpyDeviceToHost, s));
+    WAB_CUDA(cudaStreamSynchronize(s));
+    return WAB_OK;
+}
+
+int wab_vec_stats(WabVec* h, int64_t* h_out8, int32_t clear, void* stream) {
+    if (!h || !h_out8) return fail(WAB_E_NULL, "null argument");
+    DeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    WAB_CUDA(cudaMemcpyAsync(h_out8, h->st.stats, 64, cudaMemcpyDeviceToHost, s));
+    if (clear) WAB_CUDA(cudaMemsetAsync(h->st.stats, 0, 64, s));
+    WAB_CUDA(cudaStreamSynchronize(s));
+    return WAB_OK;
+}
+
+int wab_vec_stats_device(WabVec* h, int64_t* d_out8, void* stream) {
+    if (!h || !d_out8) return fail(WAB_E_NULL, "null argument");
+    DeviceGuard guard(h->device);
+    WAB_CUDA(cudaMemcpyAsync(d_out8, h->st.stats, 64, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return WAB_OK;
+}
+
+int wab_vec_export_state(WabVec* h, int32_t* x, int32_t* y, double* food, int32_t* role, int32_t* status,
+                         int32_t* turn, int64_t* episode, int32_t* n_wolves, int32_t* wolves_xy,
+                         uint32_t* bush_mask, int32_t* n_log, int32_t* log_xyc, void* stream) {
+    if (!h) return fail(WAB_E_NULL, "null argument");
+    DeviceGuard guard(h->device);
+    WAB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    const size_t n = (size_t)h->n;
+    const int wc = h->cfg.wolf_cap, lc = h->cfg.log_cap;
+    uint32_t* pos = new uint32_t[n]; uint32_t* misc = new uint32_t[n]; uint32_t* ep = new uint32_t[n];
+    uint32_t* bush = new uint32_t[4 * n]; uint8_t* nl = new uint8_t[n]; double* fd = new double[n];
+    uint32_t* wv = new uint32_t[n * wc]; uint32_t* lcell = new uint32_t[n * lc]; uint8_t* lcnt = new uint8_t[n * lc];
+    cudaError_t e = cudaMemcpy(pos, h->st.pos, 4 * n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(misc, h->st.misc, 4 * n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(ep, h->st.episode, 4 * n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(bush, h->st.bush, 16 * n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(nl, h->st.nlog, n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(fd, h->st.food, 8 * n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(wv, h->st.wolves, 4 * n * wc, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(lcell, h->st.logcell, 4 * n * lc, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(lcnt, h->st.logcnt, n * lc, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) {
+        for (size_t i = 0; i < n; ++i) {
+            const uint32_t m = misc[i];
+            const int nw = (int)((m >> 11) & 15u);
+            if (x) x[i] = unpack_x(pos[i]);
+            if (y) y[i] = unpack_y(pos[i]);
+            if (food) food[i] = h->cfg.food_mode == WAB_FOOD_F64 ? fd[i] : (double)(m & 0xFFu) / h->cfg.food_obs_scale;
+            if (role) role[i] = (int32_t)((m >> 8) & 1u);
+            if (status) status[i] = (int32_t)((m >> 9) & 3u);
+            if (turn) turn[i] = (int32_t)(m >> 16);
+            if (episode) episode[i] = (int64_t)(int32_t)ep[i];
+            if (n_wolves) n_wolves[i] = nw;
+            if (wolves_xy)
+                for (int k = 0; k < wc; ++k) {
+                    const uint32_t p = wv[(size_t)k * n + i];
+                    wolves_xy[(i * wc + k) * 2] = k < nw ? unpack_x(p) : 0;
+                    wolves_xy[(i * wc + k) * 2 + 1] = k < nw ? unpack_y(p) : 0;
+                }
+            if (bush_mask) for (int w = 0; w < 4; ++w) bush_mask[4 * i + w] = bush[4 * i + w];
+            if (n_log) n_log[i] = nl[i];
+            if (log_xyc)
+                for (int k = 0; k < lc; ++k) {
+                    const uint32_t c = lcell[(size_t)k * n + i];
+                    const bool live = k < (int)nl[i];
+                    log_xyc[(i * lc + k) * 3] = live ? unpack_x(c) : 0;
+                    log_xyc[(i * lc + k) * 3 + 1] = live ? unpack_y(c) : 0;
+                    log_xyc[(i * lc + k) * 3 + 2] = live ? (int32_t)lcnt[(size_t)k * n + i] : 0;
+                }
+        }
+    }
+    delete[] pos; delete[] misc; delete[] ep; delete[] bush; delete[] nl; delete[] fd;
+    delete[] wv; delete[] lcell; delete[] lcnt;
+    if (e != cudaSuccess) return cuda_fail(e, "export_state");
+    return WAB_OK;
+}
+
+int wab_philox_device(const uint32_t* d_ctr, uint32_t key0, uint32_t key1, int64_t n, uint32_t* d_out, void* stream) {
+    if (!d_ctr || !d_out) return fail(WAB_E_NULL, "null argument");
+    if (n <= 0) return WAB_OK;
+    Params P;
+    memset(&P, 0, sizeof(P));
+    fill_round_keys(P, key0, key1);
+    wab_philox_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(P, d_ctr, n, d_out);
+    WAB_CUDA(cudaGetLastError());
+    return WAB_OK;
+}
+
+}  // extern "C"
