@@ -118,7 +118,8 @@ class _PdProxy(types.ModuleType):
 
 # --------------------------------------------------------------------------- keyed numpy proxy
 def _env_key(env):
-    return env._wab_seed, env._wab_env_id, env._wab_episode
+    # a bare reference env (e.g. built by the reference's own test file) is keyed as (0, 0, 0)
+    return getattr(env, "_wab_seed", 0), getattr(env, "_wab_env_id", 0), getattr(env, "_wab_episode", 0)
 
 
 class _KeyedRandom:

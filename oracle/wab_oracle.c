@@ -315,8 +315,13 @@ int wab_oracle_step(WabOracleEnv *e, int32_t action, WabOracleObs *obs, double *
 
 void wab_oracle_get_state(const WabOracleEnv *e, int32_t *x, int32_t *y, double *food, int32_t *role,
                           int32_t *status, int32_t *turn, int64_t *episode) {
-    if (x) *x = e->ox; if (y) *y = e->oy; if (food) *food = e->food; if (role) *role = e->role;
-    if (status) *status = e->status; if (turn) *turn = e->turn; if (episode) *episode = e->episode;
+    if (x) *x = e->ox;
+    if (y) *y = e->oy;
+    if (food) *food = e->food;
+    if (role) *role = e->role;
+    if (status) *status = e->status;
+    if (turn) *turn = e->turn;
+    if (episode) *episode = e->episode;
 }
 int32_t wab_oracle_num_wolves(const WabOracleEnv *e) { return e->nw; }
 void wab_oracle_get_wolves(const WabOracleEnv *e, int32_t *out) {

@@ -1,0 +1,76 @@
+"""The C-ABI shared library: builds, loads, exports every symbol include/wab_b200.h declares, and
+refuses to run without a GPU (no CPU fallback). No compute calls here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from wab_gym_b200 import _lib, build
+from wab_gym_b200.config import GameConfig
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    text = open(os.path.join(REPO, "include", "wab_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(wab_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_builds_for_sm_100a():
+    path = build.build()
+    assert os.path.exists(path)
+    assert "arch=compute_100a,code=sm_100a" in " ".join(build.NVCC_FLAGS)
+
+
+def test_every_declared_symbol_is_exported():
+    L = _lib.load()
+    names = _declared_functions()
+    assert len(names) >= 14 and set(_lib.EXPORTS) == set(names)
+    for name in names:
+        assert hasattr(L, name), name
+    assert L.wab_abi_version() == 1
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(REPO, "wab_gym_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+                assert "hostsim" not in src or f in ("wab_core.cuh", "wab_params.h"), f   # comments only
+
+
+def test_create_without_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    L = _lib.load()
+    g = GameConfig.from_options()
+    cs = g.to_struct()
+    thr = np.ascontiguousarray(g.bush_thr, dtype=np.uint32)
+    h = ctypes.c_void_p()
+    rc = L.wab_vec_create(ctypes.byref(cs), thr.ctypes.data, len(thr), 16, 0, 0, 0, ctypes.byref(h))
+    assert rc == 5 and b"no CPU fallback" in L.wab_last_error()
+    from wab_gym_b200.env import WolvesAndBushesEnv
+    with pytest.raises(_lib.WabError):
+        WolvesAndBushesEnv()
+
+
+def test_config_errors_map_to_reference_exceptions():
+    L = _lib.load()
+    g = GameConfig.from_options()
+    cs = g.to_struct()
+    cs.width = 10
+    thr = np.ascontiguousarray(g.bush_thr, dtype=np.uint32)
+    h = ctypes.c_void_p()
+    rc = L.wab_vec_create(ctypes.byref(cs), thr.ctypes.data, len(thr), 16, 0, 0, 0, ctypes.byref(h))
+    assert rc == 2 and b"odd" in L.wab_last_error()           # ValueError at wab_env.py:147-148
+    cs.width = 13
+    cs.height = 13
+    rc = L.wab_vec_create(ctypes.byref(cs), thr.ctypes.data, len(thr), 16, 0, 0, 0, ctypes.byref(h))
+    assert rc == 3                                             # valid for the reference, not implemented here
+    assert L.wab_vec_create(None, None, 0, 1, 0, 0, 0, ctypes.byref(h)) == 1

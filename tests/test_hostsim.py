@@ -1,0 +1,94 @@
+"""The kernel logic header (wab_gym_b200/csrc/wab_core.cuh) compiled for the host and compared,
+step by step, with the oracle and with the reference traces. This is what lets kernel-logic bugs be
+found without a GPU; the CUDA build of the same header is checked by tests/test_vecenv_gpu.py."""
+import numpy as np
+import pytest
+
+from oracle.wab_oracle import OracleEnv
+from tests.hostsim import HostSimEnv
+from tests.util import (OPTION_SETS, golden_names, golden_wolves, load_golden, mask_words_to_int, pick_action,
+                        window_mask_from_bushes)
+
+
+def _check(orc, sim, oo, so, tag):
+    assert np.array_equal(oo[0], so[0]), (tag, "grids", np.argwhere(oo[0] != so[0]))
+    assert oo[1:] == so[1:], (tag, oo[1:], so[1:])
+    ho, hs = orc.hidden_state(), sim.hidden_state()
+    for k in ("x", "y", "role", "status", "turn", "wolves", "episode"):
+        assert ho[k] == hs[k], (tag, k, ho[k], hs[k])
+    if sim.game.food_mode == 0:
+        assert ho["food"] == hs["food"], (tag, "food")
+    assert mask_words_to_int(hs["bush_mask"]) == window_mask_from_bushes(ho), (tag, "bush window")
+
+
+@pytest.mark.parametrize("name", sorted(OPTION_SETS))
+@pytest.mark.parametrize("auto_reset,f64", [(True, False), (True, True), (False, True)])
+def test_kernel_logic_matches_oracle(name, auto_reset, f64):
+    overrides, greedy = OPTION_SETS[name]
+    seed, env_id, n_steps = 31, 1000 + len(name), 1500
+    orc = OracleEnv(overrides, seed=seed, env_id=env_id)
+    sim = HostSimEnv(overrides, seed=seed, env_id=env_id, auto_reset=auto_reset, force_f64_food=f64)
+    rng = np.random.default_rng(len(name))
+    oo = orc.reset()
+    so, ovf = sim.reset()
+    _check(orc, sim, oo, so, "reset0")
+    done, linger = False, 0
+    for n in range(n_steps):
+        if done and not auto_reset and linger <= 0:
+            oo = orc.reset()
+            so, ovf = sim.reset()
+            _check(orc, sim, oo, so, ("reset", n))
+            done = False
+        a = pick_action(rng, oo[0], orc.n_actions, greedy)
+        oo, orr, od = orc.step(a)
+        so, sr, sd, info, ovf = sim.step(a)
+        assert ovf == 0
+        assert np.float32(orr) == np.float32(sr) and od == sd, (n, orr, sr, od, sd)
+        assert sim.game.reward_table64[((info >> 2) & 1) * 4 + (info & 3)] == orr     # exact fp64 reward via info
+        if auto_reset:
+            if od:
+                oo = orc.reset()
+        else:
+            if od and not done:
+                linger = int(rng.integers(0, 3))
+            elif done:
+                linger -= 1
+            done = od
+        _check(orc, sim, oo, so, ("step", n, a))
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_kernel_logic_reproduces_reference_trace(name):
+    meta, tr = load_golden(name)
+    sim = HostSimEnv(meta["overrides"], seed=meta["seed"], env_id=meta["env_id"], auto_reset=False, force_f64_food=True)
+    for t in range(len(tr["action"])):
+        a = int(tr["action"][t])
+        if a < 0:
+            (obs, ovf), reward, done = sim.reset(), 0.0, False
+        else:
+            obs, reward, done, info, ovf = sim.step(a)
+        hs = sim.hidden_state()
+        assert ovf == 0
+        assert np.array_equal(obs[0], tr["grids"][t]), (name, t)
+        assert obs[1:] == (tr["food"][t], tr["role"][t], tr["status"][t]), (name, t)
+        assert np.float32(reward) == np.float32(tr["reward"][t]) and done == bool(tr["done"][t]), (name, t)
+        assert (hs["x"], hs["y"], hs["turn"], hs["episode"]) == (tr["x"][t], tr["y"][t], tr["turn"][t], tr["episode"][t])
+        assert hs["food"] == tr["food_f64"][t] and hs["wolves"] == golden_wolves(tr, t), (name, t)
+
+
+def test_bad_action_is_flagged_and_treated_as_stay():
+    sim = HostSimEnv()
+    sim.reset()
+    before = sim.hidden_state()
+    _, _, _, info, _ = sim.step(7)
+    after = sim.hidden_state()
+    assert (info >> 3) & 1 == 1 and (before["x"], before["y"]) == (after["x"], after["y"])
+
+
+def test_wolf_and_log_overflow_are_reported():
+    sim = HostSimEnv({"chance_wolf_on_square": 0.5, "wolf_chance_to_despawn": 0.0, "god_mode": True}, wolf_cap=2)
+    (_, ovf) = sim.reset()
+    seen = ovf
+    for _ in range(5):
+        seen |= sim.step(4)[4]
+    assert seen == 1

@@ -1,0 +1,198 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the oracle and the
+reference traces. Bit-exact for grids, food, role, status, done, positions, wolves; reward compared
+as the f32 image of the reference's float64 sum (tolerance 0)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import wab_oracle
+from oracle.wab_oracle import OracleEnv
+from tests.util import (OPTION_SETS, golden_names, golden_wolves, load_golden, mask_words_to_int, pick_action,
+                        window_mask_from_bushes)
+
+pytestmark = pytest.mark.gpu
+
+
+def _vec(*a, **k):
+    from wab_gym_b200 import VecEnv
+    return VecEnv(*a, **k)
+
+
+def _wolves(st, i):
+    return sorted((int(a), int(b)) for a, b in st["wolves"][i][: st["n_wolves"][i]])
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_compat_env_reproduces_reference_trace(name):
+    """Single-env gym surface (no auto-reset, fp64 food) vs the REAL reference's recorded trace."""
+    from wab_gym_b200 import WolvesAndBushesEnv, default_game_options
+    meta, tr = load_golden(name)
+    opts = {**default_game_options, **meta["overrides"]}
+    env = WolvesAndBushesEnv(opts, seed=meta["seed"], env_id=meta["env_id"])
+    assert env.action_space.n == meta["n_actions"]
+    vec_state = None
+    for t in range(len(tr["action"])):
+        a = int(tr["action"][t])
+        if t == 0:
+            obs, reward, done = env._get_obs(), 0.0, False      # the reset inside the constructor
+        elif a < 0:
+            obs, reward, done = env.reset(), 0.0, False
+        else:
+            obs, reward, done, info = env.step(a)
+            assert info == {}
+        assert len(obs) == 7 and obs[0].dtype == np.float64 and obs[0].shape == (11, 11)
+        for p in range(3):
+            assert np.array_equal(obs[p], tr["grids"][t][p].astype(np.float64)), (name, t, p)
+        assert (obs[3], obs[4], obs[5]) == (tr["food"][t], tr["role"][t], tr["status"][t]), (name, t)
+        assert reward == tr["reward"][t] and done == bool(tr["done"][t]), (name, t, reward)
+    with pytest.raises(IndexError):
+        env.step(env.action_space.n)
+    env.close()
+
+
+@pytest.mark.parametrize("name", sorted(OPTION_SETS))
+@pytest.mark.parametrize("f64", [False, True])
+def test_vecenv_matches_oracle_per_env(name, f64):
+    """N = 70 (two full warps + a ragged one) lockstep envs vs 70 oracle envs, every step, hidden state too."""
+    overrides, greedy = OPTION_SETS[name]
+    n, steps, seed, base = 70, 260, 5, 1000
+    env = _vec(n, overrides, seed=seed, env_id_base=base, force_f64_food=f64, wolf_cap=15)
+    oracles = [OracleEnv(overrides, seed=seed, env_id=base + i) for i in range(n)]
+    rng = np.random.default_rng(11)
+    obs = env.reset()
+    cur = [o.reset() for o in oracles]
+
+    def compare(tag, reward=None, done=None, want_r=None, want_d=None):
+        g, f, r, s = (t.cpu().numpy() for t in obs)
+        st = env.export_state()
+        for i, o in enumerate(oracles):
+            assert np.array_equal(g[i], cur[i][0]), (tag, i, np.argwhere(g[i] != cur[i][0]))
+            assert (int(f[i]), int(r[i]), int(s[i])) == cur[i][1:], (tag, i)
+            hs = o.hidden_state()
+            assert (st["x"][i], st["y"][i], st["turn"][i], st["episode"][i]) == (hs["x"], hs["y"], hs["turn"], hs["episode"]), (tag, i)
+            assert _wolves(st, i) == hs["wolves"], (tag, i)
+            assert mask_words_to_int(st["bush_mask"][i]) == window_mask_from_bushes(hs), (tag, i)
+            if env.game.food_mode == 0:
+                assert st["food"][i] == hs["food"], (tag, i)
+        if reward is not None:
+            assert np.array_equal(reward, want_r) and np.array_equal(done, want_d), tag
+
+    compare("reset")
+    n_done = n_eat = 0
+    for t in range(steps):
+        acts = np.array([pick_action(rng, cur[i][0], env.n_actions, greedy) for i in range(n)], dtype=np.uint8)
+        obs, reward, done, info = env.step(torch.from_numpy(acts).cuda())
+        want_r, want_d = np.zeros(n, np.float32), np.zeros(n, bool)
+        for i, o in enumerate(oracles):
+            c, r, d = o.step(int(acts[i]))
+            want_r[i], want_d[i] = np.float32(r), d
+            cur[i] = o.reset() if d else c
+        compare(("step", t), reward.cpu().numpy(), done.cpu().numpy(), want_r, want_d)
+        n_done += int(want_d.sum())
+        n_eat += int(((info["info"].cpu().numpy() >> 2) & 1).sum())
+    s = env.stats()
+    assert s["steps"] == n * steps and s["episodes"] == n_done and s["eats"] == n_eat
+    assert s["finished"] + s["starved"] + s["killed"] == n_done and s["bad_actions"] == 0 and s["overflows"] == 0
+    env.close()
+
+
+def test_step_many_equals_repeated_step_and_sharding_is_invisible():
+    n, steps = 4096, 64
+    acts = torch.randint(0, 5, (steps, n), dtype=torch.uint8, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
+    a = _vec(n, seed=3)
+    a.reset()
+    outs = []
+    for t in range(steps):
+        o, r, d, i = a.step(acts[t])
+        outs.append((o.grids.clone(), o.food.clone(), o.role.clone(), o.status.clone(), r.clone(), d.clone(), i["info"].clone()))
+    b = _vec(n, seed=3)
+    b.reset()
+    o, r, d, i = b.step_many(acts)
+    for t in range(steps):
+        got = (o.grids[t], o.food[t], o.role[t], o.status[t], r[t], d[t], i["info"][t])
+        for x, y in zip(outs[t], got):
+            assert torch.equal(x, y), t
+    sa, sb = a.export_state(), b.export_state()
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k]), k
+    # two shards with global ids = one batch
+    lo, hi = _vec(1024, seed=3, env_id_base=0), _vec(n - 1024, seed=3, env_id_base=1024)
+    lo.reset(), hi.reset()
+    ol, rl, dl, _ = lo.step_many(acts[:, :1024].contiguous())
+    oh, rh, dh, _ = hi.step_many(acts[:, 1024:].contiguous())
+    assert torch.equal(torch.cat([ol.grids, oh.grids], 1), o.grids) and torch.equal(torch.cat([rl, rh], 1), r)
+    assert torch.equal(torch.cat([dl, dh], 1), d)
+    assert a.stats() == b.stats()
+    for e in (a, b, lo, hi):
+        e.close()
+
+
+def test_full_size_checksum_against_oracle():
+    """BASELINE config 2 (4096 default envs): position-weighted checksum of every observation of
+    every step equals the CPU oracle's (a checksum of checksums over 4096 x 400 env-steps)."""
+    n, steps, seed = 4096, 400, 0
+    acts = torch.randint(0, 5, (steps, n), dtype=torch.uint8, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
+    env = _vec(n, seed=seed)
+    env.reset()
+    o, r, d, _ = env.step_many(acts)
+    w = torch.arange(1, 364, device="cuda", dtype=torch.int64)
+    cs = (o.grids.view(steps, n, 363).long() * w).sum() + 1000 * o.food.long().sum() + 100000 * o.role.long().sum() \
+        + 200000 * o.status.long().sum() + 400000 * d.long().sum()
+    n_steps, want = wab_oracle.run(None, seed, n, steps, acts.cpu().numpy())
+    assert n_steps == n * steps and int(cs.item()) == want
+    # size-independent invariants
+    assert int(o.grids[:, :, 2, 5, 5].min()) == 1 and int(o.grids[:, :, 2].sum()) == n * steps
+    assert int(o.status.max()) == 0                      # auto-reset: returned obs is always a live ostrich
+    st = env.stats()
+    assert st["episodes"] == int(d.sum()) and st["steps"] == n * steps
+    env.close()
+
+
+def test_host_buffer_path_and_masked_reset():
+    n = 300
+    a, b = _vec(n, seed=9), _vec(n, seed=9)
+    hb = a.alloc_host_buffers(pinned=True)
+    a.reset_host(hb)
+    ob = b.reset()
+    assert np.array_equal(hb["grids"].numpy(), ob.grids.cpu().numpy())
+    rng = np.random.default_rng(2)
+    for t in range(40):
+        acts = rng.integers(0, 5, n).astype(np.uint8)
+        hb["actions"].copy_(torch.from_numpy(acts))
+        a.step_host(hb)
+        o, r, d, i = b.step(torch.from_numpy(acts).cuda())
+        assert np.array_equal(hb["grids"].numpy(), o.grids.cpu().numpy()) and np.array_equal(hb["reward"].numpy(), r.cpu().numpy())
+        assert np.array_equal(hb["done"].numpy().astype(bool), d.cpu().numpy()) and np.array_equal(hb["food"].numpy(), o.food.cpu().numpy())
+    # masked reset: only the selected envs start a new episode
+    before = b.export_state()
+    mask = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    mask[::3] = 1
+    b.reset(mask)
+    after = b.export_state()
+    sel = mask.cpu().numpy().astype(bool)
+    assert np.array_equal(after["episode"][sel], before["episode"][sel] + 1) and np.all(after["turn"][sel] == 0)
+    assert np.array_equal(after["episode"][~sel], before["episode"][~sel]) and np.array_equal(after["x"][~sel], before["x"][~sel])
+    a.close(), b.close()
+
+
+def test_bad_actions_are_counted_not_dropped():
+    env = _vec(64, seed=1)
+    env.reset()
+    acts = torch.full((64,), 9, dtype=torch.uint8, device="cuda")
+    _, _, _, info = env.step(acts)
+    assert int(((info["info"] >> 3) & 1).sum()) == 64 and env.stats()["bad_actions"] == 64
+    env.close()
+
+
+def test_unaligned_or_missing_buffers_are_rejected():
+    from wab_gym_b200 import _lib
+    env = _vec(32)
+    L = env.lib
+    obs = env._obs_struct(env._out)
+    assert L.wab_vec_step(env._h, None, obs, None, None, None, None) == 1
+    bad = _lib.WabObs(env._out["grids"].data_ptr() + 1, env._out["food"].data_ptr(), env._out["role"].data_ptr(),
+                      env._out["status"].data_ptr())
+    assert L.wab_vec_reset(env._h, None, bad, None) == 2
+    env.close()

@@ -1,0 +1,187 @@
+"""``VecEnv`` — N lockstep Wolves-and-Bushes environments on one B200, device-resident.
+
+The batched counterpart of the reference's ``WolvesAndBushesEnv`` (``/root/reference/wab_env.py:103-342``):
+``reset()`` and ``step(actions)`` keep the reference's meaning (same rules, same observation content,
+same reward and done) for every environment of the batch, with the auto-reset convention of vector
+environments: an environment that reports ``done`` is reset inside the same ``step`` and the
+observation returned for it is the first observation of its next episode.
+
+All state lives in HBM behind the C ABI (``include/wab_b200.h``); this class only owns the output
+tensors and forwards raw pointers + the current CUDA stream. There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, NamedTuple, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import GameConfig
+
+STAT_NAMES = ("episodes", "steps", "finished", "starved", "killed", "eats", "bad_actions", "overflows")
+
+
+class ObsBatch(NamedTuple):
+    """First six elements of the reference's observation tuple (wab_env.py:374-385), batched.
+
+    ``grids[:, 0]`` wolves, ``grids[:, 1]`` bushes, ``grids[:, 2]`` ostriches — u8 one-hot [N, 3, 11, 11]
+    indexed ``[5 - dx, 5 - dy]`` like the reference's float64 grids; ``food`` = turns until starvation."""
+
+    grids: torch.Tensor
+    food: torch.Tensor
+    role: torch.Tensor
+    status: torch.Tensor
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+class VecEnv:
+    def __init__(self, num_envs: int, game_options: Optional[dict] = None, device="cuda", seed: int = 0,
+                 env_id_base: int = 0, auto_reset: bool = True, wolf_cap: int = 8, log_cap: Optional[int] = None,
+                 force_f64_food: bool = False):
+        self._h = None
+        self.lib = _lib.load()  # raises if the CUDA library is unavailable — no fallback
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("VecEnv runs on CUDA devices only (got %r)" % (device,))
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.num_envs = int(num_envs)
+        self.game = game_options if isinstance(game_options, GameConfig) else GameConfig.from_options(
+            game_options, auto_reset=auto_reset, force_f64_food=force_f64_food, wolf_cap=wolf_cap, log_cap=log_cap)
+        self.game_options = self.game.options
+        self.n_actions = self.game.n_actions
+        self.seed, self.env_id_base = int(seed), int(env_id_base)
+        cs = self.game.to_struct()
+        thr = np.ascontiguousarray(self.game.bush_thr, dtype=np.uint32)
+        handle = ctypes.c_void_p()
+        _lib.check(self.lib.wab_vec_create(ctypes.byref(cs), thr.ctypes.data, len(thr), self.num_envs,
+                                           self.seed & 0xFFFFFFFFFFFFFFFF, self.env_id_base, self.device.index,
+                                           ctypes.byref(handle)))
+        self._h = handle
+        self._out = self._alloc(None)
+        self._many: Dict[int, dict] = {}
+
+    # ------------------------------------------------------------------ buffers
+    def _alloc(self, steps: Optional[int]) -> dict:
+        n, dev = self.num_envs, self.device
+        lead = (n,) if steps is None else (steps, n)
+        u8 = dict(dtype=torch.uint8, device=dev)
+        return {
+            "grids": torch.empty(lead + (3, 11, 11), **u8), "food": torch.empty(lead, **u8),
+            "role": torch.empty(lead, **u8), "status": torch.empty(lead, **u8),
+            "reward": torch.empty(lead, dtype=torch.float32, device=dev), "done": torch.empty(lead, **u8),
+            "info": torch.empty(lead, **u8),
+        }
+
+    @staticmethod
+    def _obs_struct(buf) -> _lib.WabObs:
+        return _lib.WabObs(buf["grids"].data_ptr(), buf["food"].data_ptr(), buf["role"].data_ptr(),
+                           buf["status"].data_ptr())
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _actions_u8(self, actions: torch.Tensor, shape) -> torch.Tensor:
+        if not isinstance(actions, torch.Tensor):
+            actions = torch.as_tensor(actions)
+        if tuple(actions.shape) != tuple(shape):
+            raise ValueError("actions must have shape %r, got %r" % (tuple(shape), tuple(actions.shape)))
+        if actions.device != self.device:
+            actions = actions.to(self.device, non_blocking=True)
+        if actions.dtype != torch.uint8:
+            actions = actions.to(torch.uint8)  # values >= n_actions (or negative, wrapped) are counted as bad
+        return actions.contiguous()
+
+    # ------------------------------------------------------------------ gym-like surface
+    def reset(self, mask: Optional[torch.Tensor] = None) -> ObsBatch:
+        """reset() of the reference (wab_env.py:231-248) for every env (or those with ``mask != 0``)."""
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            if mask.shape != (self.num_envs,):
+                raise ValueError("mask must have shape (num_envs,)")
+        b = self._out
+        _lib.check(self.lib.wab_vec_reset(self._h, _ptr(mask), self._obs_struct(b), self._stream()))
+        return ObsBatch(b["grids"], b["food"], b["role"], b["status"])
+
+    def step(self, actions: torch.Tensor):
+        """step(action) of the reference (wab_env.py:250-342) for every env. Returns
+        ``(ObsBatch, reward f32[N], done bool[N], info)``; tensors are reused by the next call."""
+        a = self._actions_u8(actions, (self.num_envs,))
+        b = self._out
+        _lib.check(self.lib.wab_vec_step(self._h, _ptr(a), self._obs_struct(b), _ptr(b["reward"]), _ptr(b["done"]),
+                                         _ptr(b["info"]), self._stream()))
+        return (ObsBatch(b["grids"], b["food"], b["role"], b["status"]), b["reward"], b["done"].view(torch.bool),
+                {"info": b["info"]})
+
+    def step_many(self, actions: torch.Tensor, out: Optional[dict] = None):
+        """T lockstep steps in one launch; ``actions`` u8[T, N]. Every step's observation, reward and
+        done are materialised ([T, N, ...]); state stays in registers between steps."""
+        steps = int(actions.shape[0])
+        a = self._actions_u8(actions, (steps, self.num_envs))
+        b = out if out is not None else self._many.get(steps)
+        if b is None:
+            b = self._many[steps] = self._alloc(steps)
+        _lib.check(self.lib.wab_vec_step_many(self._h, steps, _ptr(a), self._obs_struct(b), _ptr(b["reward"]),
+                                              _ptr(b["done"]), _ptr(b["info"]), self._stream()))
+        return (ObsBatch(b["grids"], b["food"], b["role"], b["status"]), b["reward"], b["done"].view(torch.bool),
+                {"info": b["info"]})
+
+    # ------------------------------------------------------------------ host-buffer entry points
+    def alloc_host_buffers(self, pinned: bool = True) -> dict:
+        n = self.num_envs
+        mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=pinned)
+        return {"actions": mk((n,), torch.uint8), "grids": mk((n, 3, 11, 11), torch.uint8), "food": mk((n,), torch.uint8),
+                "role": mk((n,), torch.uint8), "status": mk((n,), torch.uint8), "reward": mk((n,), torch.float32),
+                "done": mk((n,), torch.uint8), "info": mk((n,), torch.uint8)}
+
+    def step_host(self, hb: dict):
+        """One step with HOST buffers (``hb`` from ``alloc_host_buffers``; ``hb['actions']`` filled by the
+        caller): H2D actions, kernel, D2H of every output, stream sync — the whole C-ABI host path."""
+        _lib.check(self.lib.wab_vec_step_host(self._h, _ptr(hb["actions"]), _ptr(hb["grids"]), _ptr(hb["food"]),
+                                              _ptr(hb["role"]), _ptr(hb["status"]), _ptr(hb["reward"]),
+                                              _ptr(hb["done"]), _ptr(hb["info"]), self._stream()))
+        return hb
+
+    def reset_host(self, hb: dict):
+        _lib.check(self.lib.wab_vec_reset_host(self._h, _ptr(hb["grids"]), _ptr(hb["food"]), _ptr(hb["role"]),
+                                               _ptr(hb["status"]), self._stream()))
+        return hb
+
+    # ------------------------------------------------------------------ statistics / introspection
+    def stats(self, clear: bool = False) -> Dict[str, int]:
+        out = np.zeros(8, dtype=np.int64)
+        _lib.check(self.lib.wab_vec_stats(self._h, out.ctypes.data, int(clear), self._stream()))
+        return dict(zip(STAT_NAMES, (int(v) for v in out)))
+
+    def stats_tensor(self) -> torch.Tensor:
+        """int64[8] on the device, enqueued on the current stream (feed to an NCCL all_reduce)."""
+        t = torch.empty(8, dtype=torch.int64, device=self.device)
+        _lib.check(self.lib.wab_vec_stats_device(self._h, _ptr(t), self._stream()))
+        return t
+
+    def export_state(self) -> Dict[str, np.ndarray]:
+        n, wc, lc = self.num_envs, self.game.wolf_cap, self.game.log_cap
+        i32 = lambda *s: np.zeros(s, dtype=np.int32)
+        st = {"x": i32(n), "y": i32(n), "food": np.zeros(n, dtype=np.float64), "role": i32(n), "status": i32(n),
+              "turn": i32(n), "episode": np.zeros(n, dtype=np.int64), "n_wolves": i32(n), "wolves": i32(n, wc, 2),
+              "bush_mask": np.zeros((n, 4), dtype=np.uint32), "n_log": i32(n), "log": i32(n, lc, 3)}
+        order = ("x", "y", "food", "role", "status", "turn", "episode", "n_wolves", "wolves", "bush_mask", "n_log", "log")
+        _lib.check(self.lib.wab_vec_export_state(self._h, *(ctypes.c_void_p(st[k].ctypes.data) for k in order),
+                                                 self._stream()))
+        return st
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.wab_vec_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
