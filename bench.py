@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--fuse", type=int, default=256, help="steps per launch of the multi-step kernel")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--skip-e2e", action="store_true", help="sweeps only: skip the host-buffer leg")
+    ap.add_argument("--skip-cpu", action="store_true", help="sweeps only: skip the cpu_baseline leg")
     return ap.parse_args()
 
 
@@ -114,14 +116,15 @@ def cpu_reference_run(n_envs, steps, warmup, seed, threads=0, budget_s=None):
     from oracle import wab_oracle
     rng = np.random.default_rng(12345)
     cores = os.cpu_count() or 1
-    if budget_s is not None:  # bounded sample: size the run from a short probe
-        probe_envs = min(n_envs, 512)
-        a = rng.integers(0, 5, (32, probe_envs)).astype(np.uint8)
-        t0 = time.perf_counter()
-        wab_oracle.run(None, seed, probe_envs, 32, a, threads)
-        rate = probe_envs * 32 / max(time.perf_counter() - t0, 1e-6)
+    if budget_s is not None:  # bounded sample: size the run from two probes (threads warm on the second)
+        rate = 1.0
+        for probe_steps in (16, 128):
+            a = rng.integers(0, 5, (probe_steps, n_envs)).astype(np.uint8)
+            t0 = time.perf_counter()
+            wab_oracle.run(None, seed, n_envs, probe_steps, a, threads)
+            rate = n_envs * probe_steps / max(time.perf_counter() - t0, 1e-6)
         steps = int(max(8, min(steps, budget_s * rate / n_envs)))
-        warmup = min(warmup, 4)
+        warmup = 0
     if warmup > 0:
         wab_oracle.run(None, seed, n_envs, warmup, rng.integers(0, 5, (warmup, n_envs)).astype(np.uint8), threads)
     acts = rng.integers(0, 5, (steps, n_envs)).astype(np.uint8)
@@ -246,6 +249,8 @@ def run_ours(args):
                "mode": "1 launch per step, %d-step CUDA graph replayed %d times (actions repeat per replay)" % (G, reps)}
 
     # ---------------- end to end through the host-buffer C-ABI call (e2e) ----------------
+    if args.skip_e2e:
+        return finish(args, env, world, rank, n, K, W, T, fused_ms, kernel_ms, launches, clocks, percall, None, stats_all, dist)
     hb = env.alloc_host_buffers(pinned=True)
     host_actions = actions[:min(K, 2048)].cpu().pin_memory()
     Ke = host_actions.shape[0]
@@ -268,6 +273,10 @@ def run_ours(args):
            "d2h_bytes_per_step": d2h, "steps": Ke, "ms_per_step": e2e_ms / Ke,
            "path": "wab_vec_step_host: pinned host actions -> H2D -> wab_step_kernel -> D2H of grids/food/role/status/reward/done/info -> stream sync"}
 
+    return finish(args, env, world, rank, n, K, W, T, fused_ms, kernel_ms, launches, clocks, percall, e2e, stats_all, dist)
+
+
+def finish(args, env, world, rank, n, K, W, T, fused_ms, kernel_ms, launches, clocks, percall, e2e, stats_all, dist):
     stats = env.stats()
     env.close()
 
@@ -297,6 +306,8 @@ def run_ours(args):
             "episode_stats": stats_all or stats,
         }
         try:
+            if args.skip_cpu:
+                raise RuntimeError("skipped (--skip-cpu)")
             cb = cpu_reference_run(n, 10 ** 9, 4, args.seed, budget_s=args.cpu_seconds)
             line["cpu_baseline"] = {"value": cb["value"], "unit": "env-steps/s", "cores": cb["cores"], "kind": "port",
                                     "sample": "%d envs x %d lockstep steps, %.1f s of %d-thread CPU work" % (

@@ -147,6 +147,9 @@ int wab_vec_export_state(WabVec *h, int32_t *x, int32_t *y, double *food, int32_
                          uint32_t *bush_mask, int32_t *n_log, int32_t *log_xyc, void *stream);
 
 int64_t wab_vec_num_envs(const WabVec *h);
+/* Lanes cooperating on one env (1, 4, 8, 16 or 32), chosen at create from the batch size so that a
+ * small batch still covers every SM; results do not depend on it. */
+int wab_vec_lanes_per_env(const WabVec *h);
 void wab_vec_destroy(WabVec *h);
 
 /* Raw Philox4x32-10 on the device for n counters (cross-checks the RNG contract). d_ctr u32[n][4],

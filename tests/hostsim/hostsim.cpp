@@ -98,8 +98,9 @@ void hostsim_step(HostSim* h, int32_t action, uint8_t* grids, int32_t* food, int
                   float* reward, int32_t* done, int32_t* info, int32_t* overflow) {
     StepOut O;
     memset(&O, 0, sizeof(O));
-    if (h->f64) env_step<true>(h->P, h->E, h->S, (uint32_t)action, O);
-    else env_step<false>(h->P, h->E, h->S, (uint32_t)action, O);
+    const Coop<1> coop{0u, 1u};
+    if (h->f64) env_step<true, 1>(h->P, h->E, h->S, (uint32_t)action, O, coop);
+    else env_step<false, 1>(h->P, h->E, h->S, (uint32_t)action, O, coop);
     if (O.done && h->P.auto_reset) {
         O.overflow |= do_reset(h, O.wm, O.bm);
         O.food_obs = food_observation(h->P, h->E, h->f64);

@@ -98,6 +98,64 @@ def test_vecenv_matches_oracle_per_env(name, f64):
     env.close()
 
 
+@pytest.mark.parametrize("lpe", [1, 4, 8, 16, 32])
+@pytest.mark.parametrize("name", ["defaults", "dense", "six_actions_random_start"])
+def test_every_lanes_per_env_variant_matches_oracle(lpe, name, monkeypatch):
+    """The kernel is compiled for 1/4/8/16/32 lanes per env (picked from the batch size); force each
+    variant and compare with the oracle. N = 41 leaves a ragged last CTA / warp in every geometry."""
+    monkeypatch.setenv("WAB_LPE", str(lpe))
+    overrides, greedy = OPTION_SETS[name]
+    n, steps, seed, base = 41, 160, 77, 5000
+    env = _vec(n, overrides, seed=seed, env_id_base=base, wolf_cap=15)
+    assert env.lanes_per_env == lpe
+    oracles = [OracleEnv(overrides, seed=seed, env_id=base + i) for i in range(n)]
+    rng = np.random.default_rng(lpe)
+    obs = env.reset()
+    cur = [o.reset() for o in oracles]
+    for t in range(steps + 1):
+        g, f, r, s = (x.cpu().numpy() for x in obs)
+        st = env.export_state()
+        for i, o in enumerate(oracles):
+            assert np.array_equal(g[i], cur[i][0]) and (int(f[i]), int(r[i]), int(s[i])) == cur[i][1:], (lpe, t, i)
+            hs = o.hidden_state()
+            assert (st["x"][i], st["y"][i], st["turn"][i]) == (hs["x"], hs["y"], hs["turn"]) and _wolves(st, i) == hs["wolves"]
+            assert mask_words_to_int(st["bush_mask"][i]) == window_mask_from_bushes(hs), (lpe, t, i)
+        if t == steps:
+            break
+        acts = np.array([pick_action(rng, cur[i][0], env.n_actions, greedy) for i in range(n)], dtype=np.uint8)
+        obs, reward, done, _ = env.step(torch.from_numpy(acts).cuda())
+        reward, done = reward.cpu().numpy(), done.cpu().numpy()
+        for i, o in enumerate(oracles):
+            c, rr, d = o.step(int(acts[i]))
+            assert np.float32(rr) == reward[i] and d == bool(done[i]), (lpe, t, i)
+            cur[i] = o.reset() if d else c
+    assert env.stats()["steps"] == n * steps and env.stats()["overflows"] == 0
+    env.close()
+
+
+def test_lanes_per_env_variants_agree_on_a_full_batch(monkeypatch):
+    n, steps = 4096, 48
+    acts = torch.randint(0, 5, (steps, n), dtype=torch.uint8, device="cuda", generator=torch.Generator("cuda").manual_seed(4))
+    ref = None
+    for lpe in (1, 4, 8, 16, 32):
+        monkeypatch.setenv("WAB_LPE", str(lpe))
+        env = _vec(n, seed=12)
+        env.reset()
+        o, r, d, i = env.step_many(acts)
+        got = [x.clone() for x in (o.grids, o.food, o.role, o.status, r, d, i["info"])] + [env.stats()]
+        if ref is None:
+            ref = got
+        else:
+            for x, y in zip(ref[:-1], got[:-1]):
+                assert torch.equal(x, y), lpe
+            assert ref[-1] == got[-1]
+        env.close()
+    monkeypatch.delenv("WAB_LPE")
+    auto = _vec(n, seed=12)
+    assert auto.lanes_per_env in (8, 16, 32)        # a 4096-env batch is spread over several lanes per env
+    auto.close()
+
+
 def test_step_many_equals_repeated_step_and_sharding_is_invisible():
     n, steps = 4096, 64
     acts = torch.randint(0, 5, (steps, n), dtype=torch.uint8, device="cuda", generator=torch.Generator("cuda").manual_seed(1))

@@ -13,7 +13,7 @@ _lib = None
 
 EXPORTS = [
     "wab_vec_create", "wab_vec_reset", "wab_vec_step", "wab_vec_step_many", "wab_vec_step_host",
-    "wab_vec_reset_host", "wab_vec_stats", "wab_vec_stats_device", "wab_vec_export_state", "wab_vec_num_envs",
+    "wab_vec_reset_host", "wab_vec_stats", "wab_vec_stats_device", "wab_vec_export_state", "wab_vec_num_envs", "wab_vec_lanes_per_env",
     "wab_vec_destroy", "wab_philox_device", "wab_last_error", "wab_abi_version",
 ]
 
@@ -34,8 +34,8 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
-    if _build.is_stale():
+    path = os.environ.get("WAB_LIB") or _build.LIB_PATH   # WAB_LIB: a differently-tuned build (tools/tune.py)
+    if path == _build.LIB_PATH and _build.is_stale():
         try:
             _build.build()
         except Exception as exc:  # no nvcc on this box: only acceptable if a prebuilt library travelled here
@@ -54,13 +54,15 @@ def load():
     L.wab_vec_export_state.argtypes = [vp] * 14
     L.wab_vec_num_envs.argtypes = [vp]
     L.wab_vec_num_envs.restype = i64
+    L.wab_vec_lanes_per_env.argtypes = [vp]
+    L.wab_vec_lanes_per_env.restype = i32
     L.wab_vec_destroy.argtypes = [vp]
     L.wab_vec_destroy.restype = None
     L.wab_philox_device.argtypes = [vp, ctypes.c_uint32, ctypes.c_uint32, i64, vp, vp]
     L.wab_last_error.restype = ctypes.c_char_p
     L.wab_abi_version.restype = i32
     for name in EXPORTS:
-        if name not in ("wab_vec_num_envs", "wab_vec_destroy", "wab_last_error", "wab_abi_version"):
+        if name not in ("wab_vec_num_envs", "wab_vec_lanes_per_env", "wab_vec_destroy", "wab_last_error", "wab_abi_version"):
             getattr(L, name).restype = ctypes.c_int
     _lib = L
     return L

@@ -23,12 +23,20 @@
 #define WAB_HD static inline
 #endif
 
+#ifndef WAB_SLIDE_UNROLL
+#define WAB_SLIDE_UNROLL 2
+#endif
+#ifndef WAB_SPAWN_UNROLL
+#define WAB_SPAWN_UNROLL 2
+#endif
+
 namespace wab {
 
 constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
 constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
 enum : uint32_t { SITE_BUSH = 1, SITE_INIT = 2, SITE_SPAWN = 3, SITE_DESP = 4, SITE_START = 5 };
 
+constexpr int kSlideUnroll = WAB_SLIDE_UNROLL, kSpawnUnroll = WAB_SPAWN_UNROLL;
 constexpr int VIEW = 11, HALF = 5, CELLS = 121, RING = 48;
 constexpr int OBS_BYTES = 3 * CELLS;        // 363 bytes per env: wolves, bushes, ostriches
 constexpr uint32_t TOP_WORD_MASK = 0x01FFFFFFu;  // 121 = 3*32 + 25
@@ -70,6 +78,7 @@ struct Params {
 struct Env {
     int32_t x, y;
     uint32_t turn, role, status, nw, nlog, episode, env_id;
+    uint32_t dep;    // 1 once some logged cell has been eaten empty (re-entering cells must consult the log)
     uint32_t m[4];   // bush occupancy of the window (food > 0), current
     int32_t food_i;  // INT mode
     double food_f;   // F64 mode
@@ -88,6 +97,22 @@ struct StepOut {
     float reward;
     uint32_t ate, bad_action, overflow, outcome;
 };
+
+// Lanes-per-env cooperation. With LPE > 1 the LPE consecutive lanes of a group hold the SAME env in
+// their registers (scalar rules are executed redundantly, which costs nothing when the batch is too
+// small to fill the machine) and split the independent Philox calls of a step between them.
+template <int LPE> struct Coop { uint32_t sub; uint32_t gmask; };   // sub = lane % LPE, gmask = lanes of the group
+
+template <int LPE>
+WAB_HD uint32_t group_or(const Coop<LPE>& c, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    if (LPE == 1) return v;
+    return __reduce_or_sync(c.gmask, v);
+#else
+    (void)c;
+    return v;
+#endif
+}
 
 WAB_HD uint32_t pack_xy(int32_t x, int32_t y) { return ((uint32_t)x & 0xFFFFu) | ((uint32_t)y << 16); }
 WAB_HD int32_t unpack_x(uint32_t p) { return (int32_t)(int16_t)(p & 0xFFFFu); }
@@ -165,12 +190,22 @@ WAB_HD int32_t log_find(const Env& E, const Slots& S, uint32_t cell) {
         if (S.logcell[(int64_t)l * S.lstride] == cell) return (int32_t)l;
     return -1;
 }
+// A bush whose first-reveal draw is `word` still has food after `eats` eats  <=>  its value
+// #{k : thr[k] <= word} exceeds eats  <=>  word >= thr[eats]   (thr ascending; one table load).
+WAB_HD uint32_t alive_after(const Params& P, uint32_t word, uint32_t eats) {
+    if (eats >= P.n_bush_thr) return 0u;
+#if defined(__CUDA_ARCH__)
+    return word >= __ldg(P.bush_thr + eats) ? 1u : 0u;
+#else
+    return word >= P.bush_thr[eats] ? 1u : 0u;
+#endif
+}
 // bush at (x, y) still has food, given its first-reveal draw `word` (only called when word >= thr_bush1)
 WAB_HD uint32_t bush_alive(const Params& P, const Env& E, const Slots& S, int32_t x, int32_t y, uint32_t word) {
-    if (E.nlog == 0) return 1u;
+    if (!E.dep) return 1u;                      // nothing has been eaten empty this episode
     int32_t l = log_find(E, S, pack_xy(x, y));
     if (l < 0) return 1u;
-    return (int32_t)S.logcnt[(int64_t)l * S.lstride] < bush_value(P, word) ? 1u : 0u;
+    return alive_after(P, word, (uint32_t)S.logcnt[(int64_t)l * S.lstride]);
 }
 
 // 11-bit value with bit g at stride 11 (positions 11*g), as four words.
@@ -184,7 +219,8 @@ WAB_HD void spread11(uint32_t v, uint32_t t[4]) {
 // Slide the window after the ostrich moved by (dx, dy) (one of them non-zero) to (E.x, E.y) and
 // reveal the 11 new cells: generate_bushes, wab_env.py:613-629, for cells without a record; cells
 // seen before get the same draw (keys do not depend on the turn) minus what was eaten.
-WAB_HD void slide_window(const Params& P, Env& E, const Slots& S, int32_t dx, int32_t dy) {
+template <int LPE>
+WAB_HD void slide_window(const Params& P, Env& E, const Slots& S, int32_t dx, int32_t dy, const Coop<LPE>& coop) {
     // drop the column that would wrap into the neighbouring row, then shift by 11*dx + dy
     if (dy > 0) {
         E.m[0] &= ~ColMask<10, 0>::v; E.m[1] &= ~ColMask<10, 1>::v; E.m[2] &= ~ColMask<10, 2>::v; E.m[3] &= ~ColMask<10, 3>::v;
@@ -204,9 +240,9 @@ WAB_HD void slide_window(const Params& P, Env& E, const Slots& S, int32_t dx, in
     const uint32_t fb = (uint32_t)fixed & 1u;
     uint32_t line = 0;
 #if defined(__CUDA_ARCH__)
-#pragma unroll 3
+#pragma unroll kSlideUnroll
 #endif
-    for (int b = 0; b < 6; ++b) {
+    for (int b = (int)coop.sub; b < 6; b += LPE) {
         const int32_t vb = vb0 + b;
         uint32_t w[4];
         const uint32_t payload = along_y ? pack_xy(fixed >> 1, vb) : pack_xy(vb, fixed >> 1);
@@ -219,11 +255,12 @@ WAB_HD void slide_window(const Params& P, Env& E, const Slots& S, int32_t dx, in
             const int32_t g = vmax - v;
             const uint32_t word = e ? we1 : we0;
             uint32_t on = (g >= 0 && g <= 10 && word >= P.thr_bush1 && P.n_bush_thr > 0) ? 1u : 0u;
-            if (on && E.nlog)
+            if (on && E.dep)
                 on = along_y ? bush_alive(P, E, S, fixed, v, word) : bush_alive(P, E, S, v, fixed, word);
             line |= on << (g & 15);
         }
     }
+    line = group_or(coop, line);
     if (along_y) {                                // row i = 0 (dx > 0) or i = 10 (dx < 0): bits 11*i + g
         E.m[0] |= (dx > 0) ? line : 0u;
         E.m[3] |= (dx < 0) ? (line << 14) : 0u;   // 110 = 96 + 14
@@ -266,8 +303,8 @@ WAB_HD void wolf_plane(const Env& E, const Slots& S, uint32_t wm[4]) {
 
 // One step of one environment: wab_env.py:250-342 up to (not including) auto-reset and the
 // observation stores. `F64` selects the reference's fp64 food arithmetic.
-template <bool F64>
-WAB_HD void env_step(const Params& P, Env& E, const Slots& S, uint32_t action, StepOut& O) {
+template <bool F64, int LPE>
+WAB_HD void env_step(const Params& P, Env& E, const Slots& S, uint32_t action, StepOut& O, const Coop<LPE>& coop) {
     // ---- :251-258 action
     O.bad_action = (action >= (uint32_t)P.n_actions) ? 1u : 0u;
     const uint32_t code = O.bad_action ? 0x05u /* dx=0, dy=0, keep */ : (uint32_t)(P.act_tbl >> (8 * action)) & 0xFFu;
@@ -279,7 +316,7 @@ WAB_HD void env_step(const Params& P, Env& E, const Slots& S, uint32_t action, S
     O.overflow = 0;
 
     // ---- :259 generate_bushes for the newly visible line
-    if (dx != 0 || dy != 0) slide_window(P, E, S, dx, dy);
+    if (dx != 0 || dy != 0) slide_window<LPE>(P, E, S, dx, dy, coop);
 
     // ---- :262-264 despawn (keep iff U > chance). rank = ordinal among earlier wolves on the cell.
     if (E.nw) {
@@ -338,21 +375,20 @@ WAB_HD void env_step(const Params& P, Env& E, const Slots& S, uint32_t action, S
         }
         // bush.food -= 1 (:312): count the eat; the cell disappears when eats == its first-reveal value
         const uint32_t cell = pack_xy(E.x, E.y);
-        const int32_t food0 = bush_value(P, bush_word(P, E, E.x, E.y));
         int32_t l = log_find(E, S, cell);
-        int32_t eats;
+        uint32_t eats;
         if (l >= 0) {
-            eats = (int32_t)S.logcnt[(int64_t)l * S.lstride] + 1;
+            eats = (uint32_t)S.logcnt[(int64_t)l * S.lstride] + 1u;
             S.logcnt[(int64_t)l * S.lstride] = (uint8_t)eats;
         } else if (E.nlog < (uint32_t)P.log_cap) {
-            eats = 1;
+            eats = 1u;
             S.logcell[(int64_t)E.nlog * S.lstride] = cell;
             S.logcnt[(int64_t)E.nlog * S.lstride] = 1;
             E.nlog += 1;
         } else {
-            eats = 1; O.overflow = 1u;             // counted, never silent (WAB_STAT_OVERFLOWS)
+            eats = 1u; O.overflow = 1u;            // counted, never silent (WAB_STAT_OVERFLOWS)
         }
-        if (eats >= food0) E.m[1] &= ~(1u << 28);
+        if (!alive_after(P, bush_word(P, E, E.x, E.y), eats)) { E.m[1] &= ~(1u << 28); E.dep = 1u; }
     }
 
     // ---- :316-322 hunger, starvation (overrides killed)
@@ -368,15 +404,16 @@ WAB_HD void env_step(const Params& P, Env& E, const Slots& S, uint32_t action, S
     if (P.wolves) {
         uint32_t hitgroups = 0;
 #if defined(__CUDA_ARCH__)
-#pragma unroll 4
+#pragma unroll kSpawnUnroll
 #endif
-        for (int grp = 0; grp < RING / 4; ++grp) {
+        for (int grp = (int)coop.sub; grp < RING / 4; grp += LPE) {
             uint32_t w[4];
             philox(P, E.env_id, E.episode, ctr2(SITE_SPAWN, E.turn, 0), (uint32_t)grp, w);
             uint32_t a = w[0] < w[1] ? w[0] : w[1], b = w[2] < w[3] ? w[2] : w[3];
             a = a < b ? a : b;
             hitgroups |= (a < P.thr_spawn ? 1u : 0u) << grp;
         }
+        hitgroups = group_or(coop, hitgroups);
         while (hitgroups) {                        // rare: recompute the groups that hit
 #if defined(__CUDA_ARCH__)
             const int grp = __ffs((int)hitgroups) - 1;
@@ -445,7 +482,7 @@ WAB_HD uint32_t reset_init_group(const Params& P, uint32_t env_id, uint32_t epis
 template <bool F64>
 WAB_HD void reset_scalars(const Params& P, Env& E) {
     E.episode += 1;                 // first reset -> episode 0 (state is created with 0xFFFFFFFF)
-    E.turn = 0; E.x = 0; E.y = 0; E.status = 0; E.nw = 0; E.nlog = 0;
+    E.turn = 0; E.x = 0; E.y = 0; E.status = 0; E.nw = 0; E.nlog = 0; E.dep = 0;
     E.role = (uint32_t)(P.starting_role < 0 ? 0 : P.starting_role);
     E.food_i = P.food_int_start;
     E.food_f = P.food_start;

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -29,6 +30,9 @@ namespace {
 
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr int STREAM_WORDS = 364;   // 32 envs * 363 bits = 363 words (+1 pad keeps rows 8-byte aligned)
+#ifndef WAB_MIN_BLOCKS_LPE1
+#define WAB_MIN_BLOCKS_LPE1 6         // thread-per-env kernel: cap registers at 80 so 6 CTAs (24 warps) fit an SM
+#endif
 
 struct StatePtrs {
     uint32_t* pos;       // [N]  x:i16 | y:i16 << 16
@@ -51,42 +55,47 @@ struct OutPtrs {
 
 template <bool F64>
 __device__ __forceinline__ void load_env(const Params& P, const StatePtrs& st, int64_t idx, Env& E,
-                                         uint32_t* wolves_s, int bs) {
+                                         uint32_t* wolves_s, int wstride) {
     const uint32_t pos = st.pos[idx], misc = st.misc[idx];
     E.x = unpack_x(pos); E.y = unpack_y(pos);
     E.food_i = (int32_t)(misc & 0xFFu);
-    E.role = (misc >> 8) & 1u; E.status = (misc >> 9) & 3u; E.nw = (misc >> 11) & 15u; E.turn = misc >> 16;
+    E.role = (misc >> 8) & 1u; E.status = (misc >> 9) & 3u; E.nw = (misc >> 11) & 15u; E.dep = (misc >> 15) & 1u;
+    E.turn = misc >> 16;
     E.episode = st.episode[idx];
     const uint4 b = st.bush[idx];
     E.m[0] = b.x; E.m[1] = b.y; E.m[2] = b.z; E.m[3] = b.w;
     E.nlog = st.nlog[idx];
     E.food_f = F64 ? st.food[idx] : 0.0;
     E.env_id = (uint32_t)(P.env_id_base + (uint64_t)idx);
-    for (uint32_t k = 0; k < E.nw; ++k) wolves_s[k * bs] = st.wolves[(int64_t)k * st.n + idx];
+    for (uint32_t k = 0; k < E.nw; ++k) wolves_s[k * wstride] = st.wolves[(int64_t)k * st.n + idx];
 }
 
 template <bool F64>
 __device__ __forceinline__ void store_env(const StatePtrs& st, int64_t idx, const Env& E,
-                                          const uint32_t* wolves_s, int bs) {
+                                          const uint32_t* wolves_s, int wstride) {
     st.pos[idx] = pack_xy(E.x, E.y);
-    st.misc[idx] = ((uint32_t)E.food_i & 0xFFu) | (E.role << 8) | (E.status << 9) | (E.nw << 11) | (E.turn << 16);
+    st.misc[idx] = ((uint32_t)E.food_i & 0xFFu) | (E.role << 8) | (E.status << 9) | (E.nw << 11) | (E.dep << 15) |
+                   (E.turn << 16);
     st.episode[idx] = E.episode;
     st.bush[idx] = make_uint4(E.m[0], E.m[1], E.m[2], E.m[3]);
     st.nlog[idx] = (uint8_t)E.nlog;
     if (F64) st.food[idx] = E.food_f;
-    for (uint32_t k = 0; k < E.nw; ++k) st.wolves[(int64_t)k * st.n + idx] = wolves_s[k * bs];
+    for (uint32_t k = 0; k < E.nw; ++k) st.wolves[(int64_t)k * st.n + idx] = wolves_s[k * wstride];
 }
 
-// Reset every env of the warp whose `need` is set (wab_env.py:231-248). All 32 lanes must call.
-// On return lanes with `need` hold the fresh state and their observation planes.
-template <bool F64>
+// Reset every env of the warp whose `need` is set (wab_env.py:231-248). All 32 lanes must call; the
+// 36 bush-block and 31 wolf-init Philox calls of ONE reset are spread over the 32 lanes whatever
+// LPE is. `need` is replicated over the LPE lanes of a group. On return the lanes of a reset env
+// hold the fresh state and its observation planes.
+template <bool F64, int LPE>
 __device__ __forceinline__ void warp_reset(const Params& P, Env& E, const Slots& S, bool need, int lane,
                                            uint32_t wm[4], uint32_t bm[4], uint32_t& overflow) {
     unsigned todo = __ballot_sync(FULL, need);
     if (need) reset_scalars<F64>(P, E);
     while (todo) {
-        const int r = __ffs((int)todo) - 1;
-        todo &= todo - 1u;
+        const int r = __ffs((int)todo) - 1;                       // first lane of the group to reset
+        todo &= (LPE == 32) ? 0u : ~(((1u << (LPE & 31)) - 1u) << r);
+        const bool mine = (lane / LPE) == (r / LPE);
         const uint32_t eid = __shfl_sync(FULL, E.env_id, r);
         const uint32_t ep = __shfl_sync(FULL, E.episode, r);
         uint32_t part[4] = {0u, 0u, 0u, 0u};
@@ -98,12 +107,12 @@ __device__ __forceinline__ void warp_reset(const Params& P, Env& E, const Slots&
         const uint32_t m3 = __reduce_or_sync(FULL, part[3]);
         const uint32_t hits = (P.wolves && lane < 31) ? reset_init_group(P, eid, ep, lane) : 0u;
         unsigned hl = __ballot_sync(FULL, hits != 0u);
-        if (lane == r) { E.m[0] = m0; E.m[1] = m1; E.m[2] = m2; E.m[3] = m3; }
+        if (mine) { E.m[0] = m0; E.m[1] = m1; E.m[2] = m2; E.m[3] = m3; }
         while (hl) {                                              // rare: p = 0.0005 per cell
             const int src = __ffs((int)hl) - 1;
             hl &= hl - 1u;
             const uint32_t h = __shfl_sync(FULL, hits, src);
-            if (lane == r) {
+            if (mine) {
                 for (int l = 0; l < 4; ++l)
                     if ((h >> l) & 1u) {
                         const int c = 4 * src + l;
@@ -125,11 +134,11 @@ __device__ __forceinline__ void warp_reset(const Params& P, Env& E, const Slots&
 
 __device__ __forceinline__ uint32_t nibble_to_bytes(uint32_t n) { return (n * 0x00204081u) & 0x01010101u; }
 
-// Write the warp's observations: 32 envs x 363 bytes, contiguous from `gbase` (16-byte aligned).
-// `stream` is this warp's STREAM_WORDS shared-memory words. n_valid = envs of this warp that exist.
-__device__ __forceinline__ void emit_obs(const Params& P, uint32_t* stream, const uint32_t wm[4],
-                                         const uint32_t bm[4], uint32_t role, bool active, int lane,
-                                         uint8_t* gbase, int n_valid) {
+// Put one env's 363-bit observation string into a shared bit stream at bit offset 363 * slot.
+// The env's last 60 bits are always zero, so the word it shares with slot + 1 is written by slot + 1
+// alone: plain stores, no atomics.
+__device__ __forceinline__ void stream_put(const Params& P, uint32_t* stream, int slot, const uint32_t wm[4],
+                                           const uint32_t bm[4], uint32_t role, bool active) {
     uint32_t B[11];
     if (active) {
         compose_obs(P, wm, bm, role, B);
@@ -137,21 +146,22 @@ __device__ __forceinline__ void emit_obs(const Params& P, uint32_t* stream, cons
 #pragma unroll
         for (int k = 0; k < 11; ++k) B[k] = 0u;
     }
-    // env `lane` owns bits [363*lane, 363*lane + 363); its last 60 bits are always zero, so the word
-    // it shares with lane+1 is written by lane+1 alone: plain stores, no atomics.
-    const uint32_t sh = (11u * (uint32_t)lane) & 31u;            // 363 mod 32 = 11
-    const int fw = (OBS_BYTES * lane) >> 5;
-    const int nown = ((OBS_BYTES * (lane + 1)) >> 5) - fw;       // 11 or 12
+    const uint32_t sh = (11u * (uint32_t)slot) & 31u;            // 363 mod 32 = 11
+    const int fw = (OBS_BYTES * slot) >> 5;
+    const int nown = ((OBS_BYTES * (slot + 1)) >> 5) - fw;       // 11 or 12
     stream[fw] = B[0] << sh;
 #pragma unroll
     for (int k = 1; k < 11; ++k) stream[fw + k] = fshl(B[k - 1], B[k], sh);
     if (nown == 12) stream[fw + 11] = fshl(B[10], 0u, sh);
-    __syncwarp();
+}
+
+// Expand a bit stream (bit b = byte b of the output) into `nbytes` bytes at gbase (16-byte aligned)
+// with `nthreads` cooperating threads: 16 bits -> one 16-byte streaming store per thread-iteration.
+__device__ __forceinline__ void stream_flush(const uint32_t* stream, uint8_t* gbase, int nbytes, int tid, int nthreads) {
     const uint16_t* hs = reinterpret_cast<const uint16_t*>(stream);
-    const int nbytes = OBS_BYTES * n_valid;
     const int nfull = nbytes >> 4;
-#pragma unroll 4
-    for (int c = lane; c < nfull; c += 32) {
+#pragma unroll 2
+    for (int c = tid; c < nfull; c += nthreads) {
         const uint32_t h = hs[c];
         uint4 v;
         v.x = nibble_to_bytes(h & 15u);
@@ -160,9 +170,8 @@ __device__ __forceinline__ void emit_obs(const Params& P, uint32_t* stream, cons
         v.w = nibble_to_bytes(h >> 12);
         __stcs(reinterpret_cast<uint4*>(gbase) + c, v);
     }
-    const int b = (nfull << 4) + lane;                            // ragged tail of a partial warp
-    if (lane < 16 && b < nbytes) gbase[b] = (uint8_t)((stream[b >> 5] >> (b & 31)) & 1u);
-    __syncwarp();
+    const int b = (nfull << 4) + tid;                             // ragged tail of a partial batch
+    if (tid < 16 && b < nbytes) gbase[b] = (uint8_t)((stream[b >> 5] >> (b & 31)) & 1u);
 }
 
 __device__ __forceinline__ void write_scalars(const OutPtrs& out, int64_t o, const StepOut& O) {
@@ -187,101 +196,158 @@ __device__ __forceinline__ void flush_stats(unsigned long long* stats, const uin
     if (threadIdx.x < 8 && block_s[threadIdx.x]) atomicAdd(&stats[threadIdx.x], (unsigned long long)block_s[threadIdx.x]);
 }
 
+// Geometry of one CTA for a lanes-per-env factor LPE.
+//   LPE == 1 : thread per env; each WARP owns a 32-env bit stream and flushes it alone (__syncwarp only).
+//   LPE  > 1 : LPE lanes per env; the CTA owns one double-buffered stream for its EPB envs (EPB % 16 == 0
+//              keeps every CTA's slab 16-byte aligned) and flushes it with all threads after one barrier.
+template <int LPE> struct Geo {
+    static constexpr int THREADS = LPE <= 8 ? 128 : 16 * LPE;
+    static constexpr int EPB = THREADS / LPE;
+    static constexpr int STREAM = LPE == 1 ? (THREADS / 32) * STREAM_WORDS : 2 * ((EPB * OBS_BYTES + 31) / 32 + 1);
+    static constexpr int MIN_BLOCKS = LPE == 1 ? WAB_MIN_BLOCKS_LPE1 : 1;
+};
+
+struct Ctx {   // per-thread view of the CTA geometry
+    int lane, sub, slot;          // slot = env index within the emission unit (warp for LPE 1, CTA otherwise)
+    int env_local;                // env index within the CTA
+    int64_t idx, unit_first;      // global env index; first env of the emission unit
+    int n_valid;                  // envs of the emission unit that exist
+    bool active, writer;          // env exists; this lane writes the env's outputs
+};
+
+template <int LPE>
+__device__ __forceinline__ Ctx make_ctx(int64_t n) {
+    Ctx c;
+    constexpr int EPB = Geo<LPE>::EPB;
+    c.lane = threadIdx.x & 31;
+    c.sub = LPE == 1 ? 0 : (c.lane % LPE);
+    c.env_local = threadIdx.x / LPE;
+    c.idx = (int64_t)blockIdx.x * EPB + c.env_local;
+    c.active = c.idx < n;
+    c.writer = c.active && c.sub == 0;
+    if (LPE == 1) { c.slot = c.lane; c.unit_first = c.idx - c.lane; }
+    else { c.slot = c.env_local; c.unit_first = (int64_t)blockIdx.x * EPB; }
+    const int64_t left = n - c.unit_first;
+    const int cap = LPE == 1 ? 32 : EPB;
+    c.n_valid = (int)(left < cap ? (left > 0 ? left : 0) : cap);
+    return c;
+}
+
+// Publish the unit's observations for one step. `buf` alternates 0/1 (LPE > 1 double buffer).
+template <int LPE>
+__device__ __forceinline__ void emit_obs(const Params& P, uint32_t* stream_base, const Ctx& c, int buf,
+                                         const uint32_t wm[4], const uint32_t bm[4], uint32_t role, uint8_t* gunit) {
+    if (LPE == 1) {
+        uint32_t* stream = stream_base + (threadIdx.x >> 5) * STREAM_WORDS;
+        stream_put(P, stream, c.slot, wm, bm, role, c.active);
+        __syncwarp();
+        stream_flush(stream, gunit, OBS_BYTES * c.n_valid, c.lane, 32);
+        __syncwarp();
+    } else {
+        uint32_t* stream = stream_base + buf * (Geo<LPE>::STREAM / 2);
+        if (c.sub == 0) stream_put(P, stream, c.slot, wm, bm, role, c.active);
+        __syncthreads();     // the NEXT step's barrier also orders this flush before the buffer is rewritten
+        stream_flush(stream, gunit, OBS_BYTES * c.n_valid, threadIdx.x, Geo<LPE>::THREADS);
+    }
+}
+
 // T lockstep steps of every env; observation, reward, done and info are written for every step.
-template <bool F64>
-__global__ void __launch_bounds__(128) wab_step_kernel(const __grid_constant__ Params P, const StatePtrs st,
-                                                       const uint8_t* __restrict__ actions, const int n_steps,
-                                                       const OutPtrs out) {
+template <bool F64, int LPE>
+__global__ void __launch_bounds__(Geo<LPE>::THREADS, Geo<LPE>::MIN_BLOCKS)
+wab_step_kernel(const __grid_constant__ Params P, const StatePtrs st, const uint8_t* __restrict__ actions,
+                const int n_steps, const OutPtrs out) {
     extern __shared__ uint32_t smem[];
-    const int bs = blockDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t* wolves_s = smem + threadIdx.x;                                   // [wolf_cap][bs]
-    uint32_t* stream = smem + P.wolf_cap * bs + warp * STREAM_WORDS;
-    uint32_t* block_s = smem + P.wolf_cap * bs + (bs >> 5) * STREAM_WORDS;     // 8 words
-    const int64_t idx = (int64_t)blockIdx.x * bs + threadIdx.x;
+    constexpr int EPB = Geo<LPE>::EPB;
     const int64_t n = st.n;
-    const bool active = idx < n;
-    const int64_t warp_first = idx - lane;
-    const int n_valid = (int)((n - warp_first) < 32 ? (n - warp_first > 0 ? n - warp_first : 0) : 32);
+    const Ctx c = make_ctx<LPE>(n);
+    uint32_t* wolves_s = smem + c.env_local;                                  // [wolf_cap][EPB]
+    uint32_t* stream_base = smem + P.wolf_cap * EPB;
+    uint32_t* block_s = stream_base + Geo<LPE>::STREAM;                       // 8 words
+    Coop<LPE> coop;
+    coop.sub = (uint32_t)c.sub;
+    coop.gmask = LPE == 32 ? FULL : (((1u << (LPE & 31)) - 1u) << (c.lane - c.sub));
 
     Env E;
     Slots S;
-    S.wolves = wolves_s; S.wstride = bs;
-    S.logcell = st.logcell + (active ? idx : 0); S.logcnt = st.logcnt + (active ? idx : 0); S.lstride = n;
-    if (active) load_env<F64>(P, st, idx, E, wolves_s, bs);
+    S.wolves = wolves_s; S.wstride = EPB;
+    S.logcell = st.logcell + (c.active ? c.idx : 0); S.logcnt = st.logcnt + (c.active ? c.idx : 0); S.lstride = n;
+    if (c.active) load_env<F64>(P, st, c.idx, E, wolves_s, EPB);
     else { E = Env(); }
 
     uint32_t cnt[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
     for (int t = 0; t < n_steps; ++t) {
         StepOut O;
         bool need_reset = false;
-        if (active) {
-            const uint32_t a = actions[(int64_t)t * n + idx];
-            env_step<F64>(P, E, S, a, O);
+        if (c.active) {
+            const uint32_t a = actions[(int64_t)t * n + c.idx];
+            env_step<F64, LPE>(P, E, S, a, O, coop);
             need_reset = O.done && P.auto_reset;
-            cnt[WAB_STAT_EPISODES] += O.done;      // auto_reset = 0: every step that reports done counts
-            cnt[WAB_STAT_STEPS] += 1u;
-            cnt[WAB_STAT_FINISHED] += (O.outcome == 1u) ? 1u : 0u;
-            cnt[WAB_STAT_STARVED] += (O.outcome == 2u) ? 1u : 0u;
-            cnt[WAB_STAT_KILLED] += (O.outcome == 3u) ? 1u : 0u;
-            cnt[WAB_STAT_EATS] += O.ate;
-            cnt[WAB_STAT_BAD_ACTIONS] += O.bad_action;
+            if (c.sub == 0) {
+                cnt[WAB_STAT_EPISODES] += O.done;  // auto_reset = 0: every step that reports done counts
+                cnt[WAB_STAT_STEPS] += 1u;
+                cnt[WAB_STAT_FINISHED] += (O.outcome == 1u) ? 1u : 0u;
+                cnt[WAB_STAT_STARVED] += (O.outcome == 2u) ? 1u : 0u;
+                cnt[WAB_STAT_KILLED] += (O.outcome == 3u) ? 1u : 0u;
+                cnt[WAB_STAT_EATS] += O.ate;
+                cnt[WAB_STAT_BAD_ACTIONS] += O.bad_action;
+            }
         } else {
             O = StepOut();
         }
         if (__any_sync(FULL, need_reset)) {
-            warp_reset<F64>(P, E, S, need_reset, lane, O.wm, O.bm, O.overflow);
+            warp_reset<F64, LPE>(P, E, S, need_reset, c.lane, O.wm, O.bm, O.overflow);
             if (need_reset) {          // VecEnv semantics: the post-reset observation is returned
                 O.food_obs = food_observation(P, E, F64);
                 O.role = E.role; O.status = E.status;
             }
         }
-        if (active) {
+        if (c.writer) {
             cnt[WAB_STAT_OVERFLOWS] += O.overflow;
-            write_scalars(out, (int64_t)t * n + idx, O);
+            write_scalars(out, (int64_t)t * n + c.idx, O);
         }
-        emit_obs(P, stream, O.wm, O.bm, O.role, active, lane,
-                 out.grids + ((int64_t)t * n + warp_first) * OBS_BYTES, n_valid);
+        emit_obs<LPE>(P, stream_base, c, t & 1, O.wm, O.bm, O.role,
+                      out.grids + ((int64_t)t * n + c.unit_first) * OBS_BYTES);
     }
-    if (active) store_env<F64>(st, idx, E, wolves_s, bs);
+    if (c.writer) store_env<F64>(st, c.idx, E, wolves_s, EPB);
     flush_stats(st.stats, cnt, block_s);
 }
 
 // reset(mask) + fresh observation of every env
-template <bool F64>
-__global__ void __launch_bounds__(128) wab_reset_kernel(const __grid_constant__ Params P, const StatePtrs st,
-                                                        const uint8_t* __restrict__ mask, const OutPtrs out) {
+template <bool F64, int LPE>
+__global__ void __launch_bounds__(Geo<LPE>::THREADS)
+wab_reset_kernel(const __grid_constant__ Params P, const StatePtrs st, const uint8_t* __restrict__ mask,
+                 const OutPtrs out) {
     extern __shared__ uint32_t smem[];
-    const int bs = blockDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t* wolves_s = smem + threadIdx.x;
-    uint32_t* stream = smem + P.wolf_cap * bs + warp * STREAM_WORDS;
-    uint32_t* block_s = smem + P.wolf_cap * bs + (bs >> 5) * STREAM_WORDS;
-    const int64_t idx = (int64_t)blockIdx.x * bs + threadIdx.x;
+    constexpr int EPB = Geo<LPE>::EPB;
     const int64_t n = st.n;
-    const bool active = idx < n;
-    const int64_t warp_first = idx - lane;
-    const int n_valid = (int)((n - warp_first) < 32 ? (n - warp_first > 0 ? n - warp_first : 0) : 32);
+    const Ctx c = make_ctx<LPE>(n);
+    uint32_t* wolves_s = smem + c.env_local;
+    uint32_t* stream_base = smem + P.wolf_cap * EPB;
+    uint32_t* block_s = stream_base + Geo<LPE>::STREAM;
     Env E;
     Slots S;
-    S.wolves = wolves_s; S.wstride = bs;
-    S.logcell = st.logcell + (active ? idx : 0); S.logcnt = st.logcnt + (active ? idx : 0); S.lstride = n;
-    if (active) load_env<F64>(P, st, idx, E, wolves_s, bs);
+    S.wolves = wolves_s; S.wstride = EPB;
+    S.logcell = st.logcell + (c.active ? c.idx : 0); S.logcnt = st.logcnt + (c.active ? c.idx : 0); S.lstride = n;
+    if (c.active) load_env<F64>(P, st, c.idx, E, wolves_s, EPB);
     else { E = Env(); }
-    const bool need = active && (mask == nullptr || mask[idx] != 0);
+    const bool need = c.active && (mask == nullptr || mask[c.idx] != 0);
     StepOut O = StepOut();
     uint32_t cnt[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-    if (active && !need) {
+    if (c.active && !need) {
         wolf_plane(E, S, O.wm);
         O.bm[0] = E.m[0]; O.bm[1] = E.m[1]; O.bm[2] = E.m[2]; O.bm[3] = E.m[3];
     }
-    warp_reset<F64>(P, E, S, need, lane, O.wm, O.bm, O.overflow);
-    if (active) {
+    warp_reset<F64, LPE>(P, E, S, need, c.lane, O.wm, O.bm, O.overflow);
+    if (c.active) {
         O.food_obs = food_observation(P, E, F64);
         O.role = E.role; O.status = E.status;
-        out.food[idx] = (uint8_t)O.food_obs; out.role[idx] = (uint8_t)O.role; out.status[idx] = (uint8_t)O.status;
-        cnt[WAB_STAT_OVERFLOWS] += O.overflow;
-        store_env<F64>(st, idx, E, wolves_s, bs);
     }
-    emit_obs(P, stream, O.wm, O.bm, O.role, active, lane, out.grids + warp_first * OBS_BYTES, n_valid);
+    if (c.writer) {
+        out.food[c.idx] = (uint8_t)O.food_obs; out.role[c.idx] = (uint8_t)O.role; out.status[c.idx] = (uint8_t)O.status;
+        cnt[WAB_STAT_OVERFLOWS] += O.overflow;
+        store_env<F64>(st, c.idx, E, wolves_s, EPB);
+    }
+    emit_obs<LPE>(P, stream_base, c, 0, O.wm, O.bm, O.role, out.grids + c.unit_first * OBS_BYTES);
     flush_stats(st.stats, cnt, block_s);
 }
 
@@ -326,18 +392,18 @@ struct WabVec {
     // device staging for the host-buffer entry points
     uint8_t* stage;
     size_t stage_bytes;
+    int lpe;          // lanes per env chosen at create (see pick_lpe)
 };
 
 namespace {
 
-int block_size_for(int64_t n) {
-    int bs = 128;
-    while (bs > 32 && (n + bs - 1) / bs < 2 * 148) bs >>= 1;   // keep >= 2 CTAs per SM when the batch allows
-    return bs;
+template <int LPE> size_t smem_bytes_for(const Params& P) {
+    return sizeof(uint32_t) * ((size_t)P.wolf_cap * Geo<LPE>::EPB + (size_t)Geo<LPE>::STREAM + 8);
 }
-size_t smem_bytes(const WabVec* h, int bs) {
-    return sizeof(uint32_t) * ((size_t)h->P.wolf_cap * bs + (size_t)(bs / 32) * STREAM_WORDS + 8);
-}
+template <bool F64, int LPE>
+void launch_step_t(const WabVec* h, const uint8_t* a, int T, const OutPtrs& out, cudaStream_t s);
+template <bool F64, int LPE>
+void launch_reset_t(const WabVec* h, const uint8_t* mask, const OutPtrs& out, cudaStream_t s);
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int check_ptr_align(const void* p, const char* name) {
@@ -345,16 +411,58 @@ int check_ptr_align(const void* p, const char* name) {
     return WAB_OK;
 }
 
+template <bool F64, int LPE>
+void launch_step_t(const WabVec* h, const uint8_t* a, int T, const OutPtrs& out, cudaStream_t s) {
+    const unsigned grid = (unsigned)((h->n + Geo<LPE>::EPB - 1) / Geo<LPE>::EPB);
+    wab_step_kernel<F64, LPE><<<grid, Geo<LPE>::THREADS, smem_bytes_for<LPE>(h->P), s>>>(h->P, h->st, a, T, out);
+}
+template <bool F64, int LPE>
+void launch_reset_t(const WabVec* h, const uint8_t* mask, const OutPtrs& out, cudaStream_t s) {
+    const unsigned grid = (unsigned)((h->n + Geo<LPE>::EPB - 1) / Geo<LPE>::EPB);
+    wab_reset_kernel<F64, LPE><<<grid, Geo<LPE>::THREADS, smem_bytes_for<LPE>(h->P), s>>>(h->P, h->st, mask, out);
+}
+// Lanes per env: the largest LPE whose whole grid is co-resident (one wave) on this device, so that a
+// small batch spreads over all SMs and shortens its per-step critical path; large batches use the
+// thread-per-env kernel, which wastes no issue slots. WAB_LPE overrides (tests, tuning).
+template <int LPE>
+bool fits_one_wave(const WabVec* h, int n_sm) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wab_step_kernel<false, LPE>, Geo<LPE>::THREADS,
+                                                      smem_bytes_for<LPE>(h->P)) != cudaSuccess)
+        return false;
+    const int64_t grid = (h->n + Geo<LPE>::EPB - 1) / Geo<LPE>::EPB;
+    return grid <= (int64_t)per_sm * n_sm;
+}
+int pick_lpe(const WabVec* h) {
+    if (const char* e = getenv("WAB_LPE")) {
+        const int v = atoi(e);
+        if (v == 1 || v == 4 || v == 8 || v == 16 || v == 32) return v;
+    }
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device);
+    if (fits_one_wave<32>(h, n_sm)) return 32;
+    if (fits_one_wave<16>(h, n_sm)) return 16;
+    if (fits_one_wave<8>(h, n_sm)) return 8;
+    if (fits_one_wave<4>(h, n_sm)) return 4;
+    return 1;
+}
+
+#define WAB_DISPATCH(FN, ...)                                                                  \
+    do {                                                                                       \
+        const bool f64__ = h->cfg.food_mode == WAB_FOOD_F64;                                   \
+        switch (h->lpe) {                                                                      \
+            case 32: f64__ ? FN<true, 32>(__VA_ARGS__) : FN<false, 32>(__VA_ARGS__); break;    \
+            case 16: f64__ ? FN<true, 16>(__VA_ARGS__) : FN<false, 16>(__VA_ARGS__); break;    \
+            case 8: f64__ ? FN<true, 8>(__VA_ARGS__) : FN<false, 8>(__VA_ARGS__); break;       \
+            case 4: f64__ ? FN<true, 4>(__VA_ARGS__) : FN<false, 4>(__VA_ARGS__); break;       \
+            default: f64__ ? FN<true, 1>(__VA_ARGS__) : FN<false, 1>(__VA_ARGS__); break;      \
+        }                                                                                      \
+    } while (0)
+
 int launch_step(WabVec* h, int n_steps, const uint8_t* d_actions, const WabObs& obs, float* d_reward,
                 uint8_t* d_done, uint8_t* d_info, cudaStream_t s) {
     OutPtrs out{obs.d_grids, obs.d_food, obs.d_role, obs.d_status, d_reward, d_done, d_info};
-    const int bs = block_size_for(h->n);
-    const unsigned grid = (unsigned)((h->n + bs - 1) / bs);
-    const size_t sm = smem_bytes(h, bs);
-    if (h->cfg.food_mode == WAB_FOOD_F64)
-        wab_step_kernel<true><<<grid, bs, sm, s>>>(h->P, h->st, d_actions, n_steps, out);
-    else
-        wab_step_kernel<false><<<grid, bs, sm, s>>>(h->P, h->st, d_actions, n_steps, out);
+    WAB_DISPATCH(launch_step_t, h, d_actions, n_steps, out, s);
     WAB_CUDA(cudaGetLastError());
     return WAB_OK;
 }
@@ -440,6 +548,7 @@ int wab_vec_create(const WabConfig* cfg, const uint32_t* bush_thr, int32_t n_bus
     st.bush = (uint4*)(base + o_bush); st.nlog = base + o_nlog; st.food = (double*)(base + o_food);
     st.wolves = (uint32_t*)(base + o_wolves); st.logcell = (uint32_t*)(base + o_lcell); st.logcnt = base + o_lcnt;
     st.stats = (unsigned long long*)(base + o_stats); st.n = n_envs;
+    h->lpe = pick_lpe(h);
     *out = h;
     return WAB_OK;
 }
@@ -454,18 +563,15 @@ void wab_vec_destroy(WabVec* h) {
 }
 
 int64_t wab_vec_num_envs(const WabVec* h) { return h ? h->n : 0; }
+int wab_vec_lanes_per_env(const WabVec* h) { return h ? h->lpe : 0; }
 
 int wab_vec_reset(WabVec* h, const uint8_t* d_mask, WabObs obs, void* stream) {
     if (!h || !obs.d_grids || !obs.d_food || !obs.d_role || !obs.d_status) return fail(WAB_E_NULL, "null argument");
     if (int rc = check_ptr_align(obs.d_grids, "d_grids")) return rc;
     DeviceGuard guard(h->device);
     OutPtrs out{obs.d_grids, obs.d_food, obs.d_role, obs.d_status, nullptr, nullptr, nullptr};
-    const int bs = block_size_for(h->n);
-    const unsigned grid = (unsigned)((h->n + bs - 1) / bs);
-    const size_t sm = smem_bytes(h, bs);
     cudaStream_t s = (cudaStream_t)stream;
-    if (h->cfg.food_mode == WAB_FOOD_F64) wab_reset_kernel<true><<<grid, bs, sm, s>>>(h->P, h->st, d_mask, out);
-    else wab_reset_kernel<false><<<grid, bs, sm, s>>>(h->P, h->st, d_mask, out);
+    WAB_DISPATCH(launch_reset_t, h, d_mask, out, s);
     WAB_CUDA(cudaGetLastError());
     return WAB_OK;
 }

@@ -63,6 +63,7 @@ class VecEnv:
                                            self.seed & 0xFFFFFFFFFFFFFFFF, self.env_id_base, self.device.index,
                                            ctypes.byref(handle)))
         self._h = handle
+        self.lanes_per_env = int(self.lib.wab_vec_lanes_per_env(self._h))
         self._out = self._alloc(None)
         self._many: Dict[int, dict] = {}
 
