@@ -177,8 +177,6 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     n, K, W, T = args.num_envs, args.steps, max(args.warmup, 3), max(1, min(args.fuse, args.steps))
-    if n % 16:
-        raise SystemExit("--num-envs must be a multiple of 16")
     env = VecEnv(n, seed=args.seed, device=dev, env_id_base=rank * n)
     gen = torch.Generator(device=dev).manual_seed(1 + rank)
     actions = torch.randint(0, env.n_actions, (K + W, n), dtype=torch.uint8, device=dev, generator=gen)

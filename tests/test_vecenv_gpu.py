@@ -187,6 +187,25 @@ def test_step_many_equals_repeated_step_and_sharding_is_invisible():
         e.close()
 
 
+@pytest.mark.parametrize("lpe", [1, 8, 32])
+def test_step_many_on_a_ragged_batch(lpe, monkeypatch):
+    """N = 77 is not a multiple of 16: every step's slab starts at a different 16-byte phase."""
+    monkeypatch.setenv("WAB_LPE", str(lpe))
+    n, steps = 77, 23
+    acts = torch.randint(0, 5, (steps, n), dtype=torch.uint8, device="cuda", generator=torch.Generator("cuda").manual_seed(8))
+    a, b = _vec(n, seed=2), _vec(n, seed=2)
+    a.reset(), b.reset()
+    o, r, d, i = a.step_many(acts)
+    canary = torch.full((steps, n, 3, 11, 11), 7, dtype=torch.uint8, device="cuda")
+    for t in range(steps):
+        ob, rb, db, ib = b.step(acts[t])
+        canary[t] = ob.grids
+        assert torch.equal(o.grids[t], ob.grids) and torch.equal(r[t], rb) and torch.equal(d[t], db), (lpe, t)
+        assert torch.equal(o.food[t], ob.food) and torch.equal(i["info"][t], ib["info"])
+    assert int(canary.max()) <= 1
+    a.close(), b.close()
+
+
 def test_full_size_checksum_against_oracle():
     """BASELINE config 2 (4096 default envs): position-weighted checksum of every observation of
     every step equals the CPU oracle's (a checksum of checksums over 4096 x 400 env-steps)."""

@@ -24,10 +24,10 @@
 #endif
 
 #ifndef WAB_SLIDE_UNROLL
-#define WAB_SLIDE_UNROLL 2
+#define WAB_SLIDE_UNROLL 1
 #endif
 #ifndef WAB_SPAWN_UNROLL
-#define WAB_SPAWN_UNROLL 2
+#define WAB_SPAWN_UNROLL 1
 #endif
 
 namespace wab {
@@ -57,6 +57,7 @@ template <int J, int W> struct ColMask { static constexpr uint32_t v = colmask_w
 struct Params {
     uint32_t rk0[10], rk1[10];     // Philox round keys (key is uniform: the seed)
     uint32_t thr_bush1;            // food0 > 0  <=>  word >= thr_bush1   (bush_thr[0])
+    uint32_t thr_bush2;            // food0 > 1  <=>  word >= thr_bush2   (bush_thr[1]; only read when n_bush_thr > 1)
     uint32_t thr_spawn, thr_init;  // event <=> word < thr
     uint32_t n_bush_thr;
     uint64_t thr_keep;             // kept <=> word >= thr_keep
@@ -78,6 +79,7 @@ struct Params {
 struct Env {
     int32_t x, y;
     uint32_t turn, role, status, nw, nlog, episode, env_id;
+    uint32_t logsig; // 32-bit Bloom signature of the cells in the depletion log (a clear bit proves absence)
     uint32_t dep;    // 1 once some logged cell has been eaten empty (re-entering cells must consult the log)
     uint32_t m[4];   // bush occupancy of the window (food > 0), current
     int32_t food_i;  // INT mode
@@ -184,9 +186,12 @@ WAB_HD uint32_t bush_word(const Params& P, const Env& E, int32_t x, int32_t y) {
     philox(P, E.env_id, E.episode, ctr2(SITE_BUSH, 0, 0), pack_xy(x >> 1, y >> 1), w);
     return pick4(w, ((uint32_t)x & 1u) | (((uint32_t)y & 1u) << 1));
 }
-// eats recorded for a cell, or -1
+WAB_HD uint32_t cell_sig(uint32_t cell) { return 1u << ((cell * 0x9E3779B1u) >> 27); }
+// log slot of a cell, or -1. The signature answers "never eaten here" without touching memory; the
+// search runs newest-first because repeated eats hit the most recent entry.
 WAB_HD int32_t log_find(const Env& E, const Slots& S, uint32_t cell) {
-    for (uint32_t l = 0; l < E.nlog; ++l)
+    if (!(E.logsig & cell_sig(cell))) return -1;
+    for (uint32_t l = E.nlog; l-- > 0u;)
         if (S.logcell[(int64_t)l * S.lstride] == cell) return (int32_t)l;
     return -1;
 }
@@ -194,6 +199,7 @@ WAB_HD int32_t log_find(const Env& E, const Slots& S, uint32_t cell) {
 // #{k : thr[k] <= word} exceeds eats  <=>  word >= thr[eats]   (thr ascending; one table load).
 WAB_HD uint32_t alive_after(const Params& P, uint32_t word, uint32_t eats) {
     if (eats >= P.n_bush_thr) return 0u;
+    if (eats == 1u) return word >= P.thr_bush2 ? 1u : 0u;    // the common case needs no table load
 #if defined(__CUDA_ARCH__)
     return word >= __ldg(P.bush_thr + eats) ? 1u : 0u;
 #else
@@ -385,6 +391,7 @@ WAB_HD void env_step(const Params& P, Env& E, const Slots& S, uint32_t action, S
             S.logcell[(int64_t)E.nlog * S.lstride] = cell;
             S.logcnt[(int64_t)E.nlog * S.lstride] = 1;
             E.nlog += 1;
+            E.logsig |= cell_sig(cell);
         } else {
             eats = 1u; O.overflow = 1u;            // counted, never silent (WAB_STAT_OVERFLOWS)
         }
@@ -482,7 +489,7 @@ WAB_HD uint32_t reset_init_group(const Params& P, uint32_t env_id, uint32_t epis
 template <bool F64>
 WAB_HD void reset_scalars(const Params& P, Env& E) {
     E.episode += 1;                 // first reset -> episode 0 (state is created with 0xFFFFFFFF)
-    E.turn = 0; E.x = 0; E.y = 0; E.status = 0; E.nw = 0; E.nlog = 0; E.dep = 0;
+    E.turn = 0; E.x = 0; E.y = 0; E.status = 0; E.nw = 0; E.nlog = 0; E.dep = 0; E.logsig = 0;
     E.role = (uint32_t)(P.starting_role < 0 ? 0 : P.starting_role);
     E.food_i = P.food_int_start;
     E.food_f = P.food_start;

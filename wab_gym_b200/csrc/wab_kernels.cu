@@ -29,7 +29,6 @@ using namespace wab;
 namespace {
 
 constexpr unsigned FULL = 0xFFFFFFFFu;
-constexpr int STREAM_WORDS = 364;   // 32 envs * 363 bits = 363 words (+1 pad keeps rows 8-byte aligned)
 #ifndef WAB_MIN_BLOCKS_LPE1
 #define WAB_MIN_BLOCKS_LPE1 6         // thread-per-env kernel: cap registers at 80 so 6 CTAs (24 warps) fit an SM
 #endif
@@ -40,6 +39,7 @@ struct StatePtrs {
     uint32_t* episode;   // [N]
     uint4* bush;         // [N]  121-bit window occupancy
     uint8_t* nlog;       // [N]
+    uint32_t* logsig;    // [N]  Bloom signature of the depletion log
     double* food;        // [N]  F64 mode only
     uint32_t* wolves;    // [wolf_cap][N]
     uint32_t* logcell;   // [log_cap][N]
@@ -65,6 +65,7 @@ __device__ __forceinline__ void load_env(const Params& P, const StatePtrs& st, i
     const uint4 b = st.bush[idx];
     E.m[0] = b.x; E.m[1] = b.y; E.m[2] = b.z; E.m[3] = b.w;
     E.nlog = st.nlog[idx];
+    E.logsig = st.logsig[idx];
     E.food_f = F64 ? st.food[idx] : 0.0;
     E.env_id = (uint32_t)(P.env_id_base + (uint64_t)idx);
     for (uint32_t k = 0; k < E.nw; ++k) wolves_s[k * wstride] = st.wolves[(int64_t)k * st.n + idx];
@@ -79,6 +80,7 @@ __device__ __forceinline__ void store_env(const StatePtrs& st, int64_t idx, cons
     st.episode[idx] = E.episode;
     st.bush[idx] = make_uint4(E.m[0], E.m[1], E.m[2], E.m[3]);
     st.nlog[idx] = (uint8_t)E.nlog;
+    st.logsig[idx] = E.logsig;
     if (F64) st.food[idx] = E.food_f;
     for (uint32_t k = 0; k < E.nw; ++k) st.wolves[(int64_t)k * st.n + idx] = wolves_s[k * wstride];
 }
@@ -134,11 +136,22 @@ __device__ __forceinline__ void warp_reset(const Params& P, Env& E, const Slots&
 
 __device__ __forceinline__ uint32_t nibble_to_bytes(uint32_t n) { return (n * 0x00204081u) & 0x01010101u; }
 
-// Put one env's 363-bit observation string into a shared bit stream at bit offset 363 * slot.
-// The env's last 60 bits are always zero, so the word it shares with slot + 1 is written by slot + 1
-// alone: plain stores, no atomics.
-__device__ __forceinline__ void stream_put(const Params& P, uint32_t* stream, int slot, const uint32_t wm[4],
-                                           const uint32_t bm[4], uint32_t role, bool active) {
+// Observation output of one WARP for one step.
+//
+// The warp's EPW envs own the contiguous byte range [b0, b0 + 363*EPW) of the grids tensor. Their
+// 363-bit strings are concatenated into a shared-memory bit stream in which bit (off + k) is byte
+// (b0 + k) of the output, off = b0 & 15 — so the stream is aligned to the 16-byte store grid whatever
+// b0 is. Each lane then expands 16 bits into 16 bytes ((nibble * 0x00204081) & 0x01010101) and issues
+// one coalesced 16-byte streaming store; the < 16 ragged bytes at either end, which share a store
+// slot with the neighbouring warp, are written as single bytes. No CTA barrier, no atomics: the last
+// 60 bits of every env's string are zero, so a word shared by two envs is written by the later one.
+template <int EPW>
+struct WarpStream {
+    static constexpr int WORDS = (EPW * OBS_BYTES + 15 + 31) / 32 + 1;
+};
+
+__device__ __forceinline__ void stream_put(const Params& P, uint32_t* stream, int bit0, bool last, int total_bits,
+                                           const uint32_t wm[4], const uint32_t bm[4], uint32_t role, bool active) {
     uint32_t B[11];
     if (active) {
         compose_obs(P, wm, bm, role, B);
@@ -146,32 +159,39 @@ __device__ __forceinline__ void stream_put(const Params& P, uint32_t* stream, in
 #pragma unroll
         for (int k = 0; k < 11; ++k) B[k] = 0u;
     }
-    const uint32_t sh = (11u * (uint32_t)slot) & 31u;            // 363 mod 32 = 11
-    const int fw = (OBS_BYTES * slot) >> 5;
-    const int nown = ((OBS_BYTES * (slot + 1)) >> 5) - fw;       // 11 or 12
+    const uint32_t sh = (uint32_t)bit0 & 31u;
+    const int fw = bit0 >> 5;
+    // words this env must write: up to (not including) the next env's first word; the last env also
+    // zero-fills the tail of the stream so no stale shared memory is ever flushed
+    const int nown = (last ? ((total_bits + 31) >> 5) : ((bit0 + OBS_BYTES) >> 5)) - fw;   // 11, 12 or 13
     stream[fw] = B[0] << sh;
 #pragma unroll
     for (int k = 1; k < 11; ++k) stream[fw + k] = fshl(B[k - 1], B[k], sh);
-    if (nown == 12) stream[fw + 11] = fshl(B[10], 0u, sh);
+    if (nown > 11) stream[fw + 11] = fshl(B[10], 0u, sh);
+    if (nown > 12) stream[fw + 12] = 0u;
 }
 
-// Expand a bit stream (bit b = byte b of the output) into `nbytes` bytes at gbase (16-byte aligned)
-// with `nthreads` cooperating threads: 16 bits -> one 16-byte streaming store per thread-iteration.
-__device__ __forceinline__ void stream_flush(const uint32_t* stream, uint8_t* gbase, int nbytes, int tid, int nthreads) {
+// gA = 16-byte aligned address of stream bit 0; valid bits are [off, end).
+__device__ __forceinline__ void stream_flush(const uint32_t* stream, uint8_t* gA, int off, int end, int lane) {
     const uint16_t* hs = reinterpret_cast<const uint16_t*>(stream);
-    const int nfull = nbytes >> 4;
+    const int c_lo = (off + 15) >> 4, c_hi = end >> 4;            // chunks entirely inside [off, end)
 #pragma unroll 2
-    for (int c = tid; c < nfull; c += nthreads) {
+    for (int c = c_lo + lane; c < c_hi; c += 32) {
         const uint32_t h = hs[c];
         uint4 v;
         v.x = nibble_to_bytes(h & 15u);
         v.y = nibble_to_bytes((h >> 4) & 15u);
         v.z = nibble_to_bytes((h >> 8) & 15u);
         v.w = nibble_to_bytes(h >> 12);
-        __stcs(reinterpret_cast<uint4*>(gbase) + c, v);
+        __stcs(reinterpret_cast<uint4*>(gA) + c, v);
     }
-    const int b = (nfull << 4) + tid;                             // ragged tail of a partial batch
-    if (tid < 16 && b < nbytes) gbase[b] = (uint8_t)((stream[b >> 5] >> (b & 31)) & 1u);
+    if (lane < 16) {                                              // ragged head and tail, one byte per lane
+        const int head_end = min(c_lo << 4, end);
+        const int hb = off + lane;
+        if (hb < head_end) gA[hb] = (uint8_t)((stream[hb >> 5] >> (hb & 31)) & 1u);
+        const int tb = max(c_hi << 4, head_end) + lane;
+        if (tb < end) gA[tb] = (uint8_t)((stream[tb >> 5] >> (tb & 31)) & 1u);
+    }
 }
 
 __device__ __forceinline__ void write_scalars(const OutPtrs& out, int64_t o, const StepOut& O) {
@@ -196,59 +216,53 @@ __device__ __forceinline__ void flush_stats(unsigned long long* stats, const uin
     if (threadIdx.x < 8 && block_s[threadIdx.x]) atomicAdd(&stats[threadIdx.x], (unsigned long long)block_s[threadIdx.x]);
 }
 
-// Geometry of one CTA for a lanes-per-env factor LPE.
-//   LPE == 1 : thread per env; each WARP owns a 32-env bit stream and flushes it alone (__syncwarp only).
-//   LPE  > 1 : LPE lanes per env; the CTA owns one double-buffered stream for its EPB envs (EPB % 16 == 0
-//              keeps every CTA's slab 16-byte aligned) and flushes it with all threads after one barrier.
+// Geometry: 128-thread CTAs for every lanes-per-env factor; a warp owns EPW = 32 / LPE envs.
 template <int LPE> struct Geo {
-    static constexpr int THREADS = LPE <= 8 ? 128 : 16 * LPE;
+    static constexpr int THREADS = 128;
+    static constexpr int EPW = 32 / LPE;
     static constexpr int EPB = THREADS / LPE;
-    static constexpr int STREAM = LPE == 1 ? (THREADS / 32) * STREAM_WORDS : 2 * ((EPB * OBS_BYTES + 31) / 32 + 1);
+    static constexpr int STREAM = (THREADS / 32) * WarpStream<EPW>::WORDS;
     static constexpr int MIN_BLOCKS = LPE == 1 ? WAB_MIN_BLOCKS_LPE1 : 1;
 };
 
-struct Ctx {   // per-thread view of the CTA geometry
-    int lane, sub, slot;          // slot = env index within the emission unit (warp for LPE 1, CTA otherwise)
+struct Ctx {   // per-thread view of the geometry
+    int lane, sub, slot;          // slot = env index within the warp
     int env_local;                // env index within the CTA
-    int64_t idx, unit_first;      // global env index; first env of the emission unit
-    int n_valid;                  // envs of the emission unit that exist
+    int64_t idx, warp_first;      // global env index; first env of the warp
+    int n_valid;                  // envs of the warp that exist
     bool active, writer;          // env exists; this lane writes the env's outputs
 };
 
 template <int LPE>
 __device__ __forceinline__ Ctx make_ctx(int64_t n) {
     Ctx c;
-    constexpr int EPB = Geo<LPE>::EPB;
+    constexpr int EPB = Geo<LPE>::EPB, EPW = Geo<LPE>::EPW;
     c.lane = threadIdx.x & 31;
     c.sub = LPE == 1 ? 0 : (c.lane % LPE);
+    c.slot = c.lane / LPE;
     c.env_local = threadIdx.x / LPE;
     c.idx = (int64_t)blockIdx.x * EPB + c.env_local;
+    c.warp_first = c.idx - c.slot;
     c.active = c.idx < n;
     c.writer = c.active && c.sub == 0;
-    if (LPE == 1) { c.slot = c.lane; c.unit_first = c.idx - c.lane; }
-    else { c.slot = c.env_local; c.unit_first = (int64_t)blockIdx.x * EPB; }
-    const int64_t left = n - c.unit_first;
-    const int cap = LPE == 1 ? 32 : EPB;
-    c.n_valid = (int)(left < cap ? (left > 0 ? left : 0) : cap);
+    const int64_t left = n - c.warp_first;
+    c.n_valid = (int)(left < EPW ? (left > 0 ? left : 0) : EPW);
     return c;
 }
 
-// Publish the unit's observations for one step. `buf` alternates 0/1 (LPE > 1 double buffer).
+// Publish the warp's observations for one step; `first_byte` = byte offset of the warp's first env
+// in the grids tensor (any alignment).
 template <int LPE>
-__device__ __forceinline__ void emit_obs(const Params& P, uint32_t* stream_base, const Ctx& c, int buf,
-                                         const uint32_t wm[4], const uint32_t bm[4], uint32_t role, uint8_t* gunit) {
-    if (LPE == 1) {
-        uint32_t* stream = stream_base + (threadIdx.x >> 5) * STREAM_WORDS;
-        stream_put(P, stream, c.slot, wm, bm, role, c.active);
-        __syncwarp();
-        stream_flush(stream, gunit, OBS_BYTES * c.n_valid, c.lane, 32);
-        __syncwarp();
-    } else {
-        uint32_t* stream = stream_base + buf * (Geo<LPE>::STREAM / 2);
-        if (c.sub == 0) stream_put(P, stream, c.slot, wm, bm, role, c.active);
-        __syncthreads();     // the NEXT step's barrier also orders this flush before the buffer is rewritten
-        stream_flush(stream, gunit, OBS_BYTES * c.n_valid, threadIdx.x, Geo<LPE>::THREADS);
-    }
+__device__ __forceinline__ void emit_obs(const Params& P, uint32_t* stream, const Ctx& c, uint8_t* grids,
+                                         int64_t first_byte, const uint32_t wm[4], const uint32_t bm[4], uint32_t role) {
+    constexpr int EPW = Geo<LPE>::EPW;
+    const int off = (int)(first_byte & 15);
+    const int total = off + EPW * OBS_BYTES;
+    if (c.sub == 0)
+        stream_put(P, stream, off + OBS_BYTES * c.slot, c.slot == EPW - 1, total, wm, bm, role, c.active);
+    __syncwarp();
+    stream_flush(stream, grids + (first_byte - off), off, off + OBS_BYTES * c.n_valid, c.lane);
+    __syncwarp();
 }
 
 // T lockstep steps of every env; observation, reward, done and info are written for every step.
@@ -261,8 +275,8 @@ wab_step_kernel(const __grid_constant__ Params P, const StatePtrs st, const uint
     const int64_t n = st.n;
     const Ctx c = make_ctx<LPE>(n);
     uint32_t* wolves_s = smem + c.env_local;                                  // [wolf_cap][EPB]
-    uint32_t* stream_base = smem + P.wolf_cap * EPB;
-    uint32_t* block_s = stream_base + Geo<LPE>::STREAM;                       // 8 words
+    uint32_t* stream = smem + P.wolf_cap * EPB + (threadIdx.x >> 5) * WarpStream<Geo<LPE>::EPW>::WORDS;
+    uint32_t* block_s = smem + P.wolf_cap * EPB + Geo<LPE>::STREAM;            // 8 words
     Coop<LPE> coop;
     coop.sub = (uint32_t)c.sub;
     coop.gmask = LPE == 32 ? FULL : (((1u << (LPE & 31)) - 1u) << (c.lane - c.sub));
@@ -275,11 +289,13 @@ wab_step_kernel(const __grid_constant__ Params P, const StatePtrs st, const uint
     else { E = Env(); }
 
     uint32_t cnt[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    uint32_t a_next = c.active ? actions[c.idx] : 0u;
     for (int t = 0; t < n_steps; ++t) {
         StepOut O;
         bool need_reset = false;
+        const uint32_t a = a_next;
+        if (c.active && t + 1 < n_steps) a_next = actions[(int64_t)(t + 1) * n + c.idx];   // prefetch: off the critical path
         if (c.active) {
-            const uint32_t a = actions[(int64_t)t * n + c.idx];
             env_step<F64, LPE>(P, E, S, a, O, coop);
             need_reset = O.done && P.auto_reset;
             if (c.sub == 0) {
@@ -305,8 +321,7 @@ wab_step_kernel(const __grid_constant__ Params P, const StatePtrs st, const uint
             cnt[WAB_STAT_OVERFLOWS] += O.overflow;
             write_scalars(out, (int64_t)t * n + c.idx, O);
         }
-        emit_obs<LPE>(P, stream_base, c, t & 1, O.wm, O.bm, O.role,
-                      out.grids + ((int64_t)t * n + c.unit_first) * OBS_BYTES);
+        emit_obs<LPE>(P, stream, c, out.grids, ((int64_t)t * n + c.warp_first) * OBS_BYTES, O.wm, O.bm, O.role);
     }
     if (c.writer) store_env<F64>(st, c.idx, E, wolves_s, EPB);
     flush_stats(st.stats, cnt, block_s);
@@ -322,8 +337,8 @@ wab_reset_kernel(const __grid_constant__ Params P, const StatePtrs st, const uin
     const int64_t n = st.n;
     const Ctx c = make_ctx<LPE>(n);
     uint32_t* wolves_s = smem + c.env_local;
-    uint32_t* stream_base = smem + P.wolf_cap * EPB;
-    uint32_t* block_s = stream_base + Geo<LPE>::STREAM;
+    uint32_t* stream = smem + P.wolf_cap * EPB + (threadIdx.x >> 5) * WarpStream<Geo<LPE>::EPW>::WORDS;
+    uint32_t* block_s = smem + P.wolf_cap * EPB + Geo<LPE>::STREAM;
     Env E;
     Slots S;
     S.wolves = wolves_s; S.wstride = EPB;
@@ -347,7 +362,7 @@ wab_reset_kernel(const __grid_constant__ Params P, const StatePtrs st, const uin
         cnt[WAB_STAT_OVERFLOWS] += O.overflow;
         store_env<F64>(st, c.idx, E, wolves_s, EPB);
     }
-    emit_obs<LPE>(P, stream_base, c, 0, O.wm, O.bm, O.role, out.grids + c.unit_first * OBS_BYTES);
+    emit_obs<LPE>(P, stream, c, out.grids, c.warp_first * OBS_BYTES, O.wm, O.bm, O.role);
     flush_stats(st.stats, cnt, block_s);
 }
 
@@ -526,6 +541,7 @@ int wab_vec_create(const WabConfig* cfg, const uint32_t* bush_thr, int32_t n_bus
     const size_t o_ep = o; o = align_up(o + 4 * n, 256);
     const size_t o_bush = o; o = align_up(o + 16 * n, 256);
     const size_t o_nlog = o; o = align_up(o + n, 256);
+    const size_t o_lsig = o; o = align_up(o + 4 * n, 256);
     const size_t o_food = o; o = align_up(o + 8 * n, 256);
     const size_t o_wolves = o; o = align_up(o + 4 * n * (size_t)cfg->wolf_cap, 256);
     const size_t o_lcell = o; o = align_up(o + 4 * n * (size_t)cfg->log_cap, 256);
@@ -545,7 +561,7 @@ int wab_vec_create(const WabConfig* cfg, const uint32_t* bush_thr, int32_t n_bus
     P.bush_thr = h->d_thr;
     StatePtrs& st = h->st;
     st.pos = (uint32_t*)(base + o_pos); st.misc = (uint32_t*)(base + o_misc); st.episode = (uint32_t*)(base + o_ep);
-    st.bush = (uint4*)(base + o_bush); st.nlog = base + o_nlog; st.food = (double*)(base + o_food);
+    st.bush = (uint4*)(base + o_bush); st.nlog = base + o_nlog; st.logsig = (uint32_t*)(base + o_lsig); st.food = (double*)(base + o_food);
     st.wolves = (uint32_t*)(base + o_wolves); st.logcell = (uint32_t*)(base + o_lcell); st.logcnt = base + o_lcnt;
     st.stats = (unsigned long long*)(base + o_stats); st.n = n_envs;
     h->lpe = pick_lpe(h);
@@ -590,8 +606,6 @@ int wab_vec_step_many(WabVec* h, int32_t n_steps, const uint8_t* d_actions, WabO
     if (!h || !d_actions || !obs.d_grids || !obs.d_food || !obs.d_role || !obs.d_status || !d_reward || !d_done)
         return fail(WAB_E_NULL, "null argument");
     if (n_steps < 1 || n_steps > 65535) return fail(WAB_E_CONFIG, "n_steps must be in [1, 65535]");
-    if (n_steps > 1 && (h->n % 16) != 0)
-        return fail(WAB_E_UNSUPPORTED, "step_many needs n_envs to be a multiple of 16 (16-byte aligned step slabs)");
     if (int rc = check_ptr_align(obs.d_grids, "d_grids")) return rc;
     DeviceGuard guard(h->device);
     return launch_step(h, n_steps, d_actions, obs, d_reward, d_done, d_info, (cudaStream_t)stream);

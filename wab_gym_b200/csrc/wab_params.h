@@ -51,6 +51,7 @@ inline void params_from_config(const WabConfig& c, const uint32_t* bush_thr_host
     fill_round_keys(P, (uint32_t)seed, (uint32_t)(seed >> 32));
     P.n_bush_thr = (uint32_t)n_bush_thr;
     P.thr_bush1 = n_bush_thr > 0 ? bush_thr[0] : 0xFFFFFFFFu;
+    P.thr_bush2 = n_bush_thr > 1 ? bush_thr[1] : 0xFFFFFFFFu;
     P.thr_spawn = cfg->thr_spawn; P.thr_init = cfg->thr_init; P.thr_keep = cfg->thr_keep;
     P.act_tbl = 0;
     for (int a = 0; a < cfg->n_actions; ++a) {
