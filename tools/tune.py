@@ -24,6 +24,9 @@ VARIANTS = {
     "slide3": ["-DWAB_SLIDE_UNROLL=3"],
     "spawn1": ["-DWAB_SPAWN_UNROLL=1"],
     "spawn4": ["-DWAB_SPAWN_UNROLL=4"],
+    "lpen5": ["-DWAB_MIN_BLOCKS_LPEN=5"],
+    "lpen6": ["-DWAB_MIN_BLOCKS_LPEN=6"],
+    "lpen8": ["-DWAB_MIN_BLOCKS_LPEN=8"],
     "s1s1": ["-DWAB_SLIDE_UNROLL=1", "-DWAB_SPAWN_UNROLL=1"],
     "s1s1mb8": ["-DWAB_SLIDE_UNROLL=1", "-DWAB_SPAWN_UNROLL=1", "-DWAB_MIN_BLOCKS_LPE1=8"],
 }

@@ -19,8 +19,10 @@
 
 #if defined(__CUDACC__)
 #define WAB_HD __host__ __device__ __forceinline__
+#define WAB_ROLLED _Pragma("unroll 1")   // rare-path loops stay rolled: the step kernel must fit the instruction cache
 #else
 #define WAB_HD static inline
+#define WAB_ROLLED
 #endif
 
 #ifndef WAB_SLIDE_UNROLL
@@ -191,6 +193,7 @@ WAB_HD uint32_t cell_sig(uint32_t cell) { return 1u << ((cell * 0x9E3779B1u) >> 
 // search runs newest-first because repeated eats hit the most recent entry.
 WAB_HD int32_t log_find(const Env& E, const Slots& S, uint32_t cell) {
     if (!(E.logsig & cell_sig(cell))) return -1;
+    WAB_ROLLED
     for (uint32_t l = E.nlog; l-- > 0u;)
         if (S.logcell[(int64_t)l * S.lstride] == cell) return (int32_t)l;
     return -1;
@@ -299,6 +302,7 @@ WAB_HD uint32_t food_observation(const Params& P, const Env& E, bool f64) {
 // wolf plane from the current wolf slots (wab_env.py:412-428)
 WAB_HD void wolf_plane(const Env& E, const Slots& S, uint32_t wm[4]) {
     wm[0] = wm[1] = wm[2] = wm[3] = 0u;
+    WAB_ROLLED
     for (uint32_t k = 0; k < E.nw; ++k) {
         uint32_t p = S.wolves[(int32_t)k * S.wstride];
         int32_t ddx = E.x - unpack_x(p), ddy = E.y - unpack_y(p);
@@ -328,14 +332,17 @@ WAB_HD void env_step(const Params& P, Env& E, const Slots& S, uint32_t action, S
     if (E.nw) {
         uint32_t kept = 0;
         uint32_t keepmask = 0;
+        WAB_ROLLED
         for (uint32_t k = 0; k < E.nw; ++k) {
             const uint32_t p = S.wolves[(int32_t)k * S.wstride];
             uint32_t rank = 0;
+            WAB_ROLLED
             for (uint32_t q = 0; q < k; ++q) rank += (S.wolves[(int32_t)q * S.wstride] == p) ? 1u : 0u;
             uint32_t w[4];
             philox(P, E.env_id, E.episode, ctr2(SITE_DESP, E.turn, rank >> 2), p, w);
             if ((uint64_t)pick4(w, rank & 3u) >= P.thr_keep) keepmask |= 1u << k;
         }
+        WAB_ROLLED
         for (uint32_t k = 0; k < E.nw; ++k)
             if ((keepmask >> k) & 1u) {
                 S.wolves[(int32_t)kept * S.wstride] = S.wolves[(int32_t)k * S.wstride];
@@ -350,6 +357,7 @@ WAB_HD void env_step(const Params& P, Env& E, const Slots& S, uint32_t action, S
 
     // ---- :267-297 wolves chase (ties -> x axis), kill on contact; wolf plane after the move (:289)
     O.wm[0] = O.wm[1] = O.wm[2] = O.wm[3] = 0u;
+    WAB_ROLLED
     for (uint32_t k = 0; k < E.nw; ++k) {
         const uint32_t p = S.wolves[(int32_t)k * S.wstride];
         int32_t wx = unpack_x(p), wy = unpack_y(p);
@@ -421,6 +429,7 @@ WAB_HD void env_step(const Params& P, Env& E, const Slots& S, uint32_t action, S
             hitgroups |= (a < P.thr_spawn ? 1u : 0u) << grp;
         }
         hitgroups = group_or(coop, hitgroups);
+        WAB_ROLLED
         while (hitgroups) {                        // rare: recompute the groups that hit
 #if defined(__CUDA_ARCH__)
             const int grp = __ffs((int)hitgroups) - 1;
@@ -430,6 +439,7 @@ WAB_HD void env_step(const Params& P, Env& E, const Slots& S, uint32_t action, S
             hitgroups &= hitgroups - 1u;
             uint32_t w[4];
             philox(P, E.env_id, E.episode, ctr2(SITE_SPAWN, E.turn, 0), (uint32_t)grp, w);
+            WAB_ROLLED
             for (int l = 0; l < 4; ++l)
                 if (w[l] < P.thr_spawn) {                                        // :571-574
                     int32_t ox, oy;
@@ -463,18 +473,29 @@ WAB_HD void env_step(const Params& P, Env& E, const Slots& S, uint32_t action, S
 // The 36 bush blocks and 31 wolf-init groups of a reset are independent Philox calls; the kernels
 // fan them out over the lanes of a warp. These two helpers are one lane's share.
 
-// bush block blk (0..35) of the reset window -> occupancy bits (generate_bushes at reset, :244)
+// bush block blk (0..35) of the reset window -> occupancy bits (generate_bushes at reset, :244).
+// The block's four cells are bits base, base+1, base+11, base+12 of the window (base = the cell with
+// the larger x and y), so they are deposited as one 13-bit pattern.
 WAB_HD void reset_bush_block(const Params& P, uint32_t env_id, uint32_t episode, int blk, uint32_t part[4]) {
     const int32_t xb = blk / 6 - 3, yb = blk % 6 - 3;       // x >> 1 for x in [-5, 5] is [-3, 2]
     uint32_t w[4];
     philox(P, env_id, episode, ctr2(SITE_BUSH, 0, 0), pack_xy(xb, yb), w);
-    for (int l = 0; l < 4; ++l) {
-        const int32_t x = 2 * xb + (l & 1), y = 2 * yb + (l >> 1);
-        const uint32_t on = (x >= -HALF && x <= HALF && y >= -HALF && y <= HALF && P.n_bush_thr > 0 &&
-                             w[l] >= P.thr_bush1) ? 1u : 0u;
-        const int pos = 11 * (HALF - x) + (HALF - y);        // [i][j] = [5 - x][5 - y], ostrich at (0, 0)
-        setbit128(part, on ? pos : 0, on);
-    }
+    const bool has = P.n_bush_thr > 0;
+    const bool x0 = xb > -3, y0 = yb > -3;                   // x = 2*xb (resp. y = 2*yb) is -6 when xb = -3: outside
+    // lane l = (x&1) | (y&1)<<1 ; [i][j] = [5 - x][5 - y]
+    const uint32_t b11 = (has && w[3] >= P.thr_bush1) ? 1u : 0u;                 // x = 2xb+1, y = 2yb+1 -> base
+    const uint32_t b10 = (has && y0 && w[1] >= P.thr_bush1) ? 1u : 0u;           // x = 2xb+1, y = 2yb   -> base + 1
+    const uint32_t b01 = (has && x0 && w[2] >= P.thr_bush1) ? 1u : 0u;           // x = 2xb,   y = 2yb+1 -> base + 11
+    const uint32_t b00 = (has && x0 && y0 && w[0] >= P.thr_bush1) ? 1u : 0u;     // x = 2xb,   y = 2yb   -> base + 12
+    const uint32_t pat = b11 | (b10 << 1) | (b01 << 11) | (b00 << 12);
+    const int base = 11 * (4 - 2 * xb) + (4 - 2 * yb);       // 0 .. 120
+    const uint32_t r = (uint32_t)base & 31u;
+    const int q = base >> 5;
+    const uint32_t lo = pat << r, hi = fshl(pat, 0u, r);     // hi = pat >> (32 - r), 0 when r = 0
+    part[0] |= (q == 0) ? lo : 0u;
+    part[1] |= (q == 1) ? lo : ((q == 0) ? hi : 0u);
+    part[2] |= (q == 2) ? lo : ((q == 1) ? hi : 0u);
+    part[3] |= (q == 3) ? lo : ((q == 2) ? hi : 0u);
 }
 // wolf-init group grp (0..30): cells c = 4*grp .. 4*grp+3, c = (x+5)*11 + (y+5)  (:578-593) -> hit bits
 WAB_HD uint32_t reset_init_group(const Params& P, uint32_t env_id, uint32_t episode, int grp) {

@@ -29,6 +29,9 @@ using namespace wab;
 namespace {
 
 constexpr unsigned FULL = 0xFFFFFFFFu;
+#ifndef WAB_MIN_BLOCKS_LPEN
+#define WAB_MIN_BLOCKS_LPEN 1         // lanes-per-env kernels: no register cap (one wave of few CTAs anyway)
+#endif
 #ifndef WAB_MIN_BLOCKS_LPE1
 #define WAB_MIN_BLOCKS_LPE1 6         // thread-per-env kernel: cap registers at 80 so 6 CTAs (24 warps) fit an SM
 #endif
@@ -68,6 +71,7 @@ __device__ __forceinline__ void load_env(const Params& P, const StatePtrs& st, i
     E.logsig = st.logsig[idx];
     E.food_f = F64 ? st.food[idx] : 0.0;
     E.env_id = (uint32_t)(P.env_id_base + (uint64_t)idx);
+    WAB_ROLLED
     for (uint32_t k = 0; k < E.nw; ++k) wolves_s[k * wstride] = st.wolves[(int64_t)k * st.n + idx];
 }
 
@@ -82,6 +86,7 @@ __device__ __forceinline__ void store_env(const StatePtrs& st, int64_t idx, cons
     st.nlog[idx] = (uint8_t)E.nlog;
     st.logsig[idx] = E.logsig;
     if (F64) st.food[idx] = E.food_f;
+    WAB_ROLLED
     for (uint32_t k = 0; k < E.nw; ++k) st.wolves[(int64_t)k * st.n + idx] = wolves_s[k * wstride];
 }
 
@@ -101,8 +106,8 @@ __device__ __forceinline__ void warp_reset(const Params& P, Env& E, const Slots&
         const uint32_t eid = __shfl_sync(FULL, E.env_id, r);
         const uint32_t ep = __shfl_sync(FULL, E.episode, r);
         uint32_t part[4] = {0u, 0u, 0u, 0u};
-        reset_bush_block(P, eid, ep, lane, part);                 // blocks 0..31
-        if (lane < 4) reset_bush_block(P, eid, ep, 32 + lane, part);   // blocks 32..35
+#pragma unroll 1
+        for (int blk = lane; blk < 36; blk += 32) reset_bush_block(P, eid, ep, blk, part);   // 36 blocks over 32 lanes
         const uint32_t m0 = __reduce_or_sync(FULL, part[0]);
         const uint32_t m1 = __reduce_or_sync(FULL, part[1]);
         const uint32_t m2 = __reduce_or_sync(FULL, part[2]);
@@ -110,11 +115,13 @@ __device__ __forceinline__ void warp_reset(const Params& P, Env& E, const Slots&
         const uint32_t hits = (P.wolves && lane < 31) ? reset_init_group(P, eid, ep, lane) : 0u;
         unsigned hl = __ballot_sync(FULL, hits != 0u);
         if (mine) { E.m[0] = m0; E.m[1] = m1; E.m[2] = m2; E.m[3] = m3; }
+        WAB_ROLLED
         while (hl) {                                              // rare: p = 0.0005 per cell
             const int src = __ffs((int)hl) - 1;
             hl &= hl - 1u;
             const uint32_t h = __shfl_sync(FULL, hits, src);
             if (mine) {
+                WAB_ROLLED
                 for (int l = 0; l < 4; ++l)
                     if ((h >> l) & 1u) {
                         const int c = 4 * src + l;
@@ -175,7 +182,7 @@ __device__ __forceinline__ void stream_put(const Params& P, uint32_t* stream, in
 __device__ __forceinline__ void stream_flush(const uint32_t* stream, uint8_t* gA, int off, int end, int lane) {
     const uint16_t* hs = reinterpret_cast<const uint16_t*>(stream);
     const int c_lo = (off + 15) >> 4, c_hi = end >> 4;            // chunks entirely inside [off, end)
-#pragma unroll 2
+#pragma unroll 1
     for (int c = c_lo + lane; c < c_hi; c += 32) {
         const uint32_t h = hs[c];
         uint4 v;
@@ -222,7 +229,7 @@ template <int LPE> struct Geo {
     static constexpr int EPW = 32 / LPE;
     static constexpr int EPB = THREADS / LPE;
     static constexpr int STREAM = (THREADS / 32) * WarpStream<EPW>::WORDS;
-    static constexpr int MIN_BLOCKS = LPE == 1 ? WAB_MIN_BLOCKS_LPE1 : 1;
+    static constexpr int MIN_BLOCKS = LPE == 1 ? WAB_MIN_BLOCKS_LPE1 : WAB_MIN_BLOCKS_LPEN;
 };
 
 struct Ctx {   // per-thread view of the geometry
