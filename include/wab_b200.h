@@ -129,6 +129,11 @@ int wab_vec_step_many(WabVec *h, int32_t n_steps, const uint8_t *d_actions, WabO
 int wab_vec_step_host(WabVec *h, const uint8_t *h_actions, uint8_t *h_grids, uint8_t *h_food,
                       uint8_t *h_role, uint8_t *h_status, float *h_reward, uint8_t *h_done,
                       uint8_t *h_info, void *stream);
+/* Same step with ONE contiguous host block for every output (one device-to-host transfer instead of
+ * seven): wab_vec_host_block_layout gives the byte offsets of grids, food, role, status, reward,
+ * done, info inside the block (each 256-byte aligned) and its total size. */
+int wab_vec_host_block_layout(const WabVec *h, int64_t *offsets7, int64_t *total_bytes);
+int wab_vec_step_host_packed(WabVec *h, const uint8_t *h_actions, uint8_t *h_block, void *stream);
 int wab_vec_reset_host(WabVec *h, uint8_t *h_grids, uint8_t *h_food, uint8_t *h_role, uint8_t *h_status,
                        void *stream);
 
@@ -151,6 +156,23 @@ int64_t wab_vec_num_envs(const WabVec *h);
  * small batch still covers every SM; results do not depend on it. */
 int wab_vec_lanes_per_env(const WabVec *h);
 void wab_vec_destroy(WabVec *h);
+
+/* ---- next row of the path: the reference's PragmaticObsWrapper (wab_env.py:670-824), the observation
+ * its actor-critic actually consumes (actor_critic.py:42, :188). 28 bytes per env:
+ * nearest_wolf[4] second_wolf[4] n_wolves[4] nearest_bush[4] second_bush[4] n_bushes[4] (each
+ * [up, right, down, left]) standing_on_bush food role status. */
+#define WAB_FEATURE_BYTES 28
+/* Bind (or unbind with NULL) a device buffer u8[N][28] ([T][N][28] for step_many): every later
+ * reset/step also writes the features of the observation it returns, fused into the same kernel. */
+int wab_vec_bind_features(WabVec *h, uint8_t *d_features);
+/* The same features for an arbitrary observation batch already in HBM (replaces
+ * PragmaticObsWrapper.observation, wab_env.py:726-761). */
+int wab_pragmatic_features(const uint8_t *d_grids, const uint8_t *d_food, const uint8_t *d_role,
+                           const uint8_t *d_status, int64_t n, uint8_t *d_features, void *stream);
+/* gym.spaces.flatten of the wrapper observation (actor_critic.py:188): f32[n_rows][wab_vec_flat_dim]
+ * one-hot vectors (449 for default options) including the role's view mask. */
+int wab_vec_flatten_features(WabVec *h, const uint8_t *d_features, int64_t n_rows, float *d_out, void *stream);
+int wab_vec_flat_dim(const WabVec *h);
 
 /* Raw Philox4x32-10 on the device for n counters (cross-checks the RNG contract). d_ctr u32[n][4],
  * d_out u32[n][4]. */

@@ -18,6 +18,7 @@ def build(force=False):
     srcs = [os.path.join(_HERE, "hostsim.cpp"),
             os.path.join(_REPO, "wab_gym_b200", "csrc", "wab_core.cuh"),
             os.path.join(_REPO, "wab_gym_b200", "csrc", "wab_params.h"),
+            os.path.join(_REPO, "wab_gym_b200", "csrc", "wab_features.cuh"),
             os.path.join(_REPO, "include", "wab_b200.h")]
     if not force and os.path.exists(_LIB) and os.path.getmtime(_LIB) >= max(map(os.path.getmtime, srcs)):
         return _LIB
@@ -37,6 +38,8 @@ def lib():
         L.hostsim_reset.argtypes = [ctypes.c_void_p] * 6
         L.hostsim_step.argtypes = [ctypes.c_void_p, ctypes.c_int32] + [ctypes.c_void_p] * 8
         L.hostsim_state.argtypes = [ctypes.c_void_p] * 5
+        L.hostsim_features.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                       ctypes.c_void_p]
         L.hostsim_philox.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p]
         _lib = L
     return _lib
@@ -89,4 +92,13 @@ def philox(ctr, key):
     c = np.ascontiguousarray(ctr, dtype=np.uint32)
     out = np.zeros(4, dtype=np.uint32)
     lib().hostsim_philox(c.ctypes.data, int(key[0]), int(key[1]), out.ctypes.data)
+    return out
+
+
+def features(wolf_grid, bush_grid, food, role, status):
+    """PragmaticObsWrapper features (28 bytes) of one observation, through the kernel header."""
+    w = np.ascontiguousarray(np.asarray(wolf_grid) != 0, dtype=np.uint8)
+    b = np.ascontiguousarray(np.asarray(bush_grid) != 0, dtype=np.uint8)
+    out = np.zeros(28, dtype=np.uint8)
+    lib().hostsim_features(w.ctypes.data, b.ctypes.data, int(food), int(role), int(status), out.ctypes.data)
     return out

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../wab_gym_b200/csrc/wab_core.cuh"
+#include "../../wab_gym_b200/csrc/wab_features.cuh"
 #include "../../wab_gym_b200/csrc/wab_params.h"
 
 using namespace wab;
@@ -28,9 +29,11 @@ struct HostSim {
     bool f64;
 };
 
-static void expand_obs(const HostSim* h, const uint32_t wm[4], const uint32_t bm[4], uint32_t role, uint8_t* grids) {
-    uint32_t B[12];
-    compose_obs(h->P, wm, bm, role, B);
+static void expand_obs(const HostSim* h, const uint32_t wm_in[4], const uint32_t bm_in[4], uint32_t role, uint8_t* grids) {
+    uint32_t B[12], wm[4], bm[4];
+    for (int w = 0; w < 4; ++w) { wm[w] = wm_in[w]; bm[w] = bm_in[w]; }
+    apply_view_mask(h->P, role, wm, bm);
+    compose_obs(wm, bm, B);
     B[11] = 0u;   // bits 352..362 (last ostrich row) are never set
     for (int b = 0; b < OBS_BYTES; ++b) grids[b] = (uint8_t)((B[b >> 5] >> (b & 31)) & 1u);
 }
@@ -122,6 +125,19 @@ void hostsim_state(const HostSim* h, int32_t* scal9, double* food, int32_t* wolv
         wolves_xy[2 * k] = unpack_x(h->S.wolves[k]); wolves_xy[2 * k + 1] = unpack_y(h->S.wolves[k]);
     }
     for (int w = 0; w < 4; ++w) bush_mask[w] = E.m[w];
+}
+
+// PragmaticObsWrapper features from two observed 11x11 grids (row-major u8), wab_env.py:726-761
+void hostsim_features(const uint8_t* wolf_grid, const uint8_t* bush_grid, int32_t food, int32_t role, int32_t status,
+                      uint8_t* out28) {
+    uint32_t wm[4] = {0, 0, 0, 0}, bm[4] = {0, 0, 0, 0};
+    for (int c = 0; c < CELLS; ++c) {
+        if (wolf_grid[c]) wm[c >> 5] |= 1u << (c & 31);
+        if (bush_grid[c]) bm[c >> 5] |= 1u << (c & 31);
+    }
+    uint32_t f[7];
+    pragmatic_features(wm, bm, (uint32_t)food, (uint32_t)role, (uint32_t)status, f);
+    memcpy(out28, f, 28);
 }
 
 void hostsim_philox(const uint32_t* ctr, uint32_t k0, uint32_t k1, uint32_t* out) {

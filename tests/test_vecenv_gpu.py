@@ -242,6 +242,13 @@ def test_host_buffer_path_and_masked_reset():
         o, r, d, i = b.step(torch.from_numpy(acts).cuda())
         assert np.array_equal(hb["grids"].numpy(), o.grids.cpu().numpy()) and np.array_equal(hb["reward"].numpy(), r.cpu().numpy())
         assert np.array_equal(hb["done"].numpy().astype(bool), d.cpu().numpy()) and np.array_equal(hb["food"].numpy(), o.food.cpu().numpy())
+    # the seven-pointer entry point (no packed block) gives the same answers
+    loose = {k: v.clone() for k, v in hb.items() if k != "block"}
+    acts = rng.integers(0, 5, n).astype(np.uint8)
+    loose["actions"].copy_(torch.from_numpy(acts))
+    a.step_host(loose)
+    o, r, d, i = b.step(torch.from_numpy(acts).cuda())
+    assert np.array_equal(loose["grids"].numpy(), o.grids.cpu().numpy()) and np.array_equal(loose["reward"].numpy(), r.cpu().numpy())
     # masked reset: only the selected envs start a new episode
     before = b.export_state()
     mask = torch.zeros(n, dtype=torch.uint8, device="cuda")
@@ -272,4 +279,46 @@ def test_unaligned_or_missing_buffers_are_rejected():
     bad = _lib.WabObs(env._out["grids"].data_ptr() + 1, env._out["food"].data_ptr(), env._out["role"].data_ptr(),
                       env._out["status"].data_ptr())
     assert L.wab_vec_reset(env._h, None, bad, None) == 2
+    env.close()
+
+
+def _ref_features(grids, food, role, status):
+    """PragmaticObsWrapper features through the host build of the same header (itself pinned to the
+    reference's known-answer tests and wrapper in tests/test_features.py)."""
+    from tests import hostsim
+    return hostsim.features(grids[0], grids[1], food, role, status)
+
+
+@pytest.mark.parametrize("name", ["defaults", "restrict_view", "dense"])
+def test_fused_and_standalone_features(name):
+    overrides, greedy = OPTION_SETS[name]
+    n, steps = 130, 60
+    env = _vec(n, overrides, seed=21, features=True, wolf_cap=15)
+    rng = np.random.default_rng(6)
+    obs = env.reset()
+    feats = env.last_features
+    for t in range(steps):
+        g, f, r, s = (x.cpu().numpy() for x in obs)
+        fused = feats.cpu().numpy()
+        alone = env.pragmatic_features(obs).cpu().numpy()
+        assert np.array_equal(fused, alone), t
+        for i in range(0, n, 7):
+            assert np.array_equal(fused[i], _ref_features(g[i], int(f[i]), int(r[i]), int(s[i]))), (t, i)
+        flat = env.flatten_features(feats).cpu().numpy()
+        assert flat.shape == (n, env.flat_dim) and env.flat_dim == 408 + int(env.game_options["turns_to_empty_food"]) + 1
+        i = int(rng.integers(0, n))
+        want = []
+        for k in range(24):
+            oh = np.zeros(12 if (k % 12) < 8 else 11, np.float32); oh[fused[i][k]] = 1; want.append(oh)
+        for k, dim in ((24, 2), (25, env.flat_dim - 408), (26, 2), (27, 3)):
+            oh = np.zeros(dim, np.float32); oh[fused[i][k]] = 1; want.append(oh)
+        from wab_gym_b200.config import GATHERER_TILE_MASK, LOOKOUT_TILE_MASK
+        vm = np.zeros(121, np.float32)
+        if env.game_options["restrict_view"]:
+            vm = (GATHERER_TILE_MASK if r[i] == 1 else LOOKOUT_TILE_MASK).reshape(-1).astype(np.float32)
+        want.append(vm)
+        assert np.array_equal(flat[i], np.concatenate(want)), (t, i)
+        acts = np.array([pick_action(rng, g[j], env.n_actions, greedy) for j in range(n)], dtype=np.uint8)
+        obs, _, _, info = env.step(torch.from_numpy(acts).cuda())
+        feats = info["features"]
     env.close()

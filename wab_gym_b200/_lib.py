@@ -14,7 +14,8 @@ _lib = None
 EXPORTS = [
     "wab_vec_create", "wab_vec_reset", "wab_vec_step", "wab_vec_step_many", "wab_vec_step_host",
     "wab_vec_reset_host", "wab_vec_stats", "wab_vec_stats_device", "wab_vec_export_state", "wab_vec_num_envs", "wab_vec_lanes_per_env",
-    "wab_vec_destroy", "wab_philox_device", "wab_last_error", "wab_abi_version",
+    "wab_vec_destroy", "wab_philox_device", "wab_vec_bind_features", "wab_pragmatic_features",
+    "wab_vec_flatten_features", "wab_vec_flat_dim", "wab_vec_host_block_layout", "wab_vec_step_host_packed", "wab_last_error", "wab_abi_version",
 ]
 
 
@@ -49,6 +50,8 @@ def load():
     L.wab_vec_step_many.argtypes = [vp, i32, vp, WabObs, vp, vp, vp, vp]
     L.wab_vec_step_host.argtypes = [vp] * 10
     L.wab_vec_reset_host.argtypes = [vp] * 6
+    L.wab_vec_host_block_layout.argtypes = [vp, vp, vp]
+    L.wab_vec_step_host_packed.argtypes = [vp, vp, vp, vp]
     L.wab_vec_stats.argtypes = [vp, vp, i32, vp]
     L.wab_vec_stats_device.argtypes = [vp, vp, vp]
     L.wab_vec_export_state.argtypes = [vp] * 14
@@ -58,11 +61,16 @@ def load():
     L.wab_vec_lanes_per_env.restype = i32
     L.wab_vec_destroy.argtypes = [vp]
     L.wab_vec_destroy.restype = None
+    L.wab_vec_bind_features.argtypes = [vp, vp]
+    L.wab_pragmatic_features.argtypes = [vp, vp, vp, vp, i64, vp, vp]
+    L.wab_vec_flatten_features.argtypes = [vp, vp, i64, vp, vp]
+    L.wab_vec_flat_dim.argtypes = [vp]
+    L.wab_vec_flat_dim.restype = i32
     L.wab_philox_device.argtypes = [vp, ctypes.c_uint32, ctypes.c_uint32, i64, vp, vp]
     L.wab_last_error.restype = ctypes.c_char_p
     L.wab_abi_version.restype = i32
     for name in EXPORTS:
-        if name not in ("wab_vec_num_envs", "wab_vec_lanes_per_env", "wab_vec_destroy", "wab_last_error", "wab_abi_version"):
+        if name not in ("wab_vec_num_envs", "wab_vec_lanes_per_env", "wab_vec_flat_dim", "wab_vec_destroy", "wab_last_error", "wab_abi_version"):
             getattr(L, name).restype = ctypes.c_int
     _lib = L
     return L

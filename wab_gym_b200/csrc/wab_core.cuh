@@ -524,15 +524,9 @@ WAB_HD void reset_scalars(const Params& P, Env& E) {
 }
 
 // 363-bit observation string of one env as 11 words (bits 0..120 wolves, 121..241 bushes,
-// 242..362 ostriches; bit 302 = ostrich [5][5], never masked). mask_grid: wab_env.py:344-357.
-WAB_HD void compose_obs(const Params& P, const uint32_t wm_in[4], const uint32_t bm_in[4], uint32_t role,
-                        uint32_t B[11]) {
-    uint32_t wm[4], bm[4];
-    for (int w = 0; w < 4; ++w) {
-        uint32_t blind = P.restrict_view ? (role == 1u ? P.mask_gath[w] : P.mask_look[w]) : 0u;
-        wm[w] = wm_in[w] & ~blind;
-        bm[w] = bm_in[w] & ~blind;
-    }
+// 242..362 ostriches; bit 302 = ostrich [5][5], never masked). wm / bm are the planes as observed
+// (mask_grid, wab_env.py:344-357, already applied by apply_view_mask).
+WAB_HD void compose_obs(const uint32_t wm[4], const uint32_t bm[4], uint32_t B[11]) {
     B[0] = wm[0]; B[1] = wm[1]; B[2] = wm[2];
     B[3] = wm[3] | (bm[0] << 25);                  // 121 = 3*32 + 25
     B[4] = (bm[0] >> 7) | (bm[1] << 25);
@@ -542,6 +536,14 @@ WAB_HD void compose_obs(const Params& P, const uint32_t wm_in[4], const uint32_t
     B[8] = 0u;
     B[9] = 1u << 14;                               // 242 + 60 = 302 = 9*32 + 14
     B[10] = 0u;
+}
+
+WAB_HD void apply_view_mask(const Params& P, uint32_t role, uint32_t wm[4], uint32_t bm[4]) {   // mask_grid :344-357
+    if (!P.restrict_view) return;
+    for (int w = 0; w < 4; ++w) {
+        const uint32_t blind = role == 1u ? P.mask_gath[w] : P.mask_look[w];
+        wm[w] &= ~blind; bm[w] &= ~blind;
+    }
 }
 
 }  // namespace wab

@@ -22,13 +22,19 @@
 
 #include "../../include/wab_b200.h"
 #include "wab_core.cuh"
+#include "wab_features.cuh"
 #include "wab_params.h"
 
 using namespace wab;
 
+#ifndef WAB_FLUSH_UNROLL
+#define WAB_FLUSH_UNROLL 2
+#endif
+
 namespace {
 
 constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr int kFlushUnroll = WAB_FLUSH_UNROLL;
 #ifndef WAB_MIN_BLOCKS_LPEN
 #define WAB_MIN_BLOCKS_LPEN 1         // lanes-per-env kernels: no register cap (one wave of few CTAs anyway)
 #endif
@@ -54,6 +60,7 @@ struct StatePtrs {
 struct OutPtrs {
     uint8_t* grids; uint8_t* food; uint8_t* role; uint8_t* status;
     float* reward; uint8_t* done; uint8_t* info;
+    uint8_t* features;   // optional [..][28] PragmaticObsWrapper features (wab_features.cuh)
 };
 
 template <bool F64>
@@ -157,11 +164,11 @@ struct WarpStream {
     static constexpr int WORDS = (EPW * OBS_BYTES + 15 + 31) / 32 + 1;
 };
 
-__device__ __forceinline__ void stream_put(const Params& P, uint32_t* stream, int bit0, bool last, int total_bits,
-                                           const uint32_t wm[4], const uint32_t bm[4], uint32_t role, bool active) {
+__device__ __forceinline__ void stream_put(uint32_t* stream, int bit0, bool last, int total_bits,
+                                           const uint32_t wm[4], const uint32_t bm[4], bool active) {
     uint32_t B[11];
     if (active) {
-        compose_obs(P, wm, bm, role, B);
+        compose_obs(wm, bm, B);
     } else {
 #pragma unroll
         for (int k = 0; k < 11; ++k) B[k] = 0u;
@@ -179,18 +186,16 @@ __device__ __forceinline__ void stream_put(const Params& P, uint32_t* stream, in
 }
 
 // gA = 16-byte aligned address of stream bit 0; valid bits are [off, end).
-__device__ __forceinline__ void stream_flush(const uint32_t* stream, uint8_t* gA, int off, int end, int lane) {
+// `lut` = 256 x uint2 in shared memory: byte value -> its 8 bits as 8 bytes (built once per CTA).
+__device__ __forceinline__ void stream_flush(const uint32_t* stream, const uint2* lut, uint8_t* gA, int off, int end,
+                                             int lane) {
     const uint16_t* hs = reinterpret_cast<const uint16_t*>(stream);
     const int c_lo = (off + 15) >> 4, c_hi = end >> 4;            // chunks entirely inside [off, end)
-#pragma unroll 1
+#pragma unroll kFlushUnroll
     for (int c = c_lo + lane; c < c_hi; c += 32) {
         const uint32_t h = hs[c];
-        uint4 v;
-        v.x = nibble_to_bytes(h & 15u);
-        v.y = nibble_to_bytes((h >> 4) & 15u);
-        v.z = nibble_to_bytes((h >> 8) & 15u);
-        v.w = nibble_to_bytes(h >> 12);
-        __stcs(reinterpret_cast<uint4*>(gA) + c, v);
+        const uint2 lo = lut[h & 0xFFu], hi = lut[h >> 8];
+        __stcs(reinterpret_cast<uint4*>(gA) + c, make_uint4(lo.x, lo.y, hi.x, hi.y));
     }
     if (lane < 16) {                                              // ragged head and tail, one byte per lane
         const int head_end = min(c_lo << 4, end);
@@ -210,6 +215,15 @@ __device__ __forceinline__ void write_scalars(const OutPtrs& out, int64_t o, con
     if (out.info) out.info[o] = (uint8_t)O.info;
 }
 
+// PragmaticObsWrapper features of the observation just produced: 28 bytes = 7 words per env
+__device__ __forceinline__ void write_features(uint8_t* features, int64_t o, const StepOut& O) {
+    uint32_t f[7];
+    pragmatic_features(O.wm, O.bm, O.food_obs, O.role, O.status, f);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(features + o * FEAT_BYTES);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) dst[k] = f[k];
+}
+
 __device__ __forceinline__ void flush_stats(unsigned long long* stats, const uint32_t c[8], uint32_t* block_s) {
     // warp redux -> shared atomics -> 8 global atomics per block
     if (threadIdx.x < 8) block_s[threadIdx.x] = 0u;
@@ -223,12 +237,18 @@ __device__ __forceinline__ void flush_stats(unsigned long long* stats, const uin
     if (threadIdx.x < 8 && block_s[threadIdx.x]) atomicAdd(&stats[threadIdx.x], (unsigned long long)block_s[threadIdx.x]);
 }
 
+__device__ __forceinline__ void build_lut(uint2* lut) {
+    for (int b = threadIdx.x; b < 256; b += blockDim.x)
+        lut[b] = make_uint2(nibble_to_bytes((uint32_t)b & 15u), nibble_to_bytes((uint32_t)b >> 4));
+    __syncthreads();
+}
+
 // Geometry: 128-thread CTAs for every lanes-per-env factor; a warp owns EPW = 32 / LPE envs.
 template <int LPE> struct Geo {
     static constexpr int THREADS = 128;
     static constexpr int EPW = 32 / LPE;
     static constexpr int EPB = THREADS / LPE;
-    static constexpr int STREAM = (THREADS / 32) * WarpStream<EPW>::WORDS;
+    static constexpr int STREAM = ((THREADS / 32) * WarpStream<EPW>::WORDS + 1) & ~1;   // even: keeps the LUT 8-byte aligned
     static constexpr int MIN_BLOCKS = LPE == 1 ? WAB_MIN_BLOCKS_LPE1 : WAB_MIN_BLOCKS_LPEN;
 };
 
@@ -260,15 +280,15 @@ __device__ __forceinline__ Ctx make_ctx(int64_t n) {
 // Publish the warp's observations for one step; `first_byte` = byte offset of the warp's first env
 // in the grids tensor (any alignment).
 template <int LPE>
-__device__ __forceinline__ void emit_obs(const Params& P, uint32_t* stream, const Ctx& c, uint8_t* grids,
-                                         int64_t first_byte, const uint32_t wm[4], const uint32_t bm[4], uint32_t role) {
+__device__ __forceinline__ void emit_obs(uint32_t* stream, const uint2* lut, const Ctx& c, uint8_t* grids,
+                                         int64_t first_byte, const uint32_t wm[4], const uint32_t bm[4]) {
     constexpr int EPW = Geo<LPE>::EPW;
     const int off = (int)(first_byte & 15);
     const int total = off + EPW * OBS_BYTES;
     if (c.sub == 0)
-        stream_put(P, stream, off + OBS_BYTES * c.slot, c.slot == EPW - 1, total, wm, bm, role, c.active);
+        stream_put(stream, off + OBS_BYTES * c.slot, c.slot == EPW - 1, total, wm, bm, c.active);
     __syncwarp();
-    stream_flush(stream, grids + (first_byte - off), off, off + OBS_BYTES * c.n_valid, c.lane);
+    stream_flush(stream, lut, grids + (first_byte - off), off, off + OBS_BYTES * c.n_valid, c.lane);
     __syncwarp();
 }
 
@@ -284,6 +304,8 @@ wab_step_kernel(const __grid_constant__ Params P, const StatePtrs st, const uint
     uint32_t* wolves_s = smem + c.env_local;                                  // [wolf_cap][EPB]
     uint32_t* stream = smem + P.wolf_cap * EPB + (threadIdx.x >> 5) * WarpStream<Geo<LPE>::EPW>::WORDS;
     uint32_t* block_s = smem + P.wolf_cap * EPB + Geo<LPE>::STREAM;            // 8 words
+    uint2* lut = reinterpret_cast<uint2*>(block_s + 8);                        // 256 x 8 bytes
+    build_lut(lut);
     Coop<LPE> coop;
     coop.sub = (uint32_t)c.sub;
     coop.gmask = LPE == 32 ? FULL : (((1u << (LPE & 31)) - 1u) << (c.lane - c.sub));
@@ -295,25 +317,24 @@ wab_step_kernel(const __grid_constant__ Params P, const StatePtrs st, const uint
     if (c.active) load_env<F64>(P, st, c.idx, E, wolves_s, EPB);
     else { E = Env(); }
 
-    uint32_t cnt[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-    uint32_t a_next = c.active ? actions[c.idx] : 0u;
-    for (int t = 0; t < n_steps; ++t) {
+    // statistics as packed 16-bit fields (n_steps <= 65535): one 64-bit add per step instead of seven
+    unsigned long long acc_outcome = 0ull;   // [alive, finished, starved, killed] counts
+    unsigned long long acc_misc = 0ull;      // [eats, bad actions, overflows]
+    const uint8_t* ap = actions + (c.active ? c.idx : 0);
+    uint32_t a_next = c.active ? *ap : 0u;
+    int64_t o = c.idx;                                   // index of this env in the [T][N] outputs
+    int64_t first_byte = c.warp_first * OBS_BYTES;       // byte offset of the warp's slab in the grids tensor
+    for (int t = 0; t < n_steps; ++t, o += n, first_byte += n * OBS_BYTES) {
         StepOut O;
         bool need_reset = false;
         const uint32_t a = a_next;
-        if (c.active && t + 1 < n_steps) a_next = actions[(int64_t)(t + 1) * n + c.idx];   // prefetch: off the critical path
+        ap += n;
+        if (c.active && t + 1 < n_steps) a_next = *ap;   // prefetch: off the critical path
         if (c.active) {
             env_step<F64, LPE>(P, E, S, a, O, coop);
             need_reset = O.done && P.auto_reset;
-            if (c.sub == 0) {
-                cnt[WAB_STAT_EPISODES] += O.done;  // auto_reset = 0: every step that reports done counts
-                cnt[WAB_STAT_STEPS] += 1u;
-                cnt[WAB_STAT_FINISHED] += (O.outcome == 1u) ? 1u : 0u;
-                cnt[WAB_STAT_STARVED] += (O.outcome == 2u) ? 1u : 0u;
-                cnt[WAB_STAT_KILLED] += (O.outcome == 3u) ? 1u : 0u;
-                cnt[WAB_STAT_EATS] += O.ate;
-                cnt[WAB_STAT_BAD_ACTIONS] += O.bad_action;
-            }
+            acc_outcome += 1ull << (16u * O.outcome);    // auto_reset = 0: every step that reports done counts
+            acc_misc += (unsigned long long)O.ate | ((unsigned long long)O.bad_action << 16);
         } else {
             O = StepOut();
         }
@@ -324,13 +345,26 @@ wab_step_kernel(const __grid_constant__ Params P, const StatePtrs st, const uint
                 O.role = E.role; O.status = E.status;
             }
         }
+        apply_view_mask(P, O.role, O.wm, O.bm);            // mask_grid, wab_env.py:344-357
         if (c.writer) {
-            cnt[WAB_STAT_OVERFLOWS] += O.overflow;
-            write_scalars(out, (int64_t)t * n + c.idx, O);
+            acc_misc += (unsigned long long)O.overflow << 32;
+            write_scalars(out, o, O);
+            if (out.features) write_features(out.features, o, O);
         }
-        emit_obs<LPE>(P, stream, c, out.grids, ((int64_t)t * n + c.warp_first) * OBS_BYTES, O.wm, O.bm, O.role);
+        emit_obs<LPE>(stream, lut, c, out.grids, first_byte, O.wm, O.bm);
     }
     if (c.writer) store_env<F64>(st, c.idx, E, wolves_s, EPB);
+    uint32_t cnt[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    if (c.writer) {
+        const uint32_t fin = (uint32_t)(acc_outcome >> 16) & 0xFFFFu, sta = (uint32_t)(acc_outcome >> 32) & 0xFFFFu,
+                       kil = (uint32_t)(acc_outcome >> 48) & 0xFFFFu;
+        cnt[WAB_STAT_EPISODES] = fin + sta + kil;
+        cnt[WAB_STAT_STEPS] = (uint32_t)n_steps;
+        cnt[WAB_STAT_FINISHED] = fin; cnt[WAB_STAT_STARVED] = sta; cnt[WAB_STAT_KILLED] = kil;
+        cnt[WAB_STAT_EATS] = (uint32_t)acc_misc & 0xFFFFu;
+        cnt[WAB_STAT_BAD_ACTIONS] = (uint32_t)(acc_misc >> 16) & 0xFFFFu;
+        cnt[WAB_STAT_OVERFLOWS] = (uint32_t)(acc_misc >> 32) & 0xFFFFu;
+    }
     flush_stats(st.stats, cnt, block_s);
 }
 
@@ -346,6 +380,8 @@ wab_reset_kernel(const __grid_constant__ Params P, const StatePtrs st, const uin
     uint32_t* wolves_s = smem + c.env_local;
     uint32_t* stream = smem + P.wolf_cap * EPB + (threadIdx.x >> 5) * WarpStream<Geo<LPE>::EPW>::WORDS;
     uint32_t* block_s = smem + P.wolf_cap * EPB + Geo<LPE>::STREAM;
+    uint2* lut = reinterpret_cast<uint2*>(block_s + 8);
+    build_lut(lut);
     Env E;
     Slots S;
     S.wolves = wolves_s; S.wstride = EPB;
@@ -364,13 +400,64 @@ wab_reset_kernel(const __grid_constant__ Params P, const StatePtrs st, const uin
         O.food_obs = food_observation(P, E, F64);
         O.role = E.role; O.status = E.status;
     }
+    apply_view_mask(P, O.role, O.wm, O.bm);
     if (c.writer) {
         out.food[c.idx] = (uint8_t)O.food_obs; out.role[c.idx] = (uint8_t)O.role; out.status[c.idx] = (uint8_t)O.status;
+        if (out.features) write_features(out.features, c.idx, O);
         cnt[WAB_STAT_OVERFLOWS] += O.overflow;
         store_env<F64>(st, c.idx, E, wolves_s, EPB);
     }
-    emit_obs<LPE>(P, stream, c, out.grids, c.warp_first * OBS_BYTES, O.wm, O.bm, O.role);
+    emit_obs<LPE>(stream, lut, c, out.grids, c.warp_first * OBS_BYTES, O.wm, O.bm);
     flush_stats(st.stats, cnt, block_s);
+}
+
+// PragmaticObsWrapper.observation (wab_env.py:726-761) for an arbitrary observation batch in HBM.
+__global__ void wab_features_kernel(const uint8_t* __restrict__ grids, const uint8_t* __restrict__ food,
+                                    const uint8_t* __restrict__ role, const uint8_t* __restrict__ status, int64_t n,
+                                    uint8_t* __restrict__ features) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    StepOut O = StepOut();
+    const uint8_t* g = grids + i * OBS_BYTES;
+    for (int c = 0; c < CELLS; ++c) {
+        O.wm[c >> 5] |= (g[c] ? 1u : 0u) << (c & 31);
+        O.bm[c >> 5] |= (g[CELLS + c] ? 1u : 0u) << (c & 31);
+    }
+    O.food_obs = food[i]; O.role = role[i]; O.status = status[i];
+    write_features(features, i, O);
+}
+
+// gym.spaces.flatten of the wrapper's observation space (wab_env.py:710-724, actor_critic.py:188):
+// one-hot of every Discrete, then the 121-cell view mask. One thread per output element.
+__global__ void wab_flatten_kernel(const __grid_constant__ Params P, const uint8_t* __restrict__ features, int64_t rows,
+                                   int food_dim, float* __restrict__ outp) {
+    const int dim = 2 * (2 * 4 * (MAX_DISTANCE + 1) + 4 * 11) + 2 + food_dim + 2 + 3 + CELLS;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= rows * dim) return;
+    const int64_t row = e / dim;
+    int k = (int)(e - row * dim);
+    const uint8_t* f = features + row * FEAT_BYTES;
+    float v = 0.f;
+    bool found = false;
+#pragma unroll
+    for (int species = 0; species < 2 && !found; ++species) {
+        const int base = species * 12;
+        if (k < 96) { v = f[base + k / 12] == k % 12 ? 1.f : 0.f; found = true; }              // nearest, second: 8 x one-hot(12)
+        else if (k < 140) { v = f[base + 8 + (k - 96) / 11] == (k - 96) % 11 ? 1.f : 0.f; found = true; }   // counts: 4 x one-hot(11)
+        else k -= 140;
+    }
+    if (!found) {
+        if (k < 2) v = f[24] == k ? 1.f : 0.f;
+        else if (k < 2 + food_dim) v = f[25] == k - 2 ? 1.f : 0.f;
+        else if (k < 4 + food_dim) v = f[26] == k - 2 - food_dim ? 1.f : 0.f;
+        else if (k < 7 + food_dim) v = f[27] == k - 4 - food_dim ? 1.f : 0.f;
+        else {                                                                                   // view mask (obs[6])
+            const int c = k - 7 - food_dim;
+            const uint32_t w = P.restrict_view ? (f[26] == 1 ? P.mask_gath[c >> 5] : P.mask_look[c >> 5]) : 0u;
+            v = (float)((w >> (c & 31)) & 1u);
+        }
+    }
+    outp[e] = v;
 }
 
 __global__ void wab_philox_kernel(const __grid_constant__ Params P, const uint32_t* __restrict__ ctr, int64_t n,
@@ -415,12 +502,13 @@ struct WabVec {
     uint8_t* stage;
     size_t stage_bytes;
     int lpe;          // lanes per env chosen at create (see pick_lpe)
+    uint8_t* d_features;   // bound feature output, or null
 };
 
 namespace {
 
 template <int LPE> size_t smem_bytes_for(const Params& P) {
-    return sizeof(uint32_t) * ((size_t)P.wolf_cap * Geo<LPE>::EPB + (size_t)Geo<LPE>::STREAM + 8);
+    return sizeof(uint32_t) * ((size_t)P.wolf_cap * Geo<LPE>::EPB + (size_t)Geo<LPE>::STREAM + 8 + 512);
 }
 template <bool F64, int LPE>
 void launch_step_t(const WabVec* h, const uint8_t* a, int T, const OutPtrs& out, cudaStream_t s);
@@ -483,7 +571,7 @@ int pick_lpe(const WabVec* h) {
 
 int launch_step(WabVec* h, int n_steps, const uint8_t* d_actions, const WabObs& obs, float* d_reward,
                 uint8_t* d_done, uint8_t* d_info, cudaStream_t s) {
-    OutPtrs out{obs.d_grids, obs.d_food, obs.d_role, obs.d_status, d_reward, d_done, d_info};
+    OutPtrs out{obs.d_grids, obs.d_food, obs.d_role, obs.d_status, d_reward, d_done, d_info, h->d_features};
     WAB_DISPATCH(launch_step_t, h, d_actions, n_steps, out, s);
     WAB_CUDA(cudaGetLastError());
     return WAB_OK;
@@ -592,7 +680,7 @@ int wab_vec_reset(WabVec* h, const uint8_t* d_mask, WabObs obs, void* stream) {
     if (!h || !obs.d_grids || !obs.d_food || !obs.d_role || !obs.d_status) return fail(WAB_E_NULL, "null argument");
     if (int rc = check_ptr_align(obs.d_grids, "d_grids")) return rc;
     DeviceGuard guard(h->device);
-    OutPtrs out{obs.d_grids, obs.d_food, obs.d_role, obs.d_status, nullptr, nullptr, nullptr};
+    OutPtrs out{obs.d_grids, obs.d_food, obs.d_role, obs.d_status, nullptr, nullptr, nullptr, h->d_features};
     cudaStream_t s = (cudaStream_t)stream;
     WAB_DISPATCH(launch_reset_t, h, d_mask, out, s);
     WAB_CUDA(cudaGetLastError());
@@ -638,6 +726,30 @@ int wab_vec_step_host(WabVec* h, const uint8_t* h_actions, uint8_t* h_grids, uin
     WAB_CUDA(cudaMemcpyAsync(h_reward, b + L.reward, n * 4, cudaMemcpyDeviceToHost, s));
     WAB_CUDA(cudaMemcpyAsync(h_done, b + L.done, n, cudaMemcpyDeviceToHost, s));
     if (h_info) WAB_CUDA(cudaMemcpyAsync(h_info, b + L.info, n, cudaMemcpyDeviceToHost, s));
+    WAB_CUDA(cudaStreamSynchronize(s));
+    return WAB_OK;
+}
+
+int wab_vec_host_block_layout(const WabVec* h, int64_t* offsets7, int64_t* total_bytes) {
+    if (!h || !offsets7 || !total_bytes) return fail(WAB_E_NULL, "null argument");
+    const StageLayout L = stage_layout(h->n);
+    const size_t v[7] = {L.grids, L.food, L.role, L.status, L.reward, L.done, L.info};
+    for (int k = 0; k < 7; ++k) offsets7[k] = (int64_t)(v[k] - L.grids);
+    *total_bytes = (int64_t)(L.total - L.grids);
+    return WAB_OK;
+}
+
+int wab_vec_step_host_packed(WabVec* h, const uint8_t* h_actions, uint8_t* h_block, void* stream) {
+    if (!h || !h_actions || !h_block) return fail(WAB_E_NULL, "null argument");
+    DeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const StageLayout L = stage_layout(h->n);
+    if (int rc = ensure_stage(h, L.total)) return rc;
+    uint8_t* b = h->stage;
+    WAB_CUDA(cudaMemcpyAsync(b + L.actions, h_actions, (size_t)h->n, cudaMemcpyHostToDevice, s));
+    WabObs obs{b + L.grids, b + L.food, b + L.role, b + L.status};
+    if (int rc = launch_step(h, 1, b + L.actions, obs, (float*)(b + L.reward), b + L.done, b + L.info, s)) return rc;
+    WAB_CUDA(cudaMemcpyAsync(h_block, b + L.grids, L.total - L.grids, cudaMemcpyDeviceToHost, s));   // one transfer
     WAB_CUDA(cudaStreamSynchronize(s));
     return WAB_OK;
 }
@@ -731,6 +843,38 @@ int wab_vec_export_state(WabVec* h, int32_t* x, int32_t* y, double* food, int32_
     delete[] pos; delete[] misc; delete[] ep; delete[] bush; delete[] nl; delete[] fd;
     delete[] wv; delete[] lcell; delete[] lcnt;
     if (e != cudaSuccess) return cuda_fail(e, "export_state");
+    return WAB_OK;
+}
+
+int wab_vec_bind_features(WabVec* h, uint8_t* d_features) {
+    if (!h) return fail(WAB_E_NULL, "null argument");
+    if (((uintptr_t)d_features & 3u) != 0) return fail(WAB_E_CONFIG, "d_features must be 4-byte aligned");
+    h->d_features = d_features;
+    return WAB_OK;
+}
+
+int wab_vec_flat_dim(const WabVec* h) {
+    return h ? 2 * (2 * 4 * (MAX_DISTANCE + 1) + 4 * 11) + 2 + ((int)h->cfg.food_obs_scale + 1) + 2 + 3 + CELLS : 0;
+}
+
+int wab_pragmatic_features(const uint8_t* d_grids, const uint8_t* d_food, const uint8_t* d_role, const uint8_t* d_status,
+                           int64_t n, uint8_t* d_features, void* stream) {
+    if (!d_grids || !d_food || !d_role || !d_status || !d_features) return fail(WAB_E_NULL, "null argument");
+    if (((uintptr_t)d_features & 3u) != 0) return fail(WAB_E_CONFIG, "d_features must be 4-byte aligned");
+    if (n <= 0) return WAB_OK;
+    wab_features_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(d_grids, d_food, d_role, d_status, n, d_features);
+    WAB_CUDA(cudaGetLastError());
+    return WAB_OK;
+}
+
+int wab_vec_flatten_features(WabVec* h, const uint8_t* d_features, int64_t n_rows, float* d_out, void* stream) {
+    if (!h || !d_features || !d_out) return fail(WAB_E_NULL, "null argument");
+    if (n_rows <= 0) return WAB_OK;
+    DeviceGuard guard(h->device);
+    const int64_t total = n_rows * wab_vec_flat_dim(h);
+    wab_flatten_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        h->P, d_features, n_rows, (int)h->cfg.food_obs_scale + 1, d_out);
+    WAB_CUDA(cudaGetLastError());
     return WAB_OK;
 }
 

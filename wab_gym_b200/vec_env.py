@@ -42,7 +42,7 @@ def _ptr(t: Optional[torch.Tensor]):
 class VecEnv:
     def __init__(self, num_envs: int, game_options: Optional[dict] = None, device="cuda", seed: int = 0,
                  env_id_base: int = 0, auto_reset: bool = True, wolf_cap: int = 8, log_cap: Optional[int] = None,
-                 force_f64_food: bool = False):
+                 force_f64_food: bool = False, features: bool = False):
         self._h = None
         self.lib = _lib.load()  # raises if the CUDA library is unavailable — no fallback
         self.device = torch.device(device)
@@ -64,6 +64,8 @@ class VecEnv:
                                            ctypes.byref(handle)))
         self._h = handle
         self.lanes_per_env = int(self.lib.wab_vec_lanes_per_env(self._h))
+        self.with_features = bool(features)
+        self.flat_dim = int(self.lib.wab_vec_flat_dim(self._h))
         self._out = self._alloc(None)
         self._many: Dict[int, dict] = {}
 
@@ -72,7 +74,9 @@ class VecEnv:
         n, dev = self.num_envs, self.device
         lead = (n,) if steps is None else (steps, n)
         u8 = dict(dtype=torch.uint8, device=dev)
+        extra = {"features": torch.empty(lead + (28,), **u8)} if self.with_features else {}
         return {
+            **extra,
             "grids": torch.empty(lead + (3, 11, 11), **u8), "food": torch.empty(lead, **u8),
             "role": torch.empty(lead, **u8), "status": torch.empty(lead, **u8),
             "reward": torch.empty(lead, dtype=torch.float32, device=dev), "done": torch.empty(lead, **u8),
@@ -83,6 +87,16 @@ class VecEnv:
     def _obs_struct(buf) -> _lib.WabObs:
         return _lib.WabObs(buf["grids"].data_ptr(), buf["food"].data_ptr(), buf["role"].data_ptr(),
                            buf["status"].data_ptr())
+
+    def _bind(self, buf):
+        """Point the fused PragmaticObsWrapper feature output at this call's buffer (or switch it off)."""
+        _lib.check(self.lib.wab_vec_bind_features(self._h, _ptr(buf.get("features"))))
+
+    def _info(self, buf):
+        info = {"info": buf["info"]}
+        if "features" in buf:
+            info["features"] = buf["features"]
+        return info
 
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -106,6 +120,7 @@ class VecEnv:
             if mask.shape != (self.num_envs,):
                 raise ValueError("mask must have shape (num_envs,)")
         b = self._out
+        self._bind(b)
         _lib.check(self.lib.wab_vec_reset(self._h, _ptr(mask), self._obs_struct(b), self._stream()))
         return ObsBatch(b["grids"], b["food"], b["role"], b["status"])
 
@@ -114,10 +129,11 @@ class VecEnv:
         ``(ObsBatch, reward f32[N], done bool[N], info)``; tensors are reused by the next call."""
         a = self._actions_u8(actions, (self.num_envs,))
         b = self._out
+        self._bind(b)
         _lib.check(self.lib.wab_vec_step(self._h, _ptr(a), self._obs_struct(b), _ptr(b["reward"]), _ptr(b["done"]),
                                          _ptr(b["info"]), self._stream()))
         return (ObsBatch(b["grids"], b["food"], b["role"], b["status"]), b["reward"], b["done"].view(torch.bool),
-                {"info": b["info"]})
+                self._info(b))
 
     def step_many(self, actions: torch.Tensor, out: Optional[dict] = None):
         """T lockstep steps in one launch; ``actions`` u8[T, N]. Every step's observation, reward and
@@ -127,28 +143,67 @@ class VecEnv:
         b = out if out is not None else self._many.get(steps)
         if b is None:
             b = self._many[steps] = self._alloc(steps)
+        self._bind(b)
         _lib.check(self.lib.wab_vec_step_many(self._h, steps, _ptr(a), self._obs_struct(b), _ptr(b["reward"]),
                                               _ptr(b["done"]), _ptr(b["info"]), self._stream()))
         return (ObsBatch(b["grids"], b["food"], b["role"], b["status"]), b["reward"], b["done"].view(torch.bool),
-                {"info": b["info"]})
+                self._info(b))
+
+    # ------------------------------------------------------------------ PragmaticObsWrapper on the device
+    @property
+    def last_features(self) -> Optional[torch.Tensor]:
+        """u8[N, 28] features of the observation returned by the last reset()/step() (features=True)."""
+        return self._out.get("features")
+
+    def pragmatic_features(self, obs: ObsBatch) -> torch.Tensor:
+        """PragmaticObsWrapper.observation (wab_env.py:726-761) for any observation batch: u8[..., 28] =
+        nearest_wolf[4] second_wolf[4] n_wolves[4] nearest_bush[4] second_bush[4] n_bushes[4] standing food role status."""
+        lead = obs.food.shape
+        out = torch.empty(lead + (28,), dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.wab_pragmatic_features(_ptr(obs.grids.contiguous()), _ptr(obs.food.contiguous()),
+                                                   _ptr(obs.role.contiguous()), _ptr(obs.status.contiguous()),
+                                                   obs.food.numel(), _ptr(out), self._stream()))
+        return out
+
+    def flatten_features(self, features: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """gym.spaces.flatten of the wrapper observation (actor_critic.py:188): f32[..., flat_dim] one-hot
+        (449 columns under default options), including the role's view mask."""
+        features = features.contiguous()
+        lead = features.shape[:-1]
+        if out is None:
+            out = torch.empty(lead + (self.flat_dim,), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.wab_vec_flatten_features(self._h, _ptr(features), features.numel() // 28, _ptr(out),
+                                                     self._stream()))
+        return out
 
     # ------------------------------------------------------------------ host-buffer entry points
     def alloc_host_buffers(self, pinned: bool = True) -> dict:
+        """Host-side buffers for the host entry points: every output is a view into ONE (pinned) block laid out by
+        ``wab_vec_host_block_layout`` so a step needs a single device-to-host transfer."""
         n = self.num_envs
-        mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=pinned)
-        return {"actions": mk((n,), torch.uint8), "grids": mk((n, 3, 11, 11), torch.uint8), "food": mk((n,), torch.uint8),
-                "role": mk((n,), torch.uint8), "status": mk((n,), torch.uint8), "reward": mk((n,), torch.float32),
-                "done": mk((n,), torch.uint8), "info": mk((n,), torch.uint8)}
+        offs = np.zeros(7, dtype=np.int64)
+        total = ctypes.c_int64()
+        _lib.check(self.lib.wab_vec_host_block_layout(self._h, offs.ctypes.data, ctypes.addressof(total)))
+        block = torch.empty(total.value, dtype=torch.uint8, pin_memory=pinned)
+        view = lambda k, nbytes: block[int(offs[k]):int(offs[k]) + nbytes]
+        return {"actions": torch.empty(n, dtype=torch.uint8, pin_memory=pinned), "block": block,
+                "grids": view(0, n * 363).view(n, 3, 11, 11), "food": view(1, n), "role": view(2, n), "status": view(3, n),
+                "reward": view(4, 4 * n).view(torch.float32), "done": view(5, n), "info": view(6, n)}
 
     def step_host(self, hb: dict):
         """One step with HOST buffers (``hb`` from ``alloc_host_buffers``; ``hb['actions']`` filled by the
         caller): H2D actions, kernel, D2H of every output, stream sync — the whole C-ABI host path."""
-        _lib.check(self.lib.wab_vec_step_host(self._h, _ptr(hb["actions"]), _ptr(hb["grids"]), _ptr(hb["food"]),
-                                              _ptr(hb["role"]), _ptr(hb["status"]), _ptr(hb["reward"]),
-                                              _ptr(hb["done"]), _ptr(hb["info"]), self._stream()))
+        self._bind({})
+        if "block" in hb:
+            _lib.check(self.lib.wab_vec_step_host_packed(self._h, _ptr(hb["actions"]), _ptr(hb["block"]), self._stream()))
+        else:
+            _lib.check(self.lib.wab_vec_step_host(self._h, _ptr(hb["actions"]), _ptr(hb["grids"]), _ptr(hb["food"]),
+                                                  _ptr(hb["role"]), _ptr(hb["status"]), _ptr(hb["reward"]),
+                                                  _ptr(hb["done"]), _ptr(hb["info"]), self._stream()))
         return hb
 
     def reset_host(self, hb: dict):
+        self._bind({})
         _lib.check(self.lib.wab_vec_reset_host(self._h, _ptr(hb["grids"]), _ptr(hb["food"]), _ptr(hb["role"]),
                                                _ptr(hb["status"]), self._stream()))
         return hb
