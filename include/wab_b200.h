@@ -174,6 +174,35 @@ int wab_pragmatic_features(const uint8_t *d_grids, const uint8_t *d_food, const 
 int wab_vec_flatten_features(WabVec *h, const uint8_t *d_features, int64_t n_rows, float *d_out, void *stream);
 int wab_vec_flat_dim(const WabVec *h);
 
+/* ---- Environment 2.0 ("/root/reference/Environment 2.0"): a toroidal W x H world of ostriches, wolves and
+ * bushes per environment. One call = one world turn: every entity, in id order (ostriches, wolves, bushes),
+ * observes and acts exactly as the reference driver loop does (Env2Tests.py:46-88: get_obs(i), take_action(i)). */
+typedef struct Wab2Config {
+    int32_t abi_version;
+    int32_t width, height;                       /* World(width, height), World.py:141                              */
+    int32_t n_ostriches, n_wolves, n_bushes;     /* create_ostriches / wolves / bushes, WAB_Environment2.py:61-110  */
+    int32_t lookout_view_radius, gatherer_view_radius, wolf_view_radius;   /* WAB_Environment2.py:35-36, :49       */
+    int32_t window_radius;                       /* R of the (2R+1)^2 observation window (>= the largest radius)    */
+    int32_t starting_role;                       /* :19                                                             */
+    int32_t ostrich_starting_food;               /* :32 (integer-valued in the reference's arithmetic)              */
+    int32_t wolf_starting_food, wolf_food_for_eating_ostrich;   /* :43-44                                           */
+    int32_t food_per_bush, food_given_per_turn;  /* :28-29, Bush.take_food Bush.py:31-39                            */
+} Wab2Config;
+typedef struct Wab2World Wab2World;
+/* World.__init__ + create_* for n_envs worlds (keyed spawn positions). Synchronises. */
+int wab2_create(const Wab2Config *cfg, int64_t n_envs, uint64_t seed, uint64_t env_id_base, int32_t device, Wab2World **out);
+/* reset_environment (WAB_Environment2.py:113-118) of every world. */
+int wab2_reset(Wab2World *h, void *stream);
+/* One world turn. d_actions u8[N][A], A = n_ostriches + n_wolves (bushes act with 0). Outputs per acting entity:
+ * d_planes u8[N][A][3][2R+1][2R+1] (ostriches, wolves, bushes listed by get_observations at [dx+R][dy+R]; may be
+ * NULL), d_internal i32[N][A][5] (x, y, food, role | is_running, status; may be NULL), d_reward f32[N][A],
+ * d_done u8[N][A]. The observation of entity i is taken right before it acts. */
+int wab2_turn(Wab2World *h, const uint8_t *d_actions, uint8_t *d_planes, int32_t *d_internal, float *d_reward,
+              uint8_t *d_done, void *stream);
+/* Hidden state for tests: out9 i32[N][E][9] = type, x, y, table X, table Y, Visible, food, role, status. Synchronises. */
+int wab2_export_state(Wab2World *h, int32_t *out9, int32_t *turn, void *stream);
+void wab2_destroy(Wab2World *h);
+
 /* Raw Philox4x32-10 on the device for n counters (cross-checks the RNG contract). d_ctr u32[n][4],
  * d_out u32[n][4]. */
 int wab_philox_device(const uint32_t *d_ctr, uint32_t key0, uint32_t key1, int64_t n, uint32_t *d_out,

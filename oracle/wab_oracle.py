@@ -41,10 +41,8 @@ class OracleObs(ctypes.Structure):
 
 
 def build(force=False):
-    src = os.path.join(_HERE, "wab_oracle.c")
-    hdr = os.path.join(_HERE, "wab_oracle.h")
-    if (not force and os.path.exists(_LIB_PATH)
-            and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(src), os.path.getmtime(hdr))):
+    srcs = [os.path.join(_HERE, f) for f in ("wab_oracle.c", "wab2_oracle.c", "wab_oracle.h", "Makefile")]
+    if not force and os.path.exists(_LIB_PATH) and os.path.getmtime(_LIB_PATH) >= max(map(os.path.getmtime, srcs)):
         return _LIB_PATH
     subprocess.check_call(["make", "-C", _HERE, "-B", "libwab_oracle.so"], stdout=subprocess.DEVNULL)
     return _LIB_PATH

@@ -19,6 +19,7 @@ def build(force=False):
             os.path.join(_REPO, "wab_gym_b200", "csrc", "wab_core.cuh"),
             os.path.join(_REPO, "wab_gym_b200", "csrc", "wab_params.h"),
             os.path.join(_REPO, "wab_gym_b200", "csrc", "wab_features.cuh"),
+            os.path.join(_REPO, "wab_gym_b200", "csrc", "wab2_core.cuh"),
             os.path.join(_REPO, "include", "wab_b200.h")]
     if not force and os.path.exists(_LIB) and os.path.getmtime(_LIB) >= max(map(os.path.getmtime, srcs)):
         return _LIB
@@ -40,6 +41,14 @@ def lib():
         L.hostsim_state.argtypes = [ctypes.c_void_p] * 5
         L.hostsim_features.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                        ctypes.c_void_p]
+        L.hostsim2_create.restype = ctypes.c_void_p
+        L.hostsim2_create.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64]
+        L.hostsim2_destroy.argtypes = [ctypes.c_void_p]
+        L.hostsim2_reset.argtypes = [ctypes.c_void_p]
+        L.hostsim2_observe.restype = ctypes.c_int32
+        L.hostsim2_observe.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
+        L.hostsim2_act.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
+        L.hostsim2_state.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.hostsim_philox.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p]
         _lib = L
     return _lib
@@ -102,3 +111,40 @@ def features(wolf_grid, bush_grid, food, role, status):
     out = np.zeros(28, dtype=np.uint8)
     lib().hostsim_features(w.ctypes.data, b.ctypes.data, int(food), int(role), int(status), out.ctypes.data)
     return out
+
+
+class HostSimWorld2:
+    """The Environment-2.0 logic header (wab2_core.cuh) compiled for the host: one world."""
+
+    def __init__(self, width, height, n_ostriches, n_wolves, n_bushes, game_options=None, seed=0, env_id=0):
+        from wab_gym_b200.world2 import make_config2
+        self.cfg = make_config2(width, height, n_ostriches, n_wolves, n_bushes, game_options)
+        self.n = n_ostriches + n_wolves + n_bushes
+        self.R = self.cfg.window_radius
+        self._h = lib().hostsim2_create(ctypes.byref(self.cfg), seed, env_id)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().hostsim2_destroy(self._h)
+            self._h = None
+
+    def reset_environment(self):
+        lib().hostsim2_reset(self._h)
+
+    def get_obs(self, entity):
+        s = 2 * self.R + 1
+        planes = np.zeros((3, s, s), dtype=np.uint8)
+        internal = np.zeros(5, dtype=np.int32)
+        rows = lib().hostsim2_observe(self._h, entity, planes.ctypes.data, internal.ctypes.data)
+        return planes, internal, rows
+
+    def take_action(self, entity, action):
+        r, d = ctypes.c_float(), ctypes.c_int32()
+        lib().hostsim2_act(self._h, entity, int(action), ctypes.addressof(r), ctypes.addressof(d))
+        return r.value, bool(d.value)
+
+    def state(self):
+        out = np.zeros((self.n, 9), dtype=np.int32)
+        turn = ctypes.c_int32()
+        lib().hostsim2_state(self._h, out.ctypes.data, ctypes.addressof(turn))
+        return out, turn.value

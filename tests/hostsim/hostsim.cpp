@@ -148,3 +148,58 @@ void hostsim_philox(const uint32_t* ctr, uint32_t k0, uint32_t k1, uint32_t* out
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------ Environment 2.0 (wab2_core.cuh)
+#include "../../wab_gym_b200/csrc/wab2_core.cuh"
+
+struct HostSim2 {
+    Params2 P;
+    std::vector<uint32_t> words;
+    World2 W;
+};
+
+extern "C" {
+
+HostSim2* hostsim2_create(const Wab2Config* c, uint64_t seed, uint64_t env_id) {
+    HostSim2* h = new HostSim2();
+    Params2& P = h->P;
+    memset(&P, 0, sizeof(P));
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) { P.rk0[r] = k0; P.rk1[r] = k1; k0 += PHILOX_W0; k1 += PHILOX_W1; }
+    P.width = c->width; P.height = c->height; P.n_ostriches = c->n_ostriches; P.n_wolves = c->n_wolves; P.n_bushes = c->n_bushes;
+    P.n_entities = c->n_ostriches + c->n_wolves + c->n_bushes; P.n_acting = c->n_ostriches + c->n_wolves;
+    P.lookout_r = c->lookout_view_radius; P.gatherer_r = c->gatherer_view_radius; P.wolf_r = c->wolf_view_radius;
+    P.window_r = c->window_radius; P.starting_role = c->starting_role; P.ostrich_food = c->ostrich_starting_food;
+    P.wolf_food = c->wolf_starting_food; P.wolf_eat_gain = c->wolf_food_for_eating_ostrich;
+    P.bush_food = c->food_per_bush; P.bush_given = c->food_given_per_turn; P.env_id_base = 0;
+    h->words.assign((size_t)3 * P.n_entities, 0u);
+    h->W.base = h->words.data(); h->W.stride = 1; h->W.env_id = (uint32_t)env_id;
+    world2_create(P, h->W);
+    return h;
+}
+void hostsim2_destroy(HostSim2* h) { delete h; }
+void hostsim2_reset(HostSim2* h) { world2_reset(h->P, h->W); }
+int32_t hostsim2_observe(HostSim2* h, int32_t a, uint8_t* planes, int32_t* internal5) {
+    const int S = 2 * h->P.window_r + 1, nbits = 3 * S * S;
+    std::vector<uint32_t> bits((size_t)(nbits + 31) / 32 + 1, 0u);
+    int32_t rows = world2_observe(h->P, h->W, a, bits.data(), 0, internal5);
+    for (int b = 0; b < nbits; ++b) planes[b] = (uint8_t)((bits[b >> 5] >> (b & 31)) & 1u);
+    return rows;
+}
+void hostsim2_act(HostSim2* h, int32_t a, int32_t action, float* reward, int32_t* done) {
+    uint32_t d = 0;
+    world2_act(h->P, h->W, a, (uint32_t)action, *reward, d);
+    *done = (int32_t)d;
+}
+void hostsim2_state(const HostSim2* h, int32_t* out9, int32_t* turn) {
+    for (int k = 0; k < h->P.n_entities; ++k) {
+        const uint32_t obj = h->words[3 * k], tab = h->words[3 * k + 1], food = h->words[3 * k + 2];
+        int32_t* o = out9 + 9 * k;
+        o[0] = (int32_t)entity_type(h->P, k); o[1] = unpack_x(obj); o[2] = unpack_y(obj); o[3] = (int32_t)(tab & 0xFFu);
+        o[4] = (int32_t)((tab >> 8) & 0xFFu); o[5] = (int32_t)((tab >> 16) & 1u); o[6] = (int32_t)food;
+        o[7] = (int32_t)((tab >> 17) & 1u); o[8] = (int32_t)((tab >> 18) & 3u);
+    }
+    *turn = (int32_t)h->W.turn;
+}
+
+}  // extern "C"

@@ -16,7 +16,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_functions():
     text = open(os.path.join(REPO, "include", "wab_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(wab_[a-z_0-9]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(wab2?_[a-z_0-9]+)\s*\(", text)))
 
 
 def test_library_builds_for_sm_100a():

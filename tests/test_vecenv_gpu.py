@@ -322,3 +322,25 @@ def test_fused_and_standalone_features(name):
         obs, _, _, info = env.step(torch.from_numpy(acts).cuda())
         feats = info["features"]
     env.close()
+
+
+def test_actor_critic_rollout_runs_on_device():
+    """BASELINE config 5 in miniature: policy consumes device-resident observations; graph replay and
+    eager stepping give the same episode statistics for the same seeds."""
+    from wab_gym_b200.policy import Policy, Rollout
+    torch.manual_seed(0)
+    env = _vec(512, seed=4, features=True)
+    pol = Policy(env.flat_dim, env.n_actions)
+    assert env.flat_dim == 449 and sum(p.numel() for p in pol.parameters()) == 449 * 128 + 128 + 128 * 150 + 150 + 150 * 128 + 128 + 128 * 5 + 5 + 128 + 1
+    ro = Rollout(env, pol, use_graph=False)
+    ro.run(50)
+    st = env.stats()
+    assert st["steps"] == 512 * 50 and st["bad_actions"] == 0 and st["episodes"] > 0
+    probs, value = ro.policy(ro.flat)
+    assert torch.allclose(probs.sum(-1), torch.ones(512, device="cuda"), atol=1e-5) and value.shape == (512, 1)
+    env.close()
+    env2 = _vec(512, seed=4, features=True)
+    rg = Rollout(env2, pol, use_graph=True)
+    rg.run(20)
+    assert env2.stats()["steps"] >= 512 * 20 and env2.stats()["bad_actions"] == 0
+    env2.close()

@@ -15,7 +15,8 @@ EXPORTS = [
     "wab_vec_create", "wab_vec_reset", "wab_vec_step", "wab_vec_step_many", "wab_vec_step_host",
     "wab_vec_reset_host", "wab_vec_stats", "wab_vec_stats_device", "wab_vec_export_state", "wab_vec_num_envs", "wab_vec_lanes_per_env",
     "wab_vec_destroy", "wab_philox_device", "wab_vec_bind_features", "wab_pragmatic_features",
-    "wab_vec_flatten_features", "wab_vec_flat_dim", "wab_vec_host_block_layout", "wab_vec_step_host_packed", "wab_last_error", "wab_abi_version",
+    "wab_vec_flatten_features", "wab_vec_flat_dim", "wab_vec_host_block_layout", "wab_vec_step_host_packed",
+    "wab2_create", "wab2_reset", "wab2_turn", "wab2_export_state", "wab2_destroy", "wab_last_error", "wab_abi_version",
 ]
 
 
@@ -66,11 +67,18 @@ def load():
     L.wab_vec_flatten_features.argtypes = [vp, vp, i64, vp, vp]
     L.wab_vec_flat_dim.argtypes = [vp]
     L.wab_vec_flat_dim.restype = i32
+    L.wab2_create.argtypes = [vp, i64, u64, u64, i32, ctypes.POINTER(vp)]
+    L.wab2_reset.argtypes = [vp, vp]
+    L.wab2_turn.argtypes = [vp] * 7
+    L.wab2_export_state.argtypes = [vp] * 4
+    L.wab2_destroy.argtypes = [vp]
+    L.wab2_destroy.restype = None
     L.wab_philox_device.argtypes = [vp, ctypes.c_uint32, ctypes.c_uint32, i64, vp, vp]
     L.wab_last_error.restype = ctypes.c_char_p
     L.wab_abi_version.restype = i32
     for name in EXPORTS:
-        if name not in ("wab_vec_num_envs", "wab_vec_lanes_per_env", "wab_vec_flat_dim", "wab_vec_destroy", "wab_last_error", "wab_abi_version"):
+        if name not in ("wab_vec_num_envs", "wab_vec_lanes_per_env", "wab_vec_flat_dim", "wab_vec_destroy", "wab2_destroy",
+                        "wab_last_error", "wab_abi_version"):
             getattr(L, name).restype = ctypes.c_int
     _lib = L
     return L

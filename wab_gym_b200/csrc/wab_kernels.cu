@@ -23,6 +23,7 @@
 #include "../../include/wab_b200.h"
 #include "wab_core.cuh"
 #include "wab_features.cuh"
+#include "wab2_core.cuh"
 #include "wab_params.h"
 
 using namespace wab;
@@ -482,6 +483,10 @@ int cuda_fail(cudaError_t e, const char* what) {
         if (e__ != cudaSuccess) return cuda_fail(e__, #call);  \
     } while (0)
 
+void fill_round_keys2(Params2& P, uint32_t k0, uint32_t k1) {
+    for (int r = 0; r < 10; ++r) { P.rk0[r] = k0; P.rk1[r] = k1; k0 += PHILOX_W0; k1 += PHILOX_W1; }
+}
+
 struct DeviceGuard {
     int prev = -1;
     explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
@@ -890,3 +895,5 @@ int wab_philox_device(const uint32_t* d_ctr, uint32_t key0, uint32_t key1, int64
 }
 
 }  // extern "C"
+
+#include "wab2_kernels.cuh"

@@ -1,0 +1,96 @@
+"""Actor-critic policy and device-resident rollout (BASELINE config 5).
+
+The reference's consumer of the environment is ``actor_critic.py``: a 4-layer MLP
+(``Policy``, ``actor_critic.py:54-97``) fed with ``gym.spaces.flatten`` of the ``PragmaticObsWrapper``
+observation plus ``U[0,1)/100`` input noise (``:188-189``), a ``Categorical`` sample per step (``:108-125``,
+with a host sync per step through ``.item()``), stepping ONE environment. Here the same network
+consumes the flattened features of N environments straight from HBM: features and the 449-column
+one-hot come from the CUDA kernels (``wab_features.cuh``), the MLP is plain torch (cuBLAS GEMMs — a
+library GEMM, not a hot op of this path), sampling stays on the device and nothing synchronises with
+the host inside the loop.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .vec_env import VecEnv
+
+
+class Policy(nn.Module):
+    """Same architecture as the reference's ``Policy`` (``actor_critic.py:54-97``)."""
+
+    def __init__(self, obs_dim: int, n_actions: int):
+        super().__init__()
+        self.affine1 = nn.Linear(obs_dim, 128)
+        self.affine2 = nn.Linear(128, 150)
+        self.affine3 = nn.Linear(150, 128)
+        self.action_head = nn.Linear(128, n_actions)
+        self.value_head = nn.Linear(128, 1)
+
+    def forward(self, x):
+        x = F.leaky_relu(self.affine1(x))
+        x = F.leaky_relu(self.affine2(x))
+        x = F.leaky_relu(self.affine3(x))
+        x = torch.clamp(x, -4, 4)
+        return F.softmax(self.action_head(x), dim=-1), self.value_head(x)
+
+
+class Rollout:
+    """N-environment rollout with every tensor resident on the device.
+
+    ``step()`` = flatten features -> + U[0,1)/100 noise -> policy -> Categorical sample -> env.step.
+    With ``use_graph=True`` one step is captured in a CUDA graph and replayed (the loop is launch-bound
+    for small batches)."""
+
+    def __init__(self, env: VecEnv, policy: Optional[Policy] = None, noise: bool = True, use_graph: bool = False,
+                 dtype: torch.dtype = torch.float32):
+        if not env.with_features:
+            raise ValueError("Rollout needs VecEnv(features=True)")
+        self.env, self.noise, self.dtype = env, noise, dtype
+        self.policy = (policy or Policy(env.flat_dim, env.n_actions)).to(env.device).to(dtype).eval()
+        self.flat = torch.empty(env.num_envs, env.flat_dim, dtype=torch.float32, device=env.device)
+        self.actions = torch.zeros(env.num_envs, dtype=torch.uint8, device=env.device)
+        self.values = torch.zeros(env.num_envs, dtype=torch.float32, device=env.device)
+        self.reward_sum = torch.zeros((), dtype=torch.float64, device=env.device)
+        env.reset()
+        self.graph = None
+        if use_graph:
+            side = torch.cuda.Stream(device=env.device)
+            side.wait_stream(torch.cuda.current_stream(env.device))
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    self._step_eager()
+                side.synchronize()
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph, stream=side):
+                    self._step_eager()
+            torch.cuda.current_stream(env.device).wait_stream(side)
+
+    @torch.no_grad()
+    def _step_eager(self):
+        env = self.env
+        env.flatten_features(env.last_features, out=self.flat)            # gym.spaces.flatten, actor_critic.py:188
+        x = self.flat
+        if self.noise:
+            x = x + torch.rand_like(x) / 100                              # actor_critic.py:189
+        probs, value = self.policy(x.to(self.dtype))
+        sample = torch.multinomial(probs.float(), 1).squeeze(1)           # Categorical(probs).sample(), :117-120
+        self.actions.copy_(sample)
+        self.values.copy_(value.squeeze(1))
+        _, reward, _, _ = env.step(self.actions)
+        self.reward_sum += reward.sum(dtype=torch.float64)
+
+    def step(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step_eager()
+
+    def run(self, steps: int) -> Dict[str, float]:
+        for _ in range(steps):
+            self.step()
+        return {"env_steps": steps * self.env.num_envs}
