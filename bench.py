@@ -115,7 +115,9 @@ def cpu_reference_run(n_envs, steps, warmup, seed, threads=0, budget_s=None):
     import numpy as np
     from oracle import wab_oracle
     rng = np.random.default_rng(12345)
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if threads <= 0:
+        threads = cores          # explicit: torchrun exports OMP_NUM_THREADS=1, which must not shrink the CPU arm
     if budget_s is not None:  # bounded sample: size the run from two probes (threads warm on the second)
         rate = 1.0
         for probe_steps in (16, 128):
@@ -131,7 +133,7 @@ def cpu_reference_run(n_envs, steps, warmup, seed, threads=0, budget_s=None):
     t0 = time.perf_counter()
     done_steps, checksum = wab_oracle.run(None, seed, n_envs, steps, acts, threads)
     dt = time.perf_counter() - t0
-    return {"value": done_steps / dt, "seconds": dt, "steps": steps, "n_envs": n_envs, "cores": cores if threads <= 0 else threads,
+    return {"value": done_steps / dt, "seconds": dt, "steps": steps, "n_envs": n_envs, "cores": threads,
             "checksum": checksum}
 
 
@@ -178,6 +180,7 @@ def run_ours(args):
 
     n, K, W, T = args.num_envs, args.steps, max(args.warmup, 3), max(1, min(args.fuse, args.steps))
     env = VecEnv(n, seed=args.seed, device=dev, env_id_base=rank * n)
+    env_lpe = env.lanes_per_env
     gen = torch.Generator(device=dev).manual_seed(1 + rank)
     actions = torch.randint(0, env.n_actions, (K + W, n), dtype=torch.uint8, device=dev, generator=gen)
     env.reset()
@@ -276,6 +279,7 @@ def run_ours(args):
 
 def finish(args, env, world, rank, n, K, W, T, fused_ms, kernel_ms, launches, clocks, percall, e2e, stats_all, dist):
     stats = env.stats()
+    env_lpe = env.lanes_per_env
     env.close()
 
     if rank == 0:
@@ -298,7 +302,8 @@ def finish(args, env, world, rank, n, K, W, T, fused_ms, kernel_ms, launches, cl
             "per_call": percall,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "wab_step_kernel<false>", "peak_source": peak_src,
+                         "traffic": (336.8e6 if (n == 4096 and T == 256) else None),   # ncu dram read+write per launch, profiles/r1c_ncu_4096_summary.txt
+                         "kernel": "wab_step_kernel<false, LPE=%d>" % env_lpe, "peak_source": peak_src,
                          "bytes_per_env_step": B_ALG, "env_steps_per_launch": n * steps_per_launch,
                          "avg_launch_ms": per_launch_s * 1e3},
             "episode_stats": stats_all or stats,

@@ -193,10 +193,11 @@ typedef struct Wab2World Wab2World;
 int wab2_create(const Wab2Config *cfg, int64_t n_envs, uint64_t seed, uint64_t env_id_base, int32_t device, Wab2World **out);
 /* reset_environment (WAB_Environment2.py:113-118) of every world. */
 int wab2_reset(Wab2World *h, void *stream);
-/* One world turn. d_actions u8[N][A], A = n_ostriches + n_wolves (bushes act with 0). Outputs per acting entity:
- * d_planes u8[N][A][3][2R+1][2R+1] (ostriches, wolves, bushes listed by get_observations at [dx+R][dy+R]; may be
- * NULL), d_internal i32[N][A][5] (x, y, food, role | is_running, status; may be NULL), d_reward f32[N][A],
- * d_done u8[N][A]. The observation of entity i is taken right before it acts. */
+/* One world turn. Every array is ENTITY-MAJOR so that the worlds of a warp are contiguous: d_actions u8[A][N],
+ * A = n_ostriches + n_wolves (bushes act with 0). Outputs per acting entity: d_planes u8[A][N][3][2R+1][2R+1]
+ * (ostriches, wolves, bushes listed by get_observations at [dx+R][dy+R]; may be NULL), d_internal i32[A][N][5]
+ * (x, y, food, role | is_running, status; may be NULL), d_reward f32[A][N], d_done u8[A][N]. The observation of
+ * entity i is taken right before it acts. */
 int wab2_turn(Wab2World *h, const uint8_t *d_actions, uint8_t *d_planes, int32_t *d_internal, float *d_reward,
               uint8_t *d_done, void *stream);
 /* Hidden state for tests: out9 i32[N][E][9] = type, x, y, table X, table Y, Visible, food, role, status. Synchronises. */

@@ -160,18 +160,18 @@ def test_vecworld2_matches_oracle(world):
             o.reset_environment()
         for turn in range(12):
             acts = np.array([actions_for(rng, no, nw, n)[: no + nw] for _ in range(n_envs)], dtype=np.uint8)
-            planes, internal, reward, done = env.turn(torch.from_numpy(acts).cuda())
+            planes, internal, reward, done = env.turn(torch.from_numpy(acts.T.copy()).cuda())
             planes, internal, reward, done = planes.cpu().numpy(), internal.cpu().numpy(), reward.cpu().numpy(), done.cpu().numpy()
             for e, o in enumerate(oracles):
                 for i in range(n):
                     a = int(acts[e][i]) if i < no + nw else 0
                     if i < no + nw:
                         po, io, _ = o.get_obs(i)
-                        assert np.array_equal(planes[e, i], po), (ep, turn, e, i)
-                        assert [float(v) for v in internal[e, i]] == list(io), (ep, turn, e, i)
+                        assert np.array_equal(planes[i, e], po), (ep, turn, e, i)
+                        assert [float(v) for v in internal[i, e]] == list(io), (ep, turn, e, i)
                     r, d = o.take_action(i, a)
                     if i < no + nw:
-                        assert reward[e, i] == r and bool(done[e, i]) == d, (ep, turn, e, i)
+                        assert reward[i, e] == r and bool(done[i, e]) == d, (ep, turn, e, i)
             st, tn = env.export_state()
             for e, o in enumerate(oracles):
                 assert np.array_equal(st[e].astype(np.float64), o.state()) and tn[e] == o.turn, (ep, turn, e)

@@ -29,9 +29,9 @@ def main():
     env = VecWorld2(n, W, H, no, nw, nb, seed=0, observations=not args.no_obs)
     env.reset_environment()
     gen = torch.Generator(device="cuda").manual_seed(1)
-    acts = torch.empty((8, n, A), dtype=torch.uint8, device="cuda")
-    acts[:, :, :no] = torch.randint(0, 6, (8, n, no), dtype=torch.uint8, device="cuda", generator=gen)
-    acts[:, :, no:] = torch.randint(0, 5, (8, n, nw), dtype=torch.uint8, device="cuda", generator=gen)
+    acts = torch.empty((8, A, n), dtype=torch.uint8, device="cuda")      # entity-major, like every v2 array
+    acts[:, :no] = torch.randint(0, 6, (8, no, n), dtype=torch.uint8, device="cuda", generator=gen)
+    acts[:, no:] = torch.randint(0, 5, (8, nw, n), dtype=torch.uint8, device="cuda", generator=gen)
     for t in range(args.warmup):
         env.turn(acts[t % 8])
     torch.cuda.synchronize()

@@ -24,6 +24,8 @@ VARIANTS = {
     "slide3": ["-DWAB_SLIDE_UNROLL=3"],
     "spawn1": ["-DWAB_SPAWN_UNROLL=1"],
     "spawn4": ["-DWAB_SPAWN_UNROLL=4"],
+    "t32": ["-DWAB_THREADS_LPEN=32"],
+    "t128": ["-DWAB_THREADS_LPEN=128"],
     "lpen5": ["-DWAB_MIN_BLOCKS_LPEN=5"],
     "lpen6": ["-DWAB_MIN_BLOCKS_LPEN=6"],
     "lpen8": ["-DWAB_MIN_BLOCKS_LPEN=8"],

@@ -96,19 +96,22 @@ WAB_HD void world2_reset(const Params2& P, World2& W) {
 // wrap-aware delta along one axis, World.py:252-291: only ONE wrap direction is ever considered (if / elif), and
 // min(d, wrap, key=abs) keeps d on ties.
 WAB_HD int32_t axis_delta(int32_t obj, int32_t ent, int32_t r, int32_t size) {
-    int32_t d = obj - ent;
-    if (ent < r) {
-        if (size - (r - ent) <= obj) {
-            const int32_t wrap = -ent - (size - obj);
-            if ((wrap < 0 ? -wrap : wrap) < (d < 0 ? -d : d)) d = wrap;
-        }
-    } else if (size < ent + r) {
-        if (obj <= r - size + ent) {
-            const int32_t wrap = obj + size - ent;
-            if ((wrap < 0 ? -wrap : wrap) < (d < 0 ? -d : d)) d = wrap;
-        }
-    }
-    return d;
+    const int32_t d = obj - ent;
+    const bool low = ent < r;                               // "if entity < radius" branch (World.py:255)
+    const bool high = !low && size < ent + r;               // "elif size < entity + radius" branch (:264)
+    const bool in_low = low && (size - (r - ent) <= obj);
+    const bool in_high = high && (obj <= r - size + ent);
+    const int32_t wrap = in_low ? d - size : d + size;      // -ent - (size - obj)  |  obj + size - ent
+    const int32_t ad = d < 0 ? -d : d, aw = wrap < 0 ? -wrap : wrap;
+    return ((in_low || in_high) && aw < ad) ? wrap : d;     // min(d, wrap, key=abs): ties keep d
+}
+
+WAB_HD void set_stream_bit(uint32_t* bits, int32_t pos) {   // streams of neighbouring lanes share boundary words
+#if defined(__CUDA_ARCH__)
+    atomicOr(bits + (pos >> 5), 1u << (pos & 31));
+#else
+    bits[pos >> 5] |= 1u << (pos & 31);
+#endif
 }
 
 // get_observations(a), World.py:360-377: sets bit (bit0 + type*S*S + (dx+R)*S + (dy+R)) of `bits` (stride 1 words)
@@ -132,7 +135,7 @@ WAB_HD int32_t world2_observe(const Params2& P, const World2& W, int a, uint32_t
         ++rows;
         if (dx >= -R && dx <= R && dy >= -R && dy <= R) {
             const int32_t pos = bit0 + ((int32_t)entity_type(P, k) * S + (dx + R)) * S + (dy + R);
-            bits[pos >> 5] |= 1u << (pos & 31);
+            set_stream_bit(bits, pos);
         }
     }
     const uint32_t obj = w2_obj(W, a);

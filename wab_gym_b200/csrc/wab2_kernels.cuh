@@ -16,10 +16,10 @@ struct State2Ptrs {
     int64_t n;
 };
 struct Out2Ptrs {
-    uint8_t* planes;    // [N][A][3][S][S] u8 or null
-    int32_t* internal;  // [N][A][5] or null
-    float* reward;      // [N][A]
-    uint8_t* done;      // [N][A]
+    uint8_t* planes;    // [A][N][3][S][S] u8 or null (entity-major: the 32 worlds of a warp are contiguous)
+    int32_t* internal;  // [A][N][5] or null
+    float* reward;      // [A][N]
+    uint8_t* done;      // [A][N]
 };
 
 __device__ __forceinline__ void load_world(const Params2& P, const State2Ptrs& st, int64_t idx, World2& W) {
@@ -60,49 +60,52 @@ __global__ void wab2_turn_kernel(const __grid_constant__ Params2 P, const State2
     const int64_t warp_first = idx - lane;
     const int n_valid = (int)((n - warp_first) < 32 ? (n - warp_first > 0 ? n - warp_first : 0) : 32);
     uint32_t* ents = smem2;                                          // [3E][bs]
-    uint32_t* streams = ents + 3 * P.n_entities * bs;                // [bs][stream_words]
-    uint2* lut = reinterpret_cast<uint2*>(streams + ((bs * stream_words + 1) & ~1));
+    uint32_t* streams = ents + 3 * P.n_entities * bs;                // [warps][stream_words]: one stream per warp
+    uint2* lut = reinterpret_cast<uint2*>(streams + (((bs >> 5) * stream_words + 1) & ~1));
     build_lut(lut);
     World2 W;
     W.base = ents + threadIdx.x; W.stride = bs;
     if (active) load_world(P, st, idx, W);
     const int S = 2 * P.window_r + 1, obs_bytes = 3 * S * S, A = P.n_acting;
-    uint32_t* my_stream = streams + threadIdx.x * stream_words;
+    uint32_t* stream = streams + warp * stream_words;
     for (int a = 0; a < P.n_entities; ++a) {
         const bool acting = a < A;
+        const int64_t o = (int64_t)a * n + idx;                       // [A][N] outputs
         if (acting && (out.planes || out.internal)) {
-            const int64_t first_byte = ((int64_t)idx * A + a) * obs_bytes;
+            const int64_t first_byte = ((int64_t)a * n + warp_first) * obs_bytes;   // the warp's 32 windows are contiguous
             const int off = (int)(first_byte & 15);
             int32_t internal[5] = {0, 0, 0, 0, 0};
-            if (out.planes)
-                for (int k = 0; k < stream_words; ++k) my_stream[k] = 0u;
+            if (out.planes) {
+                for (int k = lane; k < stream_words; k += 32) stream[k] = 0u;
+                __syncwarp();
+            }
             if (active) {
-                if (out.planes) world2_observe(P, W, a, my_stream, off, internal);
-                else { uint32_t dummy[1]; (void)dummy; /* internal only */
-                       const uint32_t obj = w2_obj(W, a), atab = w2_tab(W, a); const uint32_t at = entity_type(P, a);
-                       internal[0] = unpack_x(obj); internal[1] = unpack_y(obj); internal[2] = (int32_t)w2_food(W, a);
-                       internal[3] = at == T_BUSH ? 0 : (int32_t)((atab >> 17) & 1u); internal[4] = at == T_BUSH ? 0 : (int32_t)((atab >> 18) & 3u); }
+                if (out.planes) {
+                    world2_observe(P, W, a, stream, off + lane * obs_bytes, internal);
+                } else {
+                    const uint32_t obj = w2_obj(W, a), atab = w2_tab(W, a);
+                    const uint32_t at = entity_type(P, a);
+                    internal[0] = unpack_x(obj); internal[1] = unpack_y(obj); internal[2] = (int32_t)w2_food(W, a);
+                    internal[3] = at == T_BUSH ? 0 : (int32_t)((atab >> 17) & 1u);
+                    internal[4] = at == T_BUSH ? 0 : (int32_t)((atab >> 18) & 3u);
+                }
                 if (out.internal) {
-                    int32_t* dst = out.internal + ((int64_t)idx * A + a) * 5;
+                    int32_t* dst = out.internal + o * 5;
                     dst[0] = internal[0]; dst[1] = internal[1]; dst[2] = internal[2]; dst[3] = internal[3]; dst[4] = internal[4];
                 }
             }
             if (out.planes) {
                 __syncwarp();
-                for (int l = 0; l < n_valid; ++l) {                  // the warp flushes its 32 windows one after the other
-                    const int64_t fb = ((int64_t)(warp_first + l) * A + a) * obs_bytes;
-                    const int o = (int)(fb & 15);
-                    stream_flush(streams + (warp * 32 + l) * stream_words, lut, out.planes + (fb - o), o, o + obs_bytes, lane);
-                }
+                stream_flush(stream, lut, out.planes + (first_byte - off), off, off + obs_bytes * n_valid, lane);
                 __syncwarp();
             }
         }
         if (active) {
             float reward; uint32_t done;
-            world2_act(P, W, a, acting ? (uint32_t)actions[(int64_t)idx * A + a] : 0u, reward, done);
+            world2_act(P, W, a, acting ? (uint32_t)actions[o] : 0u, reward, done);
             if (acting) {
-                out.reward[(int64_t)idx * A + a] = reward;
-                out.done[(int64_t)idx * A + a] = (uint8_t)done;
+                out.reward[o] = reward;
+                out.done[o] = (uint8_t)done;
             }
         }
     }
@@ -153,12 +156,12 @@ int wab2_create(const Wab2Config* cfg, int64_t n_envs, uint64_t seed, uint64_t e
     P.wolf_food = cfg->wolf_starting_food; P.wolf_eat_gain = cfg->wolf_food_for_eating_ostrich;
     P.bush_food = cfg->food_per_bush; P.bush_given = cfg->food_given_per_turn; P.env_id_base = env_id_base;
     const int S = 2 * cfg->window_radius + 1;
-    h->stream_words = (3 * S * S + 15 + 31) / 32 + 1;
+    h->stream_words = (32 * 3 * S * S + 15 + 31) / 32 + 1;            // one bit stream per warp: 32 windows
     // threads per block: as many as shared memory allows (3E state words + one bit stream per thread)
     int max_smem = 48 * 1024;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     int bs = 128;
-    auto need = [&](int b) { return sizeof(uint32_t) * ((size_t)3 * E * b + (size_t)((b * h->stream_words + 1) & ~1) + 512); };
+    auto need = [&](int b) { return sizeof(uint32_t) * ((size_t)3 * E * b + (size_t)(((b >> 5) * h->stream_words + 1) & ~1) + 512); };
     while (bs > 32 && need(bs) > (size_t)max_smem / 2) bs >>= 1;
     if (need(bs) > (size_t)max_smem) { delete h; return fail(WAB_E_UNSUPPORTED, "too many entities for the shared-memory staging"); }
     h->bs = bs; h->smem_turn = need(bs); h->smem_init = sizeof(uint32_t) * (size_t)3 * E * bs;

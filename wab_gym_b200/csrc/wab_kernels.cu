@@ -36,6 +36,9 @@ namespace {
 
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr int kFlushUnroll = WAB_FLUSH_UNROLL;
+#ifndef WAB_THREADS_LPEN
+#define WAB_THREADS_LPEN 64
+#endif
 #ifndef WAB_MIN_BLOCKS_LPEN
 #define WAB_MIN_BLOCKS_LPEN 1         // lanes-per-env kernels: no register cap (one wave of few CTAs anyway)
 #endif
@@ -244,9 +247,10 @@ __device__ __forceinline__ void build_lut(uint2* lut) {
     __syncthreads();
 }
 
-// Geometry: 128-thread CTAs for every lanes-per-env factor; a warp owns EPW = 32 / LPE envs.
+// Geometry: a warp owns EPW = 32 / LPE envs. Thread-per-env uses 128-thread CTAs; the lanes-per-env variants
+// serve small batches where the grid is about one wave, so they use 64-thread CTAs to spread evenly over 148 SMs.
 template <int LPE> struct Geo {
-    static constexpr int THREADS = 128;
+    static constexpr int THREADS = LPE == 1 ? 128 : WAB_THREADS_LPEN;
     static constexpr int EPW = 32 / LPE;
     static constexpr int EPB = THREADS / LPE;
     static constexpr int STREAM = ((THREADS / 32) * WarpStream<EPW>::WORDS + 1) & ~1;   // even: keeps the LUT 8-byte aligned

@@ -70,10 +70,11 @@ class VecWorld2:
                                         self.device.index, ctypes.byref(h)))
         self._h = h
         n, a, s = self.num_envs, self.n_acting, 2 * self.R + 1
-        self.planes = torch.empty((n, a, 3, s, s), dtype=torch.uint8, device=self.device) if observations else None
-        self.internal = torch.empty((n, a, 5), dtype=torch.int32, device=self.device) if observations else None
-        self.reward = torch.empty((n, a), dtype=torch.float32, device=self.device)
-        self.done = torch.empty((n, a), dtype=torch.uint8, device=self.device)
+        # entity-major: [A, N, ...] (the worlds of a warp are contiguous for every acting entity)
+        self.planes = torch.empty((a, n, 3, s, s), dtype=torch.uint8, device=self.device) if observations else None
+        self.internal = torch.empty((a, n, 5), dtype=torch.int32, device=self.device) if observations else None
+        self.reward = torch.empty((a, n), dtype=torch.float32, device=self.device)
+        self.done = torch.empty((a, n), dtype=torch.uint8, device=self.device)
 
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -83,11 +84,11 @@ class VecWorld2:
         _lib.check(self.lib.wab2_reset(self._h, self._stream()))
 
     def turn(self, actions: torch.Tensor):
-        """One world turn. ``actions`` u8[N, n_ostriches + n_wolves] (ostrich 0-5, wolf 0-4; bushes always act with 0).
-        Returns (planes u8[N, A, 3, 2R+1, 2R+1], internal i32[N, A, 5], reward f32[N, A], done bool[N, A]); the
-        observation of entity i is what ``get_obs(i)`` returns right before it acts (World.py:360-377)."""
-        if tuple(actions.shape) != (self.num_envs, self.n_acting):
-            raise ValueError("actions must have shape (num_envs, n_ostriches + n_wolves)")
+        """One world turn. ``actions`` u8[A, N], A = n_ostriches + n_wolves (ostrich 0-5, wolf 0-4; bushes always act
+        with 0). Returns (planes u8[A, N, 3, 2R+1, 2R+1], internal i32[A, N, 5], reward f32[A, N], done bool[A, N]) —
+        entity-major; the observation of entity i is what ``get_obs(i)`` returns right before it acts (World.py:360-377)."""
+        if tuple(actions.shape) != (self.n_acting, self.num_envs):
+            raise ValueError("actions must have shape (n_ostriches + n_wolves, num_envs)")
         a = actions.to(device=self.device, dtype=torch.uint8).contiguous()
         _lib.check(self.lib.wab2_turn(self._h, _ptr(a), _ptr(self.planes), _ptr(self.internal), _ptr(self.reward),
                                       _ptr(self.done), self._stream()))
