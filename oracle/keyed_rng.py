@@ -18,15 +18,26 @@ Random123 constants) with
     key     = (seed & 0xffffffff, seed >> 32)
     counter = (env_id, episode, (site << 28) | (turn << 8) | sub, payload)
 
-returns four 32-bit words; a draw is ONE word ``w`` ("lane") and the uniform handed to the
-reference is the exact double ``U = w * 2**-32``.
+returns four 32-bit words. A *word draw* is ONE word ``w`` ("lane") and the uniform handed to the
+reference is the exact double ``U = w * 2**-32``:
 
     site   turn  sub      payload                              lane          cite
     BUSH   0     0        (x>>1 & 0xffff) | (y>>1 & 0xffff)<<16  (x&1)|(y&1)<<1  wab_env.py:627,631-635
-    INIT   0     0        c >> 2,  c = (x+W//2)*H + (y+H//2)     c & 3         wab_env.py:588-591
-    SPAWN  t     0        j >> 2,  j = ring index (see below)    j & 3         wab_env.py:571-574
     DESP   t     rank>>2  (wx & 0xffff) | (wy & 0xffff)<<16      rank & 3      wab_env.py:262-264
     START  0     0        0                                      0 food, 1 role  wab_env.py:596-599
+
+The two sites that draw for MANY cells per step with a tiny success probability (48 ring cells per
+step, 121 cells per reset, p = 0.0005) use a *two-level draw* with 48 bits of resolution:
+``U = (h * 2**32 + r) * 2**-48`` where ``h`` is a 16-bit half-word of a PRIMARY call shared by 8
+cells and ``r`` a word of a SECONDARY call shared by 4 cells. ``U < p`` is decided by ``h`` alone
+unless ``h`` equals the top 16 bits of the threshold (probability 2**-16), so an implementation
+evaluates the secondary call lazily; the draw itself is an exact, iid uniform either way.
+
+    site   turn  primary (sub 0)                    secondary (sub 1)          cite
+    INIT   0     payload c>>3, half-word c&7        payload c>>2, lane c&3     wab_env.py:588-591   c = (x+W//2)*H + (y+H//2)
+    SPAWN  t     payload j>>3, half-word j&7        payload j>>2, lane j&3     wab_env.py:571-574   j = ring index (below)
+
+(half-word k of a call = bits 16*(k&1) .. 16*(k&1)+15 of word k>>1.)
 
 ``ring index``: cells of the (W+2m)x(H+2m) box around the (already moved) ostrich minus its WxH
 view, enumerated box-x-major then box-y, skipping interior cells. ``rank``: ordinal of a wolf
@@ -94,11 +105,19 @@ def bush_words(seed, env_id, episode, x, y):
     return _draw(seed, env_id, episode, SITE_BUSH, 0, 0, _pack_xy(x >> 1, y >> 1), (x & 1) | ((y & 1) << 1))
 
 
-def init_words(seed, env_id, episode, x, y, width, height):
+def two_level_units(seed, env_id, episode, site, turn, index):
+    """Exact doubles U = (h * 2**32 + r) * 2**-48 for the cells `index` of a two-level site."""
+    index = np.asarray(index, dtype=np.int64)
+    word = _draw(seed, env_id, episode, site, turn, 0, index >> 3, (index >> 1) & 3).astype(np.uint64)
+    h = (word >> (np.uint64(16) * (index & 1).astype(np.uint64))) & np.uint64(0xFFFF)
+    r = _draw(seed, env_id, episode, site, turn, 1, index >> 2, index & 3).astype(np.uint64)
+    return ((h << np.uint64(32)) | r).astype(np.float64) * (2.0 ** -48)
+
+
+def init_units(seed, env_id, episode, x, y, width, height):
     x = np.asarray(x, dtype=np.int64)
     y = np.asarray(y, dtype=np.int64)
-    c = (x + width // 2) * height + (y + height // 2)
-    return _draw(seed, env_id, episode, SITE_INIT, 0, 0, c >> 2, c & 3)
+    return two_level_units(seed, env_id, episode, SITE_INIT, 0, (x + width // 2) * height + (y + height // 2))
 
 
 def ring_index(dx, dy, width, height, margin):
@@ -116,9 +135,8 @@ def ring_index(dx, dy, width, height, margin):
     return full_before + mid_before + within
 
 
-def spawn_words(seed, env_id, episode, turn, dx, dy, width, height, margin):
-    j = ring_index(dx, dy, width, height, margin)
-    return _draw(seed, env_id, episode, SITE_SPAWN, turn, 0, j >> 2, j & 3)
+def spawn_units(seed, env_id, episode, turn, dx, dy, width, height, margin):
+    return two_level_units(seed, env_id, episode, SITE_SPAWN, turn, ring_index(dx, dy, width, height, margin))
 
 
 def despawn_words(seed, env_id, episode, turn, wx, wy):

@@ -139,7 +139,8 @@ class _KeyedRandom:
             cells = frame.f_locals["new_wolves"]
             seed, eid, ep = _env_key(env)
             opts = env.game_options
-            words = kr.init_words(seed, eid, ep, _ints(cells["x"]), _ints(cells["y"]), opts["width"], opts["height"])
+            units = kr.init_units(seed, eid, ep, _ints(cells["x"]), _ints(cells["y"]), opts["width"], opts["height"])
+            return self._checked(units, size, site)
         elif site == "spawn_wolves":  # :571-574
             env = frame.f_locals["self"]
             cells = frame.f_locals["new_wolves"]
@@ -147,11 +148,12 @@ class _KeyedRandom:
             opts = env.game_options
             ox = int(env.ostriches.iloc[0].x)
             oy = int(env.ostriches.iloc[0].y)
-            words = kr.spawn_words(
+            units = kr.spawn_units(
                 seed, eid, ep, env.current_turn,
                 _ints(cells["x"]) - ox, _ints(cells["y"]) - oy,
                 opts["width"], opts["height"], opts["wolf_spawn_margin"],
             )
+            return self._checked(units, size, site)
         elif site == "step":  # despawn, :262-264
             env = frame.f_locals["self"]
             seed, eid, ep = _env_key(env)
@@ -161,12 +163,16 @@ class _KeyedRandom:
             return float(kr.to_unit(kr.start_words(*_env_key(env))[0]))
         else:
             raise RuntimeError("unkeyed np.random.random call from %r" % site)
+        return self._checked(kr.to_unit(words), size, site)
+
+    @staticmethod
+    def _checked(units, size, site):
         if size is None:
             raise RuntimeError("scalar draw at vector site %r" % site)
         n = int(size) if not isinstance(size, tuple) else int(size[0])
-        if n != len(words):
-            raise RuntimeError("draw count mismatch at %r: %d vs %d" % (site, n, len(words)))
-        return kr.to_unit(words)
+        if n != len(units):
+            raise RuntimeError("draw count mismatch at %r: %d vs %d" % (site, n, len(units)))
+        return units
 
     def randint(self, low, high=None, size=None):
         frame = sys._getframe(1)

@@ -65,6 +65,14 @@ static uint32_t keyed_word(const WabOracleEnv *e, uint32_t site, uint32_t turn, 
     return out[lane & 3u];
 }
 static double unit(uint32_t w) { return (double)w * (1.0 / 4294967296.0); }
+/* two-level draw of oracle/keyed_rng.py: U = (h * 2^32 + r) * 2^-48, h = half-word (index & 7) of the primary
+ * call (sub 0, payload index >> 3), r = word (index & 3) of the secondary call (sub 1, payload index >> 2) */
+static double two_level_unit(const WabOracleEnv *e, uint32_t site, uint32_t turn, uint32_t index) {
+    uint32_t word = keyed_word(e, site, turn, 0, index >> 3, (index >> 1) & 3u);
+    uint32_t h = (word >> (16u * (index & 1u))) & 0xFFFFu;
+    uint32_t r = keyed_word(e, site, turn, 1, index >> 2, index & 3u);
+    return ((double)h * 4294967296.0 + (double)r) * (1.0 / 281474976710656.0);
+}
 static uint32_t pack_xy(int32_t x, int32_t y) { return ((uint32_t)x & 0xFFFFu) | (((uint32_t)y & 0xFFFFu) << 16); }
 
 /* ------------------------------------------------------------------ bush record store */
@@ -145,8 +153,7 @@ static void initialize_wolves(WabOracleEnv *e) {
     for (int32_t x = e->ox - hw; x <= e->ox + hw; ++x)
         for (int32_t y = e->oy - hh; y <= e->oy + hh; ++y) {
             uint32_t c = (uint32_t)((x - e->ox + hw) * e->cfg.height + (y - e->oy + hh));
-            uint32_t w = keyed_word(e, SITE_INIT, 0, 0, c >> 2, c & 3u);
-            if (unit(w) < p) wolf_add(e, x, y);
+            if (two_level_unit(e, SITE_INIT, 0, c) < p) wolf_add(e, x, y);
         }
 }
 
@@ -159,8 +166,7 @@ static void spawn_wolves(WabOracleEnv *e) {
         for (int32_t y = e->oy - hh - m; y < e->oy + hh + m + 1; ++y) {  /* :549-560 */
             int visible = (x >= e->ox - hw && x <= e->ox + hw && y >= e->oy - hh && y <= e->oy + hh);
             if (visible) continue;                                       /* :566 */
-            uint32_t w = keyed_word(e, SITE_SPAWN, (uint32_t)e->turn, 0, j >> 2, j & 3u);
-            if (unit(w) < p) wolf_add(e, x, y);
+            if (two_level_unit(e, SITE_SPAWN, (uint32_t)e->turn, j) < p) wolf_add(e, x, y);
             ++j;
         }
 }

@@ -87,8 +87,10 @@ class WabConfigStruct(ctypes.Structure):
         ("food_inc", ctypes.c_double),
         ("food_dec", ctypes.c_double),
         ("food_obs_scale", ctypes.c_double),
-        ("thr_spawn", ctypes.c_uint32),
-        ("thr_init", ctypes.c_uint32),
+        ("thr_spawn_hi", ctypes.c_uint32),
+        ("thr_spawn_lo", ctypes.c_uint32),
+        ("thr_init_hi", ctypes.c_uint32),
+        ("thr_init_lo", ctypes.c_uint32),
         ("thr_keep", ctypes.c_uint64),
         ("reward_table", ctypes.c_float * 8),
         ("mask_lookout", ctypes.c_uint32 * 4),
@@ -111,6 +113,12 @@ def lt_threshold(p: float) -> int:
     """Least integer t with: for 32-bit w, (w * 2**-32 < p)  <=>  (w < t). Exact (rational arithmetic)."""
     t = math.ceil(Fraction(float(p)) * (1 << 32))
     return min(max(t, 0), 1 << 32)
+
+
+def lt_threshold48(p: float) -> int:
+    """Least integer T with: for a 48-bit draw v, (v * 2**-48 < p)  <=>  (v < T). Exact (rational arithmetic)."""
+    t = math.ceil(Fraction(float(p)) * (1 << 48))
+    return min(max(t, 0), 1 << 48)
 
 
 def gt_threshold(q: float) -> int:
@@ -237,9 +245,7 @@ class GameConfig:
         if not (1 <= max_turns <= 30000):
             raise ValueError("max_turns must be in [1, 30000] (positions are int16 on the device)")
         p_spawn = opts["chance_wolf_on_square"] / 2  # wab_env.py:573, :590
-        thr_spawn = lt_threshold(p_spawn)
-        if thr_spawn >= (1 << 32):
-            raise ValueError("chance_wolf_on_square / 2 must be < 1")
+        thr_spawn = lt_threshold48(p_spawn)
         thr_keep = gt_threshold(opts["wolf_chance_to_despawn"])
         proof = None
         if auto_reset and not force_f64_food:
@@ -299,8 +305,8 @@ class GameConfig:
         s.food_inc = 1 / o["turns_to_fill_food"]
         s.food_dec = 1 / o["turns_to_empty_food"]
         s.food_obs_scale = float(o["turns_to_empty_food"])
-        s.thr_spawn = self.thr_spawn
-        s.thr_init = self.thr_spawn
+        s.thr_spawn_hi, s.thr_spawn_lo = self.thr_spawn >> 32, self.thr_spawn & 0xFFFFFFFF
+        s.thr_init_hi, s.thr_init_lo = s.thr_spawn_hi, s.thr_spawn_lo
         s.thr_keep = self.thr_keep
         for k in range(8):
             s.reward_table[k] = float(np.float32(self.reward_table64[k]))

@@ -40,6 +40,7 @@ enum : uint32_t { SITE_BUSH = 1, SITE_INIT = 2, SITE_SPAWN = 3, SITE_DESP = 4, S
 
 constexpr int kSlideUnroll = WAB_SLIDE_UNROLL, kSpawnUnroll = WAB_SPAWN_UNROLL;
 constexpr int VIEW = 11, HALF = 5, CELLS = 121, RING = 48;
+constexpr int RING_CALLS = RING / 8, INIT_CALLS = (CELLS + 7) / 8;   // 8 two-level draws per primary Philox call
 constexpr int OBS_BYTES = 3 * CELLS;        // 363 bytes per env: wolves, bushes, ostriches
 constexpr uint32_t TOP_WORD_MASK = 0x01FFFFFFu;  // 121 = 3*32 + 25
 
@@ -60,7 +61,9 @@ struct Params {
     uint32_t rk0[10], rk1[10];     // Philox round keys (key is uniform: the seed)
     uint32_t thr_bush1;            // food0 > 0  <=>  word >= thr_bush1   (bush_thr[0])
     uint32_t thr_bush2;            // food0 > 1  <=>  word >= thr_bush2   (bush_thr[1]; only read when n_bush_thr > 1)
-    uint32_t thr_spawn, thr_init;  // event <=> word < thr
+    uint32_t thr_spawn_hi, thr_spawn_lo;   // two-level draw: event <=> (h << 32 | r) < (hi << 32 | lo)
+    uint32_t thr_init_hi, thr_init_lo;
+    uint32_t spawn_cand_mask;              // half-word can be <= thr_spawn_hi only if (h & mask) == 0
     uint32_t n_bush_thr;
     uint64_t thr_keep;             // kept <=> word >= thr_keep
     const uint32_t* bush_thr;      // device table, n_bush_thr entries
@@ -215,6 +218,39 @@ WAB_HD uint32_t bush_alive(const Params& P, const Env& E, const Slots& S, int32_
     int32_t l = log_find(E, S, pack_xy(x, y));
     if (l < 0) return 1u;
     return alive_after(P, word, (uint32_t)S.logcnt[(int64_t)l * S.lstride]);
+}
+
+// ---- two-level draws (oracle/keyed_rng.py): U = (h << 32 | r) * 2^-48, 8 half-words h per primary call.
+// Cheap superset test on a primary call: can any of its 8 half-words be <= thr_hi ?  (zero-field detection on
+// the bits above bit_length(thr_hi))
+WAB_HD bool any_candidate(const Params& P, const uint32_t w[4]) {
+    uint32_t z = 0;
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t t = w[k] & P.spawn_cand_mask;
+        z |= (t - 0x00010001u) & ~t & 0x80008000u;
+    }
+    return z != 0u;
+}
+// Exact decision for the 8 draws of primary call `grp`: bit k set <=> draw 8*grp + k is below the threshold.
+// The secondary call is evaluated only for a half-word equal to thr_hi (probability 2^-16).
+WAB_HD uint32_t two_level_hits(const Params& P, uint32_t env_id, uint32_t episode, uint32_t site, uint32_t turn,
+                               uint32_t grp, uint32_t thr_hi, uint32_t thr_lo) {
+    uint32_t w[4];
+    philox(P, env_id, episode, ctr2(site, turn, 0), grp, w);
+    uint32_t hits = 0;
+    WAB_ROLLED
+    for (uint32_t k = 0; k < 8u; ++k) {
+        const uint32_t h = (pick4(w, k >> 1) >> (16u * (k & 1u))) & 0xFFFFu;
+        bool hit = h < thr_hi;
+        if (!hit && h == thr_hi && thr_lo != 0u) {
+            const uint32_t j = 8u * grp + k;
+            uint32_t r[4];
+            philox(P, env_id, episode, ctr2(site, turn, 1), j >> 2, r);
+            hit = pick4(r, j & 3u) < thr_lo;
+        }
+        hits |= (hit ? 1u : 0u) << k;
+    }
+    return hits;
 }
 
 // 11-bit value with bit g at stride 11 (positions 11*g), as four words.
@@ -415,42 +451,44 @@ WAB_HD void env_step(const Params& P, Env& E, const Slots& S, uint32_t action, S
         if (E.food_i <= 0) { E.status = 1u; E.food_i = 0; }
     }
 
-    // ---- :325-326 spawn_wolves on the 48 ring cells around the moved ostrich
+    // ---- :325-326 spawn_wolves on the 48 ring cells around the moved ostrich: two-level draws, 8 cells per call
     if (P.wolves) {
         uint32_t hitgroups = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll kSpawnUnroll
 #endif
-        for (int grp = (int)coop.sub; grp < RING / 4; grp += LPE) {
+        for (int grp = (int)coop.sub; grp < RING_CALLS; grp += LPE) {
             uint32_t w[4];
             philox(P, E.env_id, E.episode, ctr2(SITE_SPAWN, E.turn, 0), (uint32_t)grp, w);
-            uint32_t a = w[0] < w[1] ? w[0] : w[1], b = w[2] < w[3] ? w[2] : w[3];
-            a = a < b ? a : b;
-            hitgroups |= (a < P.thr_spawn ? 1u : 0u) << grp;
+            hitgroups |= (any_candidate(P, w) ? 1u : 0u) << grp;
         }
         hitgroups = group_or(coop, hitgroups);
         WAB_ROLLED
-        while (hitgroups) {                        // rare: recompute the groups that hit
+        while (hitgroups) {                        // rare (2 * 48 / 1024 per step): settle the candidates exactly
 #if defined(__CUDA_ARCH__)
             const int grp = __ffs((int)hitgroups) - 1;
 #else
             const int grp = __builtin_ctz(hitgroups);
 #endif
             hitgroups &= hitgroups - 1u;
-            uint32_t w[4];
-            philox(P, E.env_id, E.episode, ctr2(SITE_SPAWN, E.turn, 0), (uint32_t)grp, w);
+            uint32_t hits = two_level_hits(P, E.env_id, E.episode, SITE_SPAWN, E.turn, (uint32_t)grp, P.thr_spawn_hi, P.thr_spawn_lo);
             WAB_ROLLED
-            for (int l = 0; l < 4; ++l)
-                if (w[l] < P.thr_spawn) {                                        // :571-574
-                    int32_t ox, oy;
-                    ring_offset(4 * grp + l, ox, oy);
-                    if (E.nw < (uint32_t)P.wolf_cap) {
-                        S.wolves[(int32_t)E.nw * S.wstride] = pack_xy(E.x + ox, E.y + oy);
-                        E.nw += 1;
-                    } else {
-                        O.overflow = 1u;
-                    }
+            while (hits) {                                                        // :571-574
+#if defined(__CUDA_ARCH__)
+                const int l = __ffs((int)hits) - 1;
+#else
+                const int l = __builtin_ctz(hits);
+#endif
+                hits &= hits - 1u;
+                int32_t ox, oy;
+                ring_offset(8 * grp + l, ox, oy);
+                if (E.nw < (uint32_t)P.wolf_cap) {
+                    S.wolves[(int32_t)E.nw * S.wstride] = pack_xy(E.x + ox, E.y + oy);
+                    E.nw += 1;
+                } else {
+                    O.overflow = 1u;
                 }
+            }
         }
     }
 
@@ -497,13 +535,10 @@ WAB_HD void reset_bush_block(const Params& P, uint32_t env_id, uint32_t episode,
     part[2] |= (q == 2) ? lo : ((q == 1) ? hi : 0u);
     part[3] |= (q == 3) ? lo : ((q == 2) ? hi : 0u);
 }
-// wolf-init group grp (0..30): cells c = 4*grp .. 4*grp+3, c = (x+5)*11 + (y+5)  (:578-593) -> hit bits
+// wolf-init call grp (0..15): cells c = 8*grp .. 8*grp+7, c = (x+5)*11 + (y+5)  (:578-593) -> 8 hit bits
 WAB_HD uint32_t reset_init_group(const Params& P, uint32_t env_id, uint32_t episode, int grp) {
-    uint32_t w[4];
-    philox(P, env_id, episode, ctr2(SITE_INIT, 0, 0), (uint32_t)grp, w);
-    uint32_t hits = 0;
-    for (int l = 0; l < 4; ++l)
-        hits |= ((4 * grp + l < CELLS && w[l] < P.thr_init) ? 1u : 0u) << l;
+    uint32_t hits = two_level_hits(P, env_id, episode, SITE_INIT, 0u, (uint32_t)grp, P.thr_init_hi, P.thr_init_lo);
+    if (grp == INIT_CALLS - 1) hits &= (1u << (CELLS - 8 * (INIT_CALLS - 1))) - 1u;   // cells 121..127 do not exist
     return hits;
 }
 // scalar part of a reset: spawn_ostriches (:595-611)
