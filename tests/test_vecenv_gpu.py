@@ -344,3 +344,17 @@ def test_actor_critic_rollout_runs_on_device():
     rg.run(20)
     assert env2.stats()["steps"] >= 512 * 20 and env2.stats()["bad_actions"] == 0
     env2.close()
+
+
+def test_batched_a2c_update_trains_on_device():
+    """the reference's finish_episode (actor_critic.py:128-169) batched over envs."""
+    from wab_gym_b200.a2c import A2CTrainer
+    torch.manual_seed(1)
+    env = _vec(1024, seed=8, features=True)
+    tr = A2CTrainer(env, horizon=40, lr=1e-3)
+    before = [p.detach().clone() for p in tr.policy.parameters()]
+    out = [tr.train_iteration() for _ in range(3)]
+    assert all(torch.isfinite(o["loss"]).item() for o in out)
+    assert any(not torch.equal(a, b.detach()) for a, b in zip(before, tr.policy.parameters()))
+    assert env.stats()["steps"] == 1024 * 40 * 3 and env.stats()["bad_actions"] == 0
+    env.close()
