@@ -20,8 +20,10 @@
 #if defined(__CUDACC__)
 #define WAB_HD __host__ __device__ __forceinline__
 #define WAB_ROLLED _Pragma("unroll 1")   // rare-path loops stay rolled: the step kernel must fit the instruction cache
+#define WAB_HD_RARE __host__ __device__ __noinline__   // rare paths are real calls, kept out of the hot loop's footprint
 #else
 #define WAB_HD static inline
+#define WAB_HD_RARE static
 #define WAB_ROLLED
 #endif
 
@@ -63,7 +65,6 @@ struct Params {
     uint32_t thr_bush2;            // food0 > 1  <=>  word >= thr_bush2   (bush_thr[1]; only read when n_bush_thr > 1)
     uint32_t thr_spawn_hi, thr_spawn_lo;   // two-level draw: event <=> (h << 32 | r) < (hi << 32 | lo)
     uint32_t thr_init_hi, thr_init_lo;
-    uint32_t spawn_cand_mask;              // half-word can be <= thr_spawn_hi only if (h & mask) == 0
     uint32_t n_bush_thr;
     uint64_t thr_keep;             // kept <=> word >= thr_keep
     const uint32_t* bush_thr;      // device table, n_bush_thr entries
@@ -221,19 +222,26 @@ WAB_HD uint32_t bush_alive(const Params& P, const Env& E, const Slots& S, int32_
 }
 
 // ---- two-level draws (oracle/keyed_rng.py): U = (h << 32 | r) * 2^-48, 8 half-words h per primary call.
-// Cheap superset test on a primary call: can any of its 8 half-words be <= thr_hi ?  (zero-field detection on
-// the bits above bit_length(thr_hi))
-WAB_HD bool any_candidate(const Params& P, const uint32_t w[4]) {
-    uint32_t z = 0;
+// Smallest of the 8 half-words of a primary call (DPX three-way SIMD min on the device): some draw of the
+// call can be below the threshold only if this is <= thr_hi.
+WAB_HD uint32_t min_halfword(const uint32_t w[4]) {
+#if defined(__CUDA_ARCH__)
+    uint32_t m = __vimin3_u16x2(w[0], w[1], w[2]);
+    m = __vimin3_u16x2(m, w[3], w[3]);
+    const uint32_t a = m & 0xFFFFu, b = m >> 16;
+    return a < b ? a : b;
+#else
+    uint32_t best = 0xFFFFu;
     for (int k = 0; k < 4; ++k) {
-        const uint32_t t = w[k] & P.spawn_cand_mask;
-        z |= (t - 0x00010001u) & ~t & 0x80008000u;
+        const uint32_t a = w[k] & 0xFFFFu, b = w[k] >> 16;
+        best = a < best ? a : best; best = b < best ? b : best;
     }
-    return z != 0u;
+    return best;
+#endif
 }
 // Exact decision for the 8 draws of primary call `grp`: bit k set <=> draw 8*grp + k is below the threshold.
 // The secondary call is evaluated only for a half-word equal to thr_hi (probability 2^-16).
-WAB_HD uint32_t two_level_hits(const Params& P, uint32_t env_id, uint32_t episode, uint32_t site, uint32_t turn,
+WAB_HD_RARE uint32_t two_level_hits(const Params& P, uint32_t env_id, uint32_t episode, uint32_t site, uint32_t turn,
                                uint32_t grp, uint32_t thr_hi, uint32_t thr_lo) {
     uint32_t w[4];
     philox(P, env_id, episode, ctr2(site, turn, 0), grp, w);
@@ -241,6 +249,7 @@ WAB_HD uint32_t two_level_hits(const Params& P, uint32_t env_id, uint32_t episod
     WAB_ROLLED
     for (uint32_t k = 0; k < 8u; ++k) {
         const uint32_t h = (pick4(w, k >> 1) >> (16u * (k & 1u))) & 0xFFFFu;
+        if (h > thr_hi) continue;
         bool hit = h < thr_hi;
         if (!hit && h == thr_hi && thr_lo != 0u) {
             const uint32_t j = 8u * grp + k;
@@ -460,11 +469,11 @@ WAB_HD void env_step(const Params& P, Env& E, const Slots& S, uint32_t action, S
         for (int grp = (int)coop.sub; grp < RING_CALLS; grp += LPE) {
             uint32_t w[4];
             philox(P, E.env_id, E.episode, ctr2(SITE_SPAWN, E.turn, 0), (uint32_t)grp, w);
-            hitgroups |= (any_candidate(P, w) ? 1u : 0u) << grp;
+            hitgroups |= (min_halfword(w) <= P.thr_spawn_hi ? 1u : 0u) << grp;
         }
         hitgroups = group_or(coop, hitgroups);
         WAB_ROLLED
-        while (hitgroups) {                        // rare (2 * 48 / 1024 per step): settle the candidates exactly
+        while (hitgroups) {                        // rare (48 * 33 / 65536 per step): settle the candidates exactly
 #if defined(__CUDA_ARCH__)
             const int grp = __ffs((int)hitgroups) - 1;
 #else

@@ -55,12 +55,6 @@ inline void params_from_config(const WabConfig& c, const uint32_t* bush_thr_host
     P.thr_bush2 = n_bush_thr > 1 ? bush_thr[1] : 0xFFFFFFFFu;
     P.thr_spawn_hi = cfg->thr_spawn_hi; P.thr_spawn_lo = cfg->thr_spawn_lo;
     P.thr_init_hi = cfg->thr_init_hi; P.thr_init_lo = cfg->thr_init_lo; P.thr_keep = cfg->thr_keep;
-    {   // candidate mask: a half-word h can only satisfy h <= hi if its bits above bit_length(hi) are clear
-        uint32_t bits = 0;
-        while (bits < 17 && (cfg->thr_spawn_hi >> bits) != 0u) ++bits;
-        const uint32_t m = 0xFFFFu & ~((1u << bits) - 1u);
-        P.spawn_cand_mask = m | (m << 16);
-    }
     P.act_tbl = 0;
     for (int a = 0; a < cfg->n_actions; ++a) {
         const uint64_t code = (uint64_t)(cfg->action_dx[a] + 1) | ((uint64_t)(cfg->action_dy[a] + 1) << 2) |
