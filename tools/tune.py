@@ -24,6 +24,19 @@ VARIANTS = {
     "slide3": ["-DWAB_SLIDE_UNROLL=3"],
     "spawn1": ["-DWAB_SPAWN_UNROLL=1"],
     "spawn4": ["-DWAB_SPAWN_UNROLL=4"],
+    "spawn2": ["-DWAB_SPAWN_UNROLL=2"],
+    "spawn3": ["-DWAB_SPAWN_UNROLL=3"],
+    "slide2": ["-DWAB_SLIDE_UNROLL=2"],
+    "s2s2": ["-DWAB_SLIDE_UNROLL=2", "-DWAB_SPAWN_UNROLL=2"],
+    "s3s3": ["-DWAB_SLIDE_UNROLL=3", "-DWAB_SPAWN_UNROLL=3"],
+    "s2s2mb5": ["-DWAB_SLIDE_UNROLL=2", "-DWAB_SPAWN_UNROLL=2", "-DWAB_MIN_BLOCKS_LPE1=5"],
+    "s3s3mb5": ["-DWAB_SLIDE_UNROLL=3", "-DWAB_SPAWN_UNROLL=3", "-DWAB_MIN_BLOCKS_LPE1=5"],
+    "s6s6mb4": ["-DWAB_SLIDE_UNROLL=6", "-DWAB_SPAWN_UNROLL=6", "-DWAB_MIN_BLOCKS_LPE1=4"],
+    "x_nospawn": ["-DWAB_EXP_NOSPAWN"],
+    "x_noslide": ["-DWAB_EXP_NOSLIDE"],
+    "x_nostore": ["-DWAB_EXP_NOSTORE"],
+    "x_noemit": ["-DWAB_EXP_NOEMIT"],
+    "x_nothing": ["-DWAB_EXP_NOSPAWN", "-DWAB_EXP_NOSLIDE", "-DWAB_EXP_NOEMIT"],
     "t32": ["-DWAB_THREADS_LPEN=32"],
     "t128": ["-DWAB_THREADS_LPEN=128"],
     "lpen5": ["-DWAB_MIN_BLOCKS_LPEN=5"],

@@ -371,7 +371,9 @@ WAB_HD void env_step(const Params& P, Env& E, const Slots& S, uint32_t action, S
     O.overflow = 0;
 
     // ---- :259 generate_bushes for the newly visible line
+#ifndef WAB_EXP_NOSLIDE
     if (dx != 0 || dy != 0) slide_window<LPE>(P, E, S, dx, dy, coop);
+#endif
 
     // ---- :262-264 despawn (keep iff U > chance). rank = ordinal among earlier wolves on the cell.
     if (E.nw) {
@@ -461,6 +463,7 @@ WAB_HD void env_step(const Params& P, Env& E, const Slots& S, uint32_t action, S
     }
 
     // ---- :325-326 spawn_wolves on the 48 ring cells around the moved ostrich: two-level draws, 8 cells per call
+#ifndef WAB_EXP_NOSPAWN   /* tuning experiments only (tools/tune.py): results are WRONG with these defined */
     if (P.wolves) {
         uint32_t hitgroups = 0;
 #if defined(__CUDA_ARCH__)
@@ -501,6 +504,7 @@ WAB_HD void env_step(const Params& P, Env& E, const Slots& S, uint32_t action, S
         }
     }
 
+#endif
     // ---- :328-340 reward, done
     uint32_t outcome;
     if (E.status == 0u) outcome = (E.turn >= (uint32_t)P.max_turns) ? 1u : 0u;

@@ -199,7 +199,11 @@ __device__ __forceinline__ void stream_flush(const uint32_t* stream, const uint2
     for (int c = c_lo + lane; c < c_hi; c += 32) {
         const uint32_t h = hs[c];
         const uint2 lo = lut[h & 0xFFu], hi = lut[h >> 8];
+#ifndef WAB_EXP_NOSTORE
         __stcs(reinterpret_cast<uint4*>(gA) + c, make_uint4(lo.x, lo.y, hi.x, hi.y));
+#else
+        if (lo.x == 0xdeadbeefu) gA[0] = (uint8_t)hi.y;
+#endif
     }
     if (lane < 16) {                                              // ragged head and tail, one byte per lane
         const int head_end = min(c_lo << 4, end);
@@ -356,7 +360,9 @@ wab_step_kernel(const __grid_constant__ Params P, const StatePtrs st, const uint
             write_scalars(out, o, O);
             if (out.features) write_features(out.features, o, O);
         }
+#ifndef WAB_EXP_NOEMIT
         emit_obs<LPE>(stream, lut, c, out.grids, first_byte, O.wm, O.bm);
+#endif
     }
     if (c.writer) store_env<F64>(st, c.idx, E, wolves_s, EPB);
     uint32_t cnt[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
