@@ -68,10 +68,10 @@ typedef struct WabConfig {
     double food_inc;              /* 1 / turns_to_fill_food                       wab_env.py:307-309 */
     double food_dec;              /* 1 / turns_to_empty_food                      wab_env.py:316   */
     double food_obs_scale;        /* turns_to_empty_food                          wab_env.py:452   */
-    /* two-level 48-bit draws (oracle/keyed_rng.py): event iff (h << 32 | r) < T, T = ceil(p * 2^48);
-       hi = T >> 32 (0..65536), lo = T & 0xffffffff                                                  */
-    uint32_t thr_spawn_hi, thr_spawn_lo;   /* U < chance/2                       wab_env.py:572-573 */
-    uint32_t thr_init_hi, thr_init_lo;     /* U < chance/2                       wab_env.py:589-590 */
+    /* binomial-first draws (oracle/keyed_rng.py): K = #{k < 32 : v >= cdf[k]} events among n cells, v a 64-bit
+       draw; cdf[k] = min(ceil(BinomialCDF(n, chance/2; k) * 2^64), 2^64 - 1)                                  */
+    uint64_t spawn_cdf[32];       /* n = 48 ring cells per step                   wab_env.py:571-574 */
+    uint64_t init_cdf[32];        /* n = 121 window cells per reset               wab_env.py:588-591 */
     uint64_t thr_keep;            /* wolf kept iff word >= thr (U > despawn)      wab_env.py:262-264 */
     float reward_table[8];        /* [ate*4 + outcome], outcome 0 alive, 1 finished, 2 starved,
                                      3 killed; the f32 image of the fp64 sums     wab_env.py:328-340 */

@@ -26,18 +26,27 @@ reference is the exact double ``U = w * 2**-32``:
     DESP   t     rank>>2  (wx & 0xffff) | (wy & 0xffff)<<16      rank & 3      wab_env.py:262-264
     START  0     0        0                                      0 food, 1 role  wab_env.py:596-599
 
-The two sites that draw for MANY cells per step with a tiny success probability (48 ring cells per
-step, 121 cells per reset, p = 0.0005) use a *two-level draw* with 48 bits of resolution:
-``U = (h * 2**32 + r) * 2**-48`` where ``h`` is a 16-bit half-word of a PRIMARY call shared by 8
-cells and ``r`` a word of a SECONDARY call shared by 4 cells. ``U < p`` is decided by ``h`` alone
-unless ``h`` equals the top 16 bits of the threshold (probability 2**-16), so an implementation
-evaluates the secondary call lazily; the draw itself is an exact, iid uniform either way.
+The two sites that draw for MANY cells at once with a tiny success probability (48 ring cells per step,
+W*H cells per reset, p = chance/2 = 0.0005) are *binomial-first*: instead of n independent word draws,
+the n uniforms handed to the reference are generated in the statistically identical order "how many
+succeed, which ones, then each value given its outcome":
 
-    site   turn  primary (sub 0)                    secondary (sub 1)          cite
-    INIT   0     payload c>>3, half-word c&7        payload c>>2, lane c&3     wab_env.py:588-591   c = (x+W//2)*H + (y+H//2)
-    SPAWN  t     payload j>>3, half-word j&7        payload j>>2, lane j&3     wab_env.py:571-574   j = ring index (below)
+    primary    call (site, turn, sub 0, payload 0):      v = w0 << 32 | w1            (64 bits)
+               K = #{k < 32 : v >= T_k},  T_k = min(ceil(BinomialCDF(n, p; k) * 2**64), 2**64 - 1),  K <= n
+    choice     call (site, turn, sub 1, payload i >> 2), word i & 3 -> r_i,  i = 0 .. K-1:
+               q_i = (r_i * (n - i)) >> 32 ; cell_i = the q_i-th (ascending) index not chosen so far
+    value      call (site, turn, sub 2, payload j >> 2), word j & 3 -> V_j = word * 2**-32, j = 0 .. n-1:
+               U_j = p * V_j              if j was chosen      (always <  p)
+               U_j = p + (1 - p) * V_j    otherwise            (always >= p)
 
-(half-word k of a call = bits 16*(k&1) .. 16*(k&1)+15 of word k>>1.)
+(K ~ Binomial(n, p), a uniformly random K-subset, U | success ~ U(0, p), U | failure ~ U(p, 1): the joint
+law of (U_0 .. U_{n-1}) is exactly n iid uniforms, up to the 2**-64 / 2**-32 granularity of the tables.)
+The reference evaluates ``U_j < p`` on all n values; a fast implementation needs ONE Philox call and one
+64-bit compare (``v < T_0``, probability (1-p)**n = 97.6 % for the ring) to know that nothing happens.
+
+    site   turn  n                      index                                   cite
+    INIT   0     W * H                  c = (x+W//2)*H + (y+H//2)               wab_env.py:588-591
+    SPAWN  t     ring cells (48)        j = ring index (below)                  wab_env.py:571-574
 
 ``ring index``: cells of the (W+2m)x(H+2m) box around the (already moved) ostrich minus its WxH
 view, enumerated box-x-major then box-y, skipping interior cells. ``rank``: ordinal of a wolf
@@ -105,19 +114,52 @@ def bush_words(seed, env_id, episode, x, y):
     return _draw(seed, env_id, episode, SITE_BUSH, 0, 0, _pack_xy(x >> 1, y >> 1), (x & 1) | ((y & 1) << 1))
 
 
-def two_level_units(seed, env_id, episode, site, turn, index):
-    """Exact doubles U = (h * 2**32 + r) * 2**-48 for the cells `index` of a two-level site."""
+BINOMIAL_TABLE = 32   # thresholds kept; configurations whose tail beyond this is not negligible are rejected
+
+
+def binomial_thresholds(n, p):
+    """T_k = min(ceil(CDF(k) * 2**64), 2**64 - 1) for k = 0 .. 31, exact rational arithmetic on the double p."""
+    from fractions import Fraction
+    from math import comb
+    n = int(n)
+    p = min(max(Fraction(float(p)), Fraction(0)), Fraction(1))
+    out, cdf = [], Fraction(0)
+    for k in range(BINOMIAL_TABLE):
+        if k <= n:
+            cdf += comb(n, k) * p ** k * (1 - p) ** (n - k)
+        t = -((-cdf * (1 << 64)).__floor__())            # ceil
+        out.append(min(int(t), (1 << 64) - 1))
+    return out
+
+
+def binomial_first(seed, env_id, episode, site, turn, n, p):
+    """(K, chosen cell indices in choice order) of a binomial-first site."""
+    w = [_draw(seed, env_id, episode, site, turn, 0, 0, lane) for lane in (0, 1)]
+    v = (int(w[0]) << 32) | int(w[1])
+    k = min(sum(1 for t in binomial_thresholds(n, p) if v >= t), int(n))
+    chosen = []
+    free = list(range(int(n)))
+    for i in range(k):
+        r = int(_draw(seed, env_id, episode, site, turn, 1, i >> 2, i & 3))
+        chosen.append(free.pop((r * (int(n) - i)) >> 32))
+    return k, chosen
+
+
+def binomial_first_units(seed, env_id, episode, site, turn, n, p, index):
+    """The exact doubles U_j handed to the reference for the cells `index` (any order) of a binomial-first site."""
     index = np.asarray(index, dtype=np.int64)
-    word = _draw(seed, env_id, episode, site, turn, 0, index >> 3, (index >> 1) & 3).astype(np.uint64)
-    h = (word >> (np.uint64(16) * (index & 1).astype(np.uint64))) & np.uint64(0xFFFF)
-    r = _draw(seed, env_id, episode, site, turn, 1, index >> 2, index & 3).astype(np.uint64)
-    return ((h << np.uint64(32)) | r).astype(np.float64) * (2.0 ** -48)
+    _, chosen = binomial_first(seed, env_id, episode, site, turn, n, p)
+    v = to_unit(_draw(seed, env_id, episode, site, turn, 2, index >> 2, index & 3))
+    hit = np.isin(index, np.asarray(chosen, dtype=np.int64))
+    p = float(p)
+    return np.where(hit, p * v, p + (1.0 - p) * v)
 
 
-def init_units(seed, env_id, episode, x, y, width, height):
+def init_units(seed, env_id, episode, x, y, width, height, p):
     x = np.asarray(x, dtype=np.int64)
     y = np.asarray(y, dtype=np.int64)
-    return two_level_units(seed, env_id, episode, SITE_INIT, 0, (x + width // 2) * height + (y + height // 2))
+    return binomial_first_units(seed, env_id, episode, SITE_INIT, 0, width * height, p,
+                                (x + width // 2) * height + (y + height // 2))
 
 
 def ring_index(dx, dy, width, height, margin):
@@ -135,8 +177,13 @@ def ring_index(dx, dy, width, height, margin):
     return full_before + mid_before + within
 
 
-def spawn_units(seed, env_id, episode, turn, dx, dy, width, height, margin):
-    return two_level_units(seed, env_id, episode, SITE_SPAWN, turn, ring_index(dx, dy, width, height, margin))
+def ring_size(width, height, margin):
+    return (width + 2 * margin) * (height + 2 * margin) - width * height
+
+
+def spawn_units(seed, env_id, episode, turn, dx, dy, width, height, margin, p):
+    return binomial_first_units(seed, env_id, episode, SITE_SPAWN, turn, ring_size(width, height, margin), p,
+                                ring_index(dx, dy, width, height, margin))
 
 
 def despawn_words(seed, env_id, episode, turn, wx, wy):

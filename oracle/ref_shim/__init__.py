@@ -139,7 +139,8 @@ class _KeyedRandom:
             cells = frame.f_locals["new_wolves"]
             seed, eid, ep = _env_key(env)
             opts = env.game_options
-            units = kr.init_units(seed, eid, ep, _ints(cells["x"]), _ints(cells["y"]), opts["width"], opts["height"])
+            units = kr.init_units(seed, eid, ep, _ints(cells["x"]), _ints(cells["y"]), opts["width"], opts["height"],
+                                  opts["chance_wolf_on_square"] / 2)
             return self._checked(units, size, site)
         elif site == "spawn_wolves":  # :571-574
             env = frame.f_locals["self"]
@@ -151,7 +152,7 @@ class _KeyedRandom:
             units = kr.spawn_units(
                 seed, eid, ep, env.current_turn,
                 _ints(cells["x"]) - ox, _ints(cells["y"]) - oy,
-                opts["width"], opts["height"], opts["wolf_spawn_margin"],
+                opts["width"], opts["height"], opts["wolf_spawn_margin"], opts["chance_wolf_on_square"] / 2,
             )
             return self._checked(units, size, site)
         elif site == "step":  # despawn, :262-264

@@ -43,6 +43,7 @@ typedef struct { int32_t x, y, food; } BushRec;
 struct WabOracleEnv {
     WabOracleConfig cfg;
     uint32_t *thr; uint8_t *mlook, *mgath;
+    uint64_t spawn_cdf[32], init_cdf[32];
     uint64_t seed, env_id; int64_t episode;
     int32_t turn;
     int32_t ox, oy; double food; int32_t role, status;      /* self.ostriches row 0 */
@@ -65,15 +66,28 @@ static uint32_t keyed_word(const WabOracleEnv *e, uint32_t site, uint32_t turn, 
     return out[lane & 3u];
 }
 static double unit(uint32_t w) { return (double)w * (1.0 / 4294967296.0); }
-/* two-level draw of oracle/keyed_rng.py: U = (h * 2^32 + r) * 2^-48, h = half-word (index & 7) of the primary
- * call (sub 0, payload index >> 3), r = word (index & 3) of the secondary call (sub 1, payload index >> 2) */
-static double two_level_unit(const WabOracleEnv *e, uint32_t site, uint32_t turn, uint32_t index) {
-    uint32_t word = keyed_word(e, site, turn, 0, index >> 3, (index >> 1) & 3u);
-    uint32_t h = (word >> (16u * (index & 1u))) & 0xFFFFu;
-    uint32_t r = keyed_word(e, site, turn, 1, index >> 2, index & 3u);
-    return ((double)h * 4294967296.0 + (double)r) * (1.0 / 281474976710656.0);
-}
 static uint32_t pack_xy(int32_t x, int32_t y) { return ((uint32_t)x & 0xFFFFu) | (((uint32_t)y & 0xFFFFu) << 16); }
+
+/* binomial-first sites of oracle/keyed_rng.py: the n uniforms U_j the reference compares with p.
+ * chosen[] (n bytes) marks the K cells that succeed; U_j = p * V_j for them, p + (1 - p) * V_j otherwise. */
+static void binomial_first_choose(const WabOracleEnv *e, uint32_t site, uint32_t turn, int32_t n, const uint64_t *cdf,
+                                  uint8_t *chosen) {
+    uint64_t v = ((uint64_t)keyed_word(e, site, turn, 0, 0, 0) << 32) | keyed_word(e, site, turn, 0, 0, 1);
+    int32_t k = 0;
+    for (int32_t t = 0; t < 32; ++t) k += (v >= cdf[t]);
+    if (k > n) k = n;
+    memset(chosen, 0, (size_t)n);
+    for (int32_t i = 0; i < k; ++i) {
+        uint32_t r = keyed_word(e, site, turn, 1, (uint32_t)i >> 2, (uint32_t)i & 3u);
+        int32_t q = (int32_t)(((uint64_t)r * (uint64_t)(n - i)) >> 32);
+        for (int32_t j = 0; j < n; ++j)            /* the q-th index not chosen so far */
+            if (!chosen[j] && q-- == 0) { chosen[j] = 1; break; }
+    }
+}
+static double binomial_first_unit(const WabOracleEnv *e, uint32_t site, uint32_t turn, uint32_t j, int hit, double p) {
+    double v = unit(keyed_word(e, site, turn, 2, j >> 2, j & 3u));
+    return hit ? p * v : p + (1.0 - p) * v;
+}
 
 /* ------------------------------------------------------------------ bush record store */
 static uint32_t cell_hash(int32_t x, int32_t y) {
@@ -150,25 +164,33 @@ static void generate_bushes(WabOracleEnv *e) {
 static void initialize_wolves(WabOracleEnv *e) {
     const int32_t hw = e->cfg.width / 2, hh = e->cfg.height / 2;
     const double p = e->cfg.chance_wolf_on_square / 2;                  /* :590 */
+    const int32_t n = e->cfg.width * e->cfg.height;
+    uint8_t *chosen = (uint8_t *)malloc((size_t)n);
+    binomial_first_choose(e, SITE_INIT, 0, n, e->init_cdf, chosen);
     for (int32_t x = e->ox - hw; x <= e->ox + hw; ++x)
         for (int32_t y = e->oy - hh; y <= e->oy + hh; ++y) {
             uint32_t c = (uint32_t)((x - e->ox + hw) * e->cfg.height + (y - e->oy + hh));
-            if (two_level_unit(e, SITE_INIT, 0, c) < p) wolf_add(e, x, y);
+            if (binomial_first_unit(e, SITE_INIT, 0, c, chosen[c], p) < p) wolf_add(e, x, y);
         }
+    free(chosen);
 }
 
 /* spawn_wolves, wab_env.py:527-576 */
 static void spawn_wolves(WabOracleEnv *e) {
     const int32_t hw = e->cfg.width / 2, hh = e->cfg.height / 2, m = e->cfg.wolf_spawn_margin;
     const double p = e->cfg.chance_wolf_on_square / 2;                  /* :573 */
+    const int32_t n = (e->cfg.width + 2 * m) * (e->cfg.height + 2 * m) - e->cfg.width * e->cfg.height;
+    uint8_t *chosen = (uint8_t *)malloc((size_t)n);
+    binomial_first_choose(e, SITE_SPAWN, (uint32_t)e->turn, n, e->spawn_cdf, chosen);
     uint32_t j = 0;
     for (int32_t x = e->ox - hw - m; x < e->ox + hw + m + 1; ++x)        /* :536-547 */
         for (int32_t y = e->oy - hh - m; y < e->oy + hh + m + 1; ++y) {  /* :549-560 */
             int visible = (x >= e->ox - hw && x <= e->ox + hw && y >= e->oy - hh && y <= e->oy + hh);
             if (visible) continue;                                       /* :566 */
-            if (two_level_unit(e, SITE_SPAWN, (uint32_t)e->turn, j) < p) wolf_add(e, x, y);
+            if (binomial_first_unit(e, SITE_SPAWN, (uint32_t)e->turn, j, chosen[j], p) < p) wolf_add(e, x, y);
             ++j;
         }
+    free(chosen);
 }
 
 /* update_master_df_and_distances, wab_env.py:504-508: the frame the kill/eat/obs code reads */
@@ -210,6 +232,7 @@ WabOracleEnv *wab_oracle_create(const WabOracleConfig *cfg, uint64_t seed, uint6
     if (!cfg || cfg->width % 2 == 0 || cfg->height % 2 == 0) return NULL;  /* :147-148 */
     if (cfg->n_actions < 1 || cfg->n_actions > WAB_ORACLE_MAX_ACTIONS) return NULL;
     if (cfg->restrict_view && (!cfg->mask_lookout || !cfg->mask_gatherer)) return NULL;
+    if (!cfg->spawn_cdf || !cfg->init_cdf) return NULL;
     WabOracleEnv *e = (WabOracleEnv *)calloc(1, sizeof(*e));
     e->cfg = *cfg;
     e->thr = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(cfg->n_bush_thr > 0 ? cfg->n_bush_thr : 1));
@@ -218,6 +241,8 @@ WabOracleEnv *wab_oracle_create(const WabOracleConfig *cfg, uint64_t seed, uint6
     if (cfg->mask_lookout) { e->mlook = (uint8_t *)malloc(cells); memcpy(e->mlook, cfg->mask_lookout, cells); }
     if (cfg->mask_gatherer) { e->mgath = (uint8_t *)malloc(cells); memcpy(e->mgath, cfg->mask_gatherer, cells); }
     e->cfg.bush_thr = e->thr; e->cfg.mask_lookout = e->mlook; e->cfg.mask_gatherer = e->mgath;
+    memcpy(e->spawn_cdf, cfg->spawn_cdf, sizeof(e->spawn_cdf)); memcpy(e->init_cdf, cfg->init_cdf, sizeof(e->init_cdf));
+    e->cfg.spawn_cdf = e->spawn_cdf; e->cfg.init_cdf = e->init_cdf;
     e->seed = seed; e->env_id = env_id; e->episode = -1;
     e->capw = 8; e->wx = (int32_t *)malloc(sizeof(int32_t) * 8); e->wy = (int32_t *)malloc(sizeof(int32_t) * 8);
     e->caprec = 1024; e->recs = (BushRec *)malloc(sizeof(BushRec) * 1024);

@@ -32,6 +32,7 @@ class OracleConfig(ctypes.Structure):
         ("reward_for_eating", ctypes.c_double),
         ("bush_thr", ctypes.POINTER(ctypes.c_uint32)), ("n_bush_thr", ctypes.c_int32),
         ("mask_lookout", ctypes.POINTER(ctypes.c_uint8)), ("mask_gatherer", ctypes.POINTER(ctypes.c_uint8)),
+        ("spawn_cdf", ctypes.POINTER(ctypes.c_uint64)), ("init_cdf", ctypes.POINTER(ctypes.c_uint64)),
     ]
 
 
@@ -107,6 +108,12 @@ class _ConfigHolder:
         self._thr = np.ascontiguousarray(self.game.bush_thr, dtype=np.uint32)
         c.bush_thr = self._thr.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))
         c.n_bush_thr = len(self._thr)
+        from . import keyed_rng as kr
+        p = o["chance_wolf_on_square"] / 2
+        self._scdf = np.asarray(kr.binomial_thresholds(kr.ring_size(c.width, c.height, c.wolf_spawn_margin), p), dtype=np.uint64)
+        self._icdf = np.asarray(kr.binomial_thresholds(c.width * c.height, p), dtype=np.uint64)
+        c.spawn_cdf = self._scdf.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))
+        c.init_cdf = self._icdf.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))
         if c.width == 11 and c.height == 11:
             self._ml = np.ascontiguousarray(LOOKOUT_TILE_MASK, dtype=np.uint8)
             self._mg = np.ascontiguousarray(GATHERER_TILE_MASK, dtype=np.uint8)

@@ -70,18 +70,7 @@ static uint32_t do_reset(HostSim* h, uint32_t wm[4], uint32_t bm[4]) {
     uint32_t m[4] = {0, 0, 0, 0};
     for (int blk = 0; blk < 36; ++blk) reset_bush_block(h->P, h->E.env_id, h->E.episode, blk, m);
     for (int w = 0; w < 4; ++w) h->E.m[w] = m[w];
-    if (h->P.wolves)
-        for (int grp = 0; grp < INIT_CALLS; ++grp) {
-            uint32_t hits = reset_init_group(h->P, h->E.env_id, h->E.episode, grp);
-            for (int l = 0; l < 8; ++l)
-                if ((hits >> l) & 1u) {
-                    int c = 8 * grp + l;
-                    if (h->E.nw < (uint32_t)h->P.wolf_cap) {
-                        h->S.wolves[h->E.nw] = pack_xy(c / 11 - HALF, c % 11 - HALF);
-                        h->E.nw += 1;
-                    } else overflow = 1;
-                }
-        }
+    if (h->P.wolves) reset_init_wolves(h->P, h->E, h->S, overflow);
     wolf_plane(h->E, h->S, wm);
     for (int w = 0; w < 4; ++w) bm[w] = h->E.m[w];
     return overflow;

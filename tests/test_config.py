@@ -47,17 +47,19 @@ def test_probability_thresholds_are_exact(p):
             assert (u > p) == (w >= gt), (p, w)
 
 
-@pytest.mark.parametrize("p", [0.0005, 0.006, 0.25, 1e-9, 2.0 ** -16, 33 * 2.0 ** -16, 0.0, 1.0])
-def test_48_bit_threshold_is_exact(p):
-    t = C.lt_threshold48(p)
-    for v in {0, 1, t - 2, t - 1, t, t + 1, (t >> 32) << 32, ((t >> 32) << 32) - 1, 2 ** 48 - 1}:
-        if 0 <= v < 2 ** 48:
-            assert (v * 2.0 ** -48 < p) == (v < t), (p, v)
+def test_binomial_first_tables():
+    from oracle import keyed_rng as kr
+    for n, p in ((48, 0.0005), (121, 0.0005), (48, 0.006), (48, 0.0), (121, 0.01)):
+        t = C.binomial_thresholds(n, p)
+        assert t == kr.binomial_thresholds(n, p) and len(t) == 32 and all(a <= b for a, b in zip(t, t[1:]))
+        assert abs(t[0] / 2 ** 64 - (1 - p) ** n) < 1e-12
+    with pytest.raises(ValueError):
+        C.binomial_thresholds(48, 0.6)
 
 
 def test_default_thresholds_values():
     g = C.GameConfig.from_options()
-    assert g.thr_spawn == math.ceil(Fraction(0.0005) * 2 ** 48) and g.thr_spawn >> 32 == 32
+    assert g.spawn_cdf[0] == math.ceil((1 - Fraction(0.0005)) ** 48 * 2 ** 64)
     assert g.thr_keep == math.floor(Fraction(0.05) * 2 ** 32) + 1
     assert g.n_actions == 5 and g.food_mode == C.WAB_FOOD_INT and g.food_int == (40, 5, 40)
 
@@ -105,7 +107,8 @@ def test_integer_food_proof():
 def test_validation_errors():
     with pytest.raises(ValueError):
         C.GameConfig.from_options({"width": 10})                      # wab_env.py:147-148
-    assert C.GameConfig.from_options({"chance_wolf_on_square": 2.5}).thr_spawn == 1 << 48     # p >= 1: always
+    with pytest.raises(ValueError):
+        C.GameConfig.from_options({"chance_wolf_on_square": 2.5})
     with pytest.raises(ValueError):
         C.GameConfig.from_options({"max_turns": 10 ** 6})
 

@@ -86,7 +86,7 @@ def test_bad_action_is_flagged_and_treated_as_stay():
 
 
 def test_wolf_and_log_overflow_are_reported():
-    sim = HostSimEnv({"chance_wolf_on_square": 0.5, "wolf_chance_to_despawn": 0.0, "god_mode": True}, wolf_cap=2)
+    sim = HostSimEnv({"chance_wolf_on_square": 0.1, "wolf_chance_to_despawn": 0.0, "god_mode": True}, wolf_cap=2)
     (_, ovf) = sim.reset()
     seen = ovf
     for _ in range(5):

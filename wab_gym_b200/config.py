@@ -87,10 +87,8 @@ class WabConfigStruct(ctypes.Structure):
         ("food_inc", ctypes.c_double),
         ("food_dec", ctypes.c_double),
         ("food_obs_scale", ctypes.c_double),
-        ("thr_spawn_hi", ctypes.c_uint32),
-        ("thr_spawn_lo", ctypes.c_uint32),
-        ("thr_init_hi", ctypes.c_uint32),
-        ("thr_init_lo", ctypes.c_uint32),
+        ("spawn_cdf", ctypes.c_uint64 * 32),
+        ("init_cdf", ctypes.c_uint64 * 32),
         ("thr_keep", ctypes.c_uint64),
         ("reward_table", ctypes.c_float * 8),
         ("mask_lookout", ctypes.c_uint32 * 4),
@@ -115,10 +113,23 @@ def lt_threshold(p: float) -> int:
     return min(max(t, 0), 1 << 32)
 
 
-def lt_threshold48(p: float) -> int:
-    """Least integer T with: for a 48-bit draw v, (v * 2**-48 < p)  <=>  (v < T). Exact (rational arithmetic)."""
-    t = math.ceil(Fraction(float(p)) * (1 << 48))
-    return min(max(t, 0), 1 << 48)
+BINOMIAL_TABLE = 32
+
+
+def binomial_thresholds(n: int, p: float) -> List[int]:
+    """Inverse-CDF table of the binomial-first draws: T_k = min(ceil(CDF_{n,p}(k) * 2**64), 2**64 - 1), k < 32, in
+    exact rational arithmetic on the double p. With a 64-bit draw v, the number of events among n cells is
+    K = #{k : v >= T_k}. Raises when the mass beyond the table is not negligible (absurdly large chances)."""
+    n = int(n)
+    pf = min(max(Fraction(float(p)), Fraction(0)), Fraction(1))
+    out, cdf = [], Fraction(0)
+    for k in range(BINOMIAL_TABLE):
+        if k <= n:
+            cdf += math.comb(n, k) * pf ** k * (1 - pf) ** (n - k)
+        out.append(min(int(math.ceil(cdf * (1 << 64))), (1 << 64) - 1))
+    if 1 - cdf > Fraction(1, 1 << 40):
+        raise ValueError("chance_wolf_on_square is too large for the binomial-first draw table (n=%d, p=%g)" % (n, float(p)))
+    return out
 
 
 def gt_threshold(q: float) -> int:
@@ -219,7 +230,8 @@ class GameConfig:
     options: Dict[str, object]
     actions: List[Tuple[int, int, int]]
     bush_thr: np.ndarray
-    thr_spawn: int
+    spawn_cdf: List[int]
+    init_cdf: List[int]
     thr_keep: int
     food_mode: int
     food_int: Tuple[int, int, int]
@@ -245,7 +257,9 @@ class GameConfig:
         if not (1 <= max_turns <= 30000):
             raise ValueError("max_turns must be in [1, 30000] (positions are int16 on the device)")
         p_spawn = opts["chance_wolf_on_square"] / 2  # wab_env.py:573, :590
-        thr_spawn = lt_threshold48(p_spawn)
+        ring = (width + 2 * int(opts["wolf_spawn_margin"])) * (height + 2 * int(opts["wolf_spawn_margin"])) - width * height
+        spawn_cdf = binomial_thresholds(ring, p_spawn)
+        init_cdf = binomial_thresholds(width * height, p_spawn)
         thr_keep = gt_threshold(opts["wolf_chance_to_despawn"])
         proof = None
         if auto_reset and not force_f64_food:
@@ -271,7 +285,8 @@ class GameConfig:
             options=opts,
             actions=action_table(opts),
             bush_thr=bush_thresholds(opts["bush_power"], opts["max_berries_per_bush"]),
-            thr_spawn=thr_spawn,
+            spawn_cdf=spawn_cdf,
+            init_cdf=init_cdf,
             thr_keep=thr_keep,
             food_mode=WAB_FOOD_INT if proof else WAB_FOOD_F64,
             food_int=proof or (0, 0, 0),
@@ -305,8 +320,8 @@ class GameConfig:
         s.food_inc = 1 / o["turns_to_fill_food"]
         s.food_dec = 1 / o["turns_to_empty_food"]
         s.food_obs_scale = float(o["turns_to_empty_food"])
-        s.thr_spawn_hi, s.thr_spawn_lo = self.thr_spawn >> 32, self.thr_spawn & 0xFFFFFFFF
-        s.thr_init_hi, s.thr_init_lo = s.thr_spawn_hi, s.thr_spawn_lo
+        for k in range(BINOMIAL_TABLE):
+            s.spawn_cdf[k], s.init_cdf[k] = self.spawn_cdf[k], self.init_cdf[k]
         s.thr_keep = self.thr_keep
         for k in range(8):
             s.reward_table[k] = float(np.float32(self.reward_table64[k]))

@@ -42,7 +42,6 @@ enum : uint32_t { SITE_BUSH = 1, SITE_INIT = 2, SITE_SPAWN = 3, SITE_DESP = 4, S
 
 constexpr int kSlideUnroll = WAB_SLIDE_UNROLL, kSpawnUnroll = WAB_SPAWN_UNROLL;
 constexpr int VIEW = 11, HALF = 5, CELLS = 121, RING = 48;
-constexpr int RING_CALLS = RING / 8, INIT_CALLS = (CELLS + 7) / 8;   // 8 two-level draws per primary Philox call
 constexpr int OBS_BYTES = 3 * CELLS;        // 363 bytes per env: wolves, bushes, ostriches
 constexpr uint32_t TOP_WORD_MASK = 0x01FFFFFFu;  // 121 = 3*32 + 25
 
@@ -63,8 +62,7 @@ struct Params {
     uint32_t rk0[10], rk1[10];     // Philox round keys (key is uniform: the seed)
     uint32_t thr_bush1;            // food0 > 0  <=>  word >= thr_bush1   (bush_thr[0])
     uint32_t thr_bush2;            // food0 > 1  <=>  word >= thr_bush2   (bush_thr[1]; only read when n_bush_thr > 1)
-    uint32_t thr_spawn_hi, thr_spawn_lo;   // two-level draw: event <=> (h << 32 | r) < (hi << 32 | lo)
-    uint32_t thr_init_hi, thr_init_lo;
+    uint64_t spawn_cdf[32], init_cdf[32];  // binomial-first tables: K = #{k : v >= cdf[k]} (oracle/keyed_rng.py)
     uint32_t n_bush_thr;
     uint64_t thr_keep;             // kept <=> word >= thr_keep
     const uint32_t* bush_thr;      // device table, n_bush_thr entries
@@ -221,45 +219,34 @@ WAB_HD uint32_t bush_alive(const Params& P, const Env& E, const Slots& S, int32_
     return alive_after(P, word, (uint32_t)S.logcnt[(int64_t)l * S.lstride]);
 }
 
-// ---- two-level draws (oracle/keyed_rng.py): U = (h << 32 | r) * 2^-48, 8 half-words h per primary call.
-// Smallest of the 8 half-words of a primary call (DPX three-way SIMD min on the device): some draw of the
-// call can be below the threshold only if this is <= thr_hi.
-WAB_HD uint32_t min_halfword(const uint32_t w[4]) {
-#if defined(__CUDA_ARCH__)
-    uint32_t m = __vimin3_u16x2(w[0], w[1], w[2]);
-    m = __vimin3_u16x2(m, w[3], w[3]);
-    const uint32_t a = m & 0xFFFFu, b = m >> 16;
-    return a < b ? a : b;
-#else
-    uint32_t best = 0xFFFFu;
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t a = w[k] & 0xFFFFu, b = w[k] >> 16;
-        best = a < best ? a : best; best = b < best ? b : best;
-    }
-    return best;
-#endif
-}
-// Exact decision for the 8 draws of primary call `grp`: bit k set <=> draw 8*grp + k is below the threshold.
-// The secondary call is evaluated only for a half-word equal to thr_hi (probability 2^-16).
-WAB_HD_RARE uint32_t two_level_hits(const Params& P, uint32_t env_id, uint32_t episode, uint32_t site, uint32_t turn,
-                               uint32_t grp, uint32_t thr_hi, uint32_t thr_lo) {
+// ---- binomial-first sites (oracle/keyed_rng.py): the spawn ring of a step and the window of a reset.
+// One Philox call gives a 64-bit draw v; nothing happens iff v < cdf[0] (97.6 % for the ring). Otherwise
+// K = #{k : v >= cdf[k]} cells succeed and are chosen one by one among the cells still free.
+WAB_HD uint64_t binomial_draw(const Params& P, uint32_t env_id, uint32_t episode, uint32_t site, uint32_t turn) {
     uint32_t w[4];
-    philox(P, env_id, episode, ctr2(site, turn, 0), grp, w);
-    uint32_t hits = 0;
+    philox(P, env_id, episode, ctr2(site, turn, 0), 0u, w);
+    return ((uint64_t)w[0] << 32) | (uint64_t)w[1];
+}
+// Rare path: the chosen cell indices, as a bit mask over n <= 128 cells (bit j of mask[j >> 5]).
+WAB_HD_RARE void binomial_choose(const Params& P, uint32_t env_id, uint32_t episode, uint32_t site, uint32_t turn,
+                                 int32_t n, const uint64_t* cdf, uint64_t v, uint32_t mask[4]) {
+    int32_t k = 0;
     WAB_ROLLED
-    for (uint32_t k = 0; k < 8u; ++k) {
-        const uint32_t h = (pick4(w, k >> 1) >> (16u * (k & 1u))) & 0xFFFFu;
-        if (h > thr_hi) continue;
-        bool hit = h < thr_hi;
-        if (!hit && h == thr_hi && thr_lo != 0u) {
-            const uint32_t j = 8u * grp + k;
-            uint32_t r[4];
-            philox(P, env_id, episode, ctr2(site, turn, 1), j >> 2, r);
-            hit = pick4(r, j & 3u) < thr_lo;
+    for (int t = 0; t < 32; ++t) k += (v >= cdf[t]) ? 1 : 0;
+    k = k > n ? n : k;
+    mask[0] = mask[1] = mask[2] = mask[3] = 0u;
+    uint32_t r[4] = {0u, 0u, 0u, 0u};
+    WAB_ROLLED
+    for (int32_t i = 0; i < k; ++i) {
+        if ((i & 3) == 0) philox(P, env_id, episode, ctr2(site, turn, 1), (uint32_t)(i >> 2), r);
+        int32_t q = (int32_t)(((uint64_t)pick4(r, (uint32_t)i & 3u) * (uint64_t)(uint32_t)(n - i)) >> 32);
+        WAB_ROLLED
+        for (int32_t j = 0; j < n; ++j) {                 // the q-th cell not chosen so far
+            const uint32_t bit = 1u << (j & 31);
+            const uint32_t word = (j >> 5) == 0 ? mask[0] : (j >> 5) == 1 ? mask[1] : (j >> 5) == 2 ? mask[2] : mask[3];
+            if (!(word & bit) && q-- == 0) { setbit128(mask, j, 1u); break; }
         }
-        hits |= (hit ? 1u : 0u) << k;
     }
-    return hits;
 }
 
 // 11-bit value with bit g at stride 11 (positions 11*g), as four words.
@@ -462,48 +449,27 @@ WAB_HD void env_step(const Params& P, Env& E, const Slots& S, uint32_t action, S
         if (E.food_i <= 0) { E.status = 1u; E.food_i = 0; }
     }
 
-    // ---- :325-326 spawn_wolves on the 48 ring cells around the moved ostrich: two-level draws, 8 cells per call
+    // ---- :325-326 spawn_wolves on the 48 ring cells around the moved ostrich: one binomial-first draw
 #ifndef WAB_EXP_NOSPAWN   /* tuning experiments only (tools/tune.py): results are WRONG with these defined */
     if (P.wolves) {
-        uint32_t hitgroups = 0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll kSpawnUnroll
-#endif
-        for (int grp = (int)coop.sub; grp < RING_CALLS; grp += LPE) {
-            uint32_t w[4];
-            philox(P, E.env_id, E.episode, ctr2(SITE_SPAWN, E.turn, 0), (uint32_t)grp, w);
-            hitgroups |= (min_halfword(w) <= P.thr_spawn_hi ? 1u : 0u) << grp;
-        }
-        hitgroups = group_or(coop, hitgroups);
-        WAB_ROLLED
-        while (hitgroups) {                        // rare (48 * 33 / 65536 per step): settle the candidates exactly
-#if defined(__CUDA_ARCH__)
-            const int grp = __ffs((int)hitgroups) - 1;
-#else
-            const int grp = __builtin_ctz(hitgroups);
-#endif
-            hitgroups &= hitgroups - 1u;
-            uint32_t hits = two_level_hits(P, E.env_id, E.episode, SITE_SPAWN, E.turn, (uint32_t)grp, P.thr_spawn_hi, P.thr_spawn_lo);
+        const uint64_t v = binomial_draw(P, E.env_id, E.episode, SITE_SPAWN, E.turn);
+        if (v >= P.spawn_cdf[0]) {                 // rare (2.4 % of steps): at least one wolf appears
+            uint32_t chosen[4];
+            binomial_choose(P, E.env_id, E.episode, SITE_SPAWN, E.turn, RING, P.spawn_cdf, v, chosen);
             WAB_ROLLED
-            while (hits) {                                                        // :571-574
-#if defined(__CUDA_ARCH__)
-                const int l = __ffs((int)hits) - 1;
-#else
-                const int l = __builtin_ctz(hits);
-#endif
-                hits &= hits - 1u;
-                int32_t ox, oy;
-                ring_offset(8 * grp + l, ox, oy);
-                if (E.nw < (uint32_t)P.wolf_cap) {
-                    S.wolves[(int32_t)E.nw * S.wstride] = pack_xy(E.x + ox, E.y + oy);
-                    E.nw += 1;
-                } else {
-                    O.overflow = 1u;
+            for (int j = 0; j < RING; ++j)                                        // :571-574, ring order
+                if ((j < 32 ? chosen[0] >> j : chosen[1] >> (j - 32)) & 1u) {
+                    int32_t ox, oy;
+                    ring_offset(j, ox, oy);
+                    if (E.nw < (uint32_t)P.wolf_cap) {
+                        S.wolves[(int32_t)E.nw * S.wstride] = pack_xy(E.x + ox, E.y + oy);
+                        E.nw += 1;
+                    } else {
+                        O.overflow = 1u;
+                    }
                 }
-            }
         }
     }
-
 #endif
     // ---- :328-340 reward, done
     uint32_t outcome;
@@ -548,11 +514,25 @@ WAB_HD void reset_bush_block(const Params& P, uint32_t env_id, uint32_t episode,
     part[2] |= (q == 2) ? lo : ((q == 1) ? hi : 0u);
     part[3] |= (q == 3) ? lo : ((q == 2) ? hi : 0u);
 }
-// wolf-init call grp (0..15): cells c = 8*grp .. 8*grp+7, c = (x+5)*11 + (y+5)  (:578-593) -> 8 hit bits
-WAB_HD uint32_t reset_init_group(const Params& P, uint32_t env_id, uint32_t episode, int grp) {
-    uint32_t hits = two_level_hits(P, env_id, episode, SITE_INIT, 0u, (uint32_t)grp, P.thr_init_hi, P.thr_init_lo);
-    if (grp == INIT_CALLS - 1) hits &= (1u << (CELLS - 8 * (INIT_CALLS - 1))) - 1u;   // cells 121..127 do not exist
-    return hits;
+// initialize_wolves (:578-593): one binomial-first draw over the 121 window cells, c = (x+5)*11 + (y+5).
+// Appends the wolves of a freshly reset env (executed by the lanes that own the env).
+WAB_HD void reset_init_wolves(const Params& P, Env& E, const Slots& S, uint32_t& overflow) {
+    const uint64_t v = binomial_draw(P, E.env_id, E.episode, SITE_INIT, 0u);
+    if (v < P.init_cdf[0]) return;                     // 94 % of resets start without a wolf in view
+    uint32_t chosen[4];
+    binomial_choose(P, E.env_id, E.episode, SITE_INIT, 0u, CELLS, P.init_cdf, v, chosen);
+    WAB_ROLLED
+    for (int c = 0; c < CELLS; ++c) {
+        const uint32_t word = (c >> 5) == 0 ? chosen[0] : (c >> 5) == 1 ? chosen[1] : (c >> 5) == 2 ? chosen[2] : chosen[3];
+        if ((word >> (c & 31)) & 1u) {
+            if (E.nw < (uint32_t)P.wolf_cap) {
+                S.wolves[(int32_t)E.nw * S.wstride] = pack_xy(c / 11 - HALF, c % 11 - HALF);
+                E.nw += 1;
+            } else {
+                overflow = 1u;
+            }
+        }
+    }
 }
 // scalar part of a reset: spawn_ostriches (:595-611)
 template <bool F64>

@@ -102,7 +102,7 @@ __device__ __forceinline__ void store_env(const StatePtrs& st, int64_t idx, cons
 }
 
 // Reset every env of the warp whose `need` is set (wab_env.py:231-248). All 32 lanes must call; the
-// 36 bush-block and 16 wolf-init Philox calls of ONE reset are spread over the 32 lanes whatever
+// 36 bush-block Philox calls of ONE reset are spread over the 32 lanes whatever
 // LPE is. `need` is replicated over the LPE lanes of a group. On return the lanes of a reset env
 // hold the fresh state and its observation planes.
 template <bool F64, int LPE>
@@ -123,29 +123,9 @@ __device__ __forceinline__ void warp_reset(const Params& P, Env& E, const Slots&
         const uint32_t m1 = __reduce_or_sync(FULL, part[1]);
         const uint32_t m2 = __reduce_or_sync(FULL, part[2]);
         const uint32_t m3 = __reduce_or_sync(FULL, part[3]);
-        const uint32_t hits = (P.wolves && lane < INIT_CALLS) ? reset_init_group(P, eid, ep, lane) : 0u;
-        unsigned hl = __ballot_sync(FULL, hits != 0u);
         if (mine) { E.m[0] = m0; E.m[1] = m1; E.m[2] = m2; E.m[3] = m3; }
-        WAB_ROLLED
-        while (hl) {                                              // rare: p = 0.0005 per cell
-            const int src = __ffs((int)hl) - 1;
-            hl &= hl - 1u;
-            const uint32_t h = __shfl_sync(FULL, hits, src);
-            if (mine) {
-                WAB_ROLLED
-                for (int l = 0; l < 8; ++l)
-                    if ((h >> l) & 1u) {
-                        const int c = 8 * src + l;
-                        if (E.nw < (uint32_t)P.wolf_cap) {
-                            S.wolves[(int32_t)E.nw * S.wstride] = pack_xy(c / 11 - HALF, c % 11 - HALF);
-                            E.nw += 1;
-                        } else {
-                            overflow = 1u;
-                        }
-                    }
-            }
-        }
     }
+    if (need && P.wolves) reset_init_wolves(P, E, S, overflow);       // one Philox call per reset env
     if (need) {
         wolf_plane(E, S, wm);
         bm[0] = E.m[0]; bm[1] = E.m[1]; bm[2] = E.m[2]; bm[3] = E.m[3];

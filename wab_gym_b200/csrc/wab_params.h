@@ -23,7 +23,9 @@ inline int validate_config(const WabConfig* cfg, int32_t n_bush_thr, int64_t n_e
         return fail(WAB_E_UNSUPPORTED, "the sm_100a kernels implement the 11x11 viewport only");
     if (cfg->wolf_spawn_margin != 1) return fail(WAB_E_UNSUPPORTED, "the sm_100a kernels implement wolf_spawn_margin = 1 only");
     if (n_envs < 1) return fail(WAB_E_CONFIG, "n_envs must be >= 1");
-    if (cfg->thr_spawn_hi > 65536u || cfg->thr_init_hi > 65536u) return fail(WAB_E_CONFIG, "48-bit thresholds out of range");
+    for (int k = 1; k < 32; ++k)
+        if (cfg->spawn_cdf[k] < cfg->spawn_cdf[k - 1] || cfg->init_cdf[k] < cfg->init_cdf[k - 1])
+            return fail(WAB_E_CONFIG, "binomial-first tables must be non-decreasing");
     if (cfg->n_actions < 1 || cfg->n_actions > WAB_MAX_ACTIONS) return fail(WAB_E_CONFIG, "n_actions out of range");
     if (cfg->max_turns < 1 || cfg->max_turns > 30000) return fail(WAB_E_CONFIG, "max_turns must be in [1, 30000]");
     if (cfg->wolf_cap < 1 || cfg->wolf_cap > 15) return fail(WAB_E_CONFIG, "wolf_cap must be in [1, 15]");
@@ -53,8 +55,8 @@ inline void params_from_config(const WabConfig& c, const uint32_t* bush_thr_host
     P.n_bush_thr = (uint32_t)n_bush_thr;
     P.thr_bush1 = n_bush_thr > 0 ? bush_thr[0] : 0xFFFFFFFFu;
     P.thr_bush2 = n_bush_thr > 1 ? bush_thr[1] : 0xFFFFFFFFu;
-    P.thr_spawn_hi = cfg->thr_spawn_hi; P.thr_spawn_lo = cfg->thr_spawn_lo;
-    P.thr_init_hi = cfg->thr_init_hi; P.thr_init_lo = cfg->thr_init_lo; P.thr_keep = cfg->thr_keep;
+    for (int k = 0; k < 32; ++k) { P.spawn_cdf[k] = cfg->spawn_cdf[k]; P.init_cdf[k] = cfg->init_cdf[k]; }
+    P.thr_keep = cfg->thr_keep;
     P.act_tbl = 0;
     for (int a = 0; a < cfg->n_actions; ++a) {
         const uint64_t code = (uint64_t)(cfg->action_dx[a] + 1) | ((uint64_t)(cfg->action_dy[a] + 1) << 2) |
