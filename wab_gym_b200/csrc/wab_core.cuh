@@ -228,11 +228,16 @@ WAB_HD uint64_t binomial_draw(const Params& P, uint32_t env_id, uint32_t episode
     return ((uint64_t)w[0] << 32) | (uint64_t)w[1];
 }
 // Rare path: the chosen cell indices, as a bit mask over n <= 128 cells (bit j of mask[j >> 5]).
-WAB_HD_RARE void binomial_choose(const Params& P, uint32_t env_id, uint32_t episode, uint32_t site, uint32_t turn,
-                                 int32_t n, const uint64_t* cdf, uint64_t v, uint32_t mask[4]) {
-    int32_t k = 0;
+// The tables are read straight from the kernel parameters (constant bank), never through a pointer.
+WAB_HD void binomial_choose(const Params& P, uint32_t env_id, uint32_t episode, uint32_t site, uint32_t turn,
+                                 int32_t n, uint64_t v, uint32_t mask[4]) {
+    const bool init = site == SITE_INIT;
+    int32_t k = 1;                                       // the caller saw v >= cdf[0]
     WAB_ROLLED
-    for (int t = 0; t < 32; ++t) k += (v >= cdf[t]) ? 1 : 0;
+    for (int t = 1; t < 32; ++t) {
+        if (v < (init ? P.init_cdf[t] : P.spawn_cdf[t])) break;
+        ++k;
+    }
     k = k > n ? n : k;
     mask[0] = mask[1] = mask[2] = mask[3] = 0u;
     uint32_t r[4] = {0u, 0u, 0u, 0u};
@@ -240,12 +245,16 @@ WAB_HD_RARE void binomial_choose(const Params& P, uint32_t env_id, uint32_t epis
     for (int32_t i = 0; i < k; ++i) {
         if ((i & 3) == 0) philox(P, env_id, episode, ctr2(site, turn, 1), (uint32_t)(i >> 2), r);
         int32_t q = (int32_t)(((uint64_t)pick4(r, (uint32_t)i & 3u) * (uint64_t)(uint32_t)(n - i)) >> 32);
-        WAB_ROLLED
-        for (int32_t j = 0; j < n; ++j) {                 // the q-th cell not chosen so far
-            const uint32_t bit = 1u << (j & 31);
-            const uint32_t word = (j >> 5) == 0 ? mask[0] : (j >> 5) == 1 ? mask[1] : (j >> 5) == 2 ? mask[2] : mask[3];
-            if (!(word & bit) && q-- == 0) { setbit128(mask, j, 1u); break; }
+        int32_t j = q;                                    // first choice: the q-th cell is simply cell q
+        if (i > 0) {                                      // later choices skip the cells already taken
+            j = 0;
+            WAB_ROLLED
+            for (; j < n; ++j) {
+                const uint32_t word = (j >> 5) == 0 ? mask[0] : (j >> 5) == 1 ? mask[1] : (j >> 5) == 2 ? mask[2] : mask[3];
+                if (!((word >> (j & 31)) & 1u) && q-- == 0) break;
+            }
         }
+        setbit128(mask, j, 1u);
     }
 }
 
@@ -455,10 +464,18 @@ WAB_HD void env_step(const Params& P, Env& E, const Slots& S, uint32_t action, S
         const uint64_t v = binomial_draw(P, E.env_id, E.episode, SITE_SPAWN, E.turn);
         if (v >= P.spawn_cdf[0]) {                 // rare (2.4 % of steps): at least one wolf appears
             uint32_t chosen[4];
-            binomial_choose(P, E.env_id, E.episode, SITE_SPAWN, E.turn, RING, P.spawn_cdf, v, chosen);
+            binomial_choose(P, E.env_id, E.episode, SITE_SPAWN, E.turn, RING, v, chosen);
             WAB_ROLLED
-            for (int j = 0; j < RING; ++j)                                        // :571-574, ring order
-                if ((j < 32 ? chosen[0] >> j : chosen[1] >> (j - 32)) & 1u) {
+            for (int w = 0; w < 2; ++w) {                                         // :571-574, ring order
+                uint32_t bits = w ? chosen[1] : chosen[0];
+                WAB_ROLLED
+                while (bits) {
+#if defined(__CUDA_ARCH__)
+                    const int j = 32 * w + __ffs((int)bits) - 1;
+#else
+                    const int j = 32 * w + __builtin_ctz(bits);
+#endif
+                    bits &= bits - 1u;
                     int32_t ox, oy;
                     ring_offset(j, ox, oy);
                     if (E.nw < (uint32_t)P.wolf_cap) {
@@ -468,6 +485,7 @@ WAB_HD void env_step(const Params& P, Env& E, const Slots& S, uint32_t action, S
                         O.overflow = 1u;
                     }
                 }
+            }
         }
     }
 #endif
@@ -520,11 +538,18 @@ WAB_HD void reset_init_wolves(const Params& P, Env& E, const Slots& S, uint32_t&
     const uint64_t v = binomial_draw(P, E.env_id, E.episode, SITE_INIT, 0u);
     if (v < P.init_cdf[0]) return;                     // 94 % of resets start without a wolf in view
     uint32_t chosen[4];
-    binomial_choose(P, E.env_id, E.episode, SITE_INIT, 0u, CELLS, P.init_cdf, v, chosen);
+    binomial_choose(P, E.env_id, E.episode, SITE_INIT, 0u, CELLS, v, chosen);
     WAB_ROLLED
-    for (int c = 0; c < CELLS; ++c) {
-        const uint32_t word = (c >> 5) == 0 ? chosen[0] : (c >> 5) == 1 ? chosen[1] : (c >> 5) == 2 ? chosen[2] : chosen[3];
-        if ((word >> (c & 31)) & 1u) {
+    for (int w = 0; w < 4; ++w) {
+        uint32_t bits = w == 0 ? chosen[0] : w == 1 ? chosen[1] : w == 2 ? chosen[2] : chosen[3];
+        WAB_ROLLED
+        while (bits) {
+#if defined(__CUDA_ARCH__)
+            const int c = 32 * w + __ffs((int)bits) - 1;
+#else
+            const int c = 32 * w + __builtin_ctz(bits);
+#endif
+            bits &= bits - 1u;
             if (E.nw < (uint32_t)P.wolf_cap) {
                 S.wolves[(int32_t)E.nw * S.wstride] = pack_xy(c / 11 - HALF, c % 11 - HALF);
                 E.nw += 1;
