@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--num-envs", type=int, default=4096, help="environments per GPU")
     ap.add_argument("--fuse", type=int, default=256, help="steps per launch of the multi-step kernel")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--skip-e2e", action="store_true", help="sweeps only: skip the host-buffer leg")
     ap.add_argument("--skip-cpu", action="store_true", help="sweeps only: skip the cpu_baseline leg")
@@ -156,7 +156,7 @@ def run_reference(args):
         "cpu_baseline": {"value": res["value"], "unit": "env-steps/s", "cores": res["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": res["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "oracle C port of wab_env.py step+obs with OpenMP over envs; the pandas reference itself measured 13.7-18 steps/s/core in the build container",
+        "note": "oracle C port of wab_env.py step+obs with OpenMP over envs; the pandas reference itself: 16.6 steps/s single process, 125 steps/s over 8 cores in the build container (profiles/r1_reference_cpu_timing.json)",
     }
     print(json.dumps(line), flush=True)
 
@@ -302,7 +302,7 @@ def finish(args, env, world, rank, n, K, W, T, fused_ms, kernel_ms, launches, cl
             "per_call": percall,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (336.8e6 if (n == 4096 and T == 256) else None),   # ncu dram read+write per launch, profiles/r1c_ncu_4096_summary.txt
+                         "traffic": (337.2e6 if (n == 4096 and T == 256) else None),   # ncu dram read+write per launch, profiles/r1e_ncu_4096_summary.txt
                          "kernel": "wab_step_kernel<false, LPE=%d>" % env_lpe, "peak_source": peak_src,
                          "bytes_per_env_step": B_ALG, "env_steps_per_launch": n * steps_per_launch,
                          "avg_launch_ms": per_launch_s * 1e3},
