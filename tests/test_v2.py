@@ -176,3 +176,25 @@ def test_vecworld2_matches_oracle(world):
             for e, o in enumerate(oracles):
                 assert np.array_equal(st[e].astype(np.float64), o.state()) and tn[e] == o.turn, (ep, turn, e)
     env.close()
+
+
+@pytest.mark.gpu
+def test_vecworld2_outputs_never_touch_guard_bytes():
+    import torch
+    from wab_gym_b200 import _lib
+    from wab_gym_b200.world2 import VecWorld2
+    import ctypes
+    n, G = 45, 256
+    env = VecWorld2(n, 7, 9, 6, 4, 5, seed=2)
+    env.reset_environment()
+    raw = torch.full((env.planes.numel() + 2 * G,), 0xAB, dtype=torch.uint8, device="cuda")
+    # 16-byte aligned interior: G is a multiple of 16
+    inner = raw[G:G + env.planes.numel()].view(env.planes.shape)
+    env.planes = inner
+    acts = torch.randint(0, 5, (env.n_acting, n), dtype=torch.uint8, device="cuda")
+    for _ in range(4):
+        env.turn(acts)
+    torch.cuda.synchronize()
+    assert int((raw[:G] != 0xAB).sum()) == 0 and int((raw[-G:] != 0xAB).sum()) == 0
+    assert int(inner.max()) <= 1
+    env.close()

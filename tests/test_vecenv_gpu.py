@@ -358,3 +358,33 @@ def test_batched_a2c_update_trains_on_device():
     assert any(not torch.equal(a, b.detach()) for a, b in zip(before, tr.policy.parameters()))
     assert env.stats()["steps"] == 1024 * 40 * 3 and env.stats()["bad_actions"] == 0
     env.close()
+
+
+@pytest.mark.parametrize("lpe", [1, 16])
+@pytest.mark.parametrize("n", [33, 4096])
+def test_outputs_never_touch_guard_bytes(lpe, n, monkeypatch):
+    """compute-sanitizer is closed on this pool, so bounds are checked with canaries: every output lives inside a
+    larger buffer whose 256 guard bytes on either side must survive reset / step / step_many untouched."""
+    monkeypatch.setenv("WAB_LPE", str(lpe))
+    steps, G = 9, 256
+    env = _vec(n, seed=5, features=True, game_options={"chance_wolf_on_square": 0.01})
+
+    def guarded(shape, dtype):
+        numel = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        raw = torch.full((numel + 2 * G,), 0xAB, dtype=torch.uint8, device="cuda")
+        return raw, raw[G:G + numel].view(dtype).view(shape)
+
+    shapes = {"grids": ((steps, n, 3, 11, 11), torch.uint8), "food": ((steps, n), torch.uint8), "role": ((steps, n), torch.uint8),
+              "status": ((steps, n), torch.uint8), "reward": ((steps, n), torch.float32), "done": ((steps, n), torch.uint8),
+              "info": ((steps, n), torch.uint8), "features": ((steps, n, 28), torch.uint8)}
+    raws, out = {}, {}
+    for k, (shape, dt) in shapes.items():
+        raws[k], out[k] = guarded(shape, dt)
+    env.reset()
+    acts = torch.randint(0, 5, (steps, n), dtype=torch.uint8, device="cuda", generator=torch.Generator("cuda").manual_seed(2))
+    env.step_many(acts, out=out)
+    torch.cuda.synchronize()
+    for k, raw in raws.items():
+        assert int((raw[:G] != 0xAB).sum()) == 0 and int((raw[-G:] != 0xAB).sum()) == 0, (k, lpe, n)
+    assert int(out["grids"].max()) <= 1 and int(out["features"].max()) <= 40 and int(out["status"].max()) == 0
+    env.close()
