@@ -141,13 +141,25 @@ def test_kernel_logic_matches_oracle_long(world):
     assert kills > 0 or W * H > 200
 
 
+GPU_WORLDS = WORLDS + [
+    (19, 21, 6, 6, 10, 4, 11),       # smallest world the occupancy-plane kernel accepts: every edge case of the wrap rule
+    (64, 64, 8, 64, 256, 6, 0),      # BASELINE config 4 population
+    (33, 64, 12, 40, 30, 8, 5),
+]
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("world", WORLDS)
-def test_vecworld2_matches_oracle(world):
+@pytest.mark.parametrize("force_thread_kernel", [False, True])
+@pytest.mark.parametrize("world", GPU_WORLDS)
+def test_vecworld2_matches_oracle(world, force_thread_kernel, monkeypatch):
     import torch
     from wab_gym_b200.world2 import VecWorld2
     W, H, no, nw, nb, seed, base = world
-    n_envs, n = 70, no + nw + nb
+    if force_thread_kernel:
+        if no + nw + nb > 200:
+            pytest.skip("thread-per-world kernel is too slow to be interesting here")
+        monkeypatch.setenv("WAB2_NO_GRID", "1")
+    n_envs, n = (70 if no + nw + nb < 200 else 9), no + nw + nb
     env = VecWorld2(n_envs, W, H, no, nw, nb, seed=seed, env_id_base=base)
     oracles = [OracleWorld2(W, H, no, nw, nb, seed=seed, env_id=base + e) for e in range(n_envs)]
     rng = random.Random(3)

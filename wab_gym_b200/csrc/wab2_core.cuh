@@ -19,6 +19,7 @@ struct Params2 {
     int32_t width, height, n_ostriches, n_wolves, n_bushes, n_entities, n_acting;
     int32_t lookout_r, gatherer_r, wolf_r, window_r;       // WAB_Environment2.py:35-36, :49; obs window radius
     int32_t starting_role, ostrich_food, wolf_food, wolf_eat_gain, bush_food, bush_given;
+    uint8_t halfwidth[3][16];      // [lookout | gatherer | wolf][|dx|] = floor(sqrt(r^2 - dx^2)): the circle of World.py:295-297
     uint64_t env_id_base;
 };
 

@@ -10,10 +10,11 @@
 namespace {
 
 struct State2Ptrs {
-    uint32_t* ent;      // [3 * E][N] entity words (wab2_core.cuh)
+    uint32_t* ent;      // entity words (wab2_core.cuh): word k of world i at ent[k * stride_word + i * stride_world]
     uint32_t* episode;  // [N]
     uint32_t* turn;     // [N]
     int64_t n;
+    int64_t stride_word, stride_world;   // [3E][N] (thread per world: n, 1) or [N][3E] (warp per world: 1, 3E)
 };
 struct Out2Ptrs {
     uint8_t* planes;    // [A][N][3][S][S] u8 or null (entity-major: the 32 worlds of a warp are contiguous)
@@ -23,12 +24,12 @@ struct Out2Ptrs {
 };
 
 __device__ __forceinline__ void load_world(const Params2& P, const State2Ptrs& st, int64_t idx, World2& W) {
-    for (int k = 0; k < 3 * P.n_entities; ++k) W.base[k * W.stride] = st.ent[(int64_t)k * st.n + idx];
+    for (int k = 0; k < 3 * P.n_entities; ++k) W.base[k * W.stride] = st.ent[k * st.stride_word + idx * st.stride_world];
     W.episode = st.episode[idx]; W.turn = st.turn[idx];
     W.env_id = (uint32_t)(P.env_id_base + (uint64_t)idx);
 }
 __device__ __forceinline__ void store_world(const Params2& P, const State2Ptrs& st, int64_t idx, const World2& W) {
-    for (int k = 0; k < 3 * P.n_entities; ++k) st.ent[(int64_t)k * st.n + idx] = W.base[k * W.stride];
+    for (int k = 0; k < 3 * P.n_entities; ++k) st.ent[k * st.stride_word + idx * st.stride_world] = W.base[k * W.stride];
     st.episode[idx] = W.episode; st.turn[idx] = W.turn;
 }
 
@@ -114,6 +115,8 @@ __global__ void wab2_turn_kernel(const __grid_constant__ Params2 P, const State2
 
 }  // namespace
 
+#include "wab2_grid.cuh"
+
 struct Wab2World {
     Wab2Config cfg;
     Params2 P;
@@ -123,6 +126,7 @@ struct Wab2World {
     void* slab;
     int bs, stream_words;
     size_t smem_turn, smem_init;
+    bool grid;            // warp-per-world kernel with occupancy planes (wab2_grid.cuh)
 };
 
 extern "C" {
@@ -156,7 +160,18 @@ int wab2_create(const Wab2Config* cfg, int64_t n_envs, uint64_t seed, uint64_t e
     P.wolf_food = cfg->wolf_starting_food; P.wolf_eat_gain = cfg->wolf_food_for_eating_ostrich;
     P.bush_food = cfg->food_per_bush; P.bush_given = cfg->food_given_per_turn; P.env_id_base = env_id_base;
     const int S = 2 * cfg->window_radius + 1;
-    h->stream_words = (32 * 3 * S * S + 15 + 31) / 32 + 1;            // one bit stream per warp: 32 windows
+    const int rads[3] = {cfg->lookout_view_radius, cfg->gatherer_view_radius, cfg->wolf_view_radius};
+    for (int s3 = 0; s3 < 3; ++s3)
+        for (int d = 0; d < 16; ++d) {
+            int m = 0;
+            while (d <= rads[s3] && (m + 1) * (m + 1) + d * d <= rads[s3] * rads[s3]) ++m;
+            P.halfwidth[s3][d] = (uint8_t)m;
+        }
+    const int rmax = rads[0] > rads[1] ? (rads[0] > rads[2] ? rads[0] : rads[2]) : (rads[1] > rads[2] ? rads[1] : rads[2]);
+    // every window fits the world once -> occupancy-plane kernel, one warp per world
+    h->grid = cfg->window_radius >= rmax && cfg->width >= S && cfg->height >= S && cfg->width <= 64 && cfg->height <= 64 &&
+              getenv("WAB2_NO_GRID") == nullptr;
+    h->stream_words = h->grid ? (3 * S * S + 15 + 31) / 32 + 1 : (32 * 3 * S * S + 15 + 31) / 32 + 1;
     // threads per block: as many as shared memory allows (3E state words + one bit stream per thread)
     int max_smem = 48 * 1024;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
@@ -165,7 +180,12 @@ int wab2_create(const Wab2Config* cfg, int64_t n_envs, uint64_t seed, uint64_t e
     while (bs > 32 && need(bs) > (size_t)max_smem / 2) bs >>= 1;
     if (need(bs) > (size_t)max_smem) { delete h; return fail(WAB_E_UNSUPPORTED, "too many entities for the shared-memory staging"); }
     h->bs = bs; h->smem_turn = need(bs); h->smem_init = sizeof(uint32_t) * (size_t)3 * E * bs;
-    cudaError_t e = cudaFuncSetAttribute(wab2_turn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_turn);
+    cudaError_t e = cudaSuccess;
+    if (h->grid) {
+        h->smem_turn = sizeof(uint32_t) * ((size_t)4 * grid_geom(E, cfg->width, h->stream_words).total + 512);
+        e = cudaFuncSetAttribute(wab2_grid_turn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_turn);
+    } else
+        e = cudaFuncSetAttribute(wab2_turn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_turn);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(wab2_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_init);
     const size_t n = (size_t)n_envs;
     size_t o = 0;
@@ -178,6 +198,8 @@ int wab2_create(const Wab2Config* cfg, int64_t n_envs, uint64_t seed, uint64_t e
     uint8_t* base = (uint8_t*)h->slab;
     h->st.ent = (uint32_t*)(base + o_ent); h->st.episode = (uint32_t*)(base + o_ep); h->st.turn = (uint32_t*)(base + o_turn);
     h->st.n = n_envs;
+    h->st.stride_word = h->grid ? 1 : n_envs;
+    h->st.stride_world = h->grid ? 3 * E : 1;
     wab2_init_kernel<<<(unsigned)((n_envs + bs - 1) / bs), bs, h->smem_init, 0>>>(h->P, h->st, 0);
     e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -207,8 +229,12 @@ int wab2_turn(Wab2World* h, const uint8_t* d_actions, uint8_t* d_planes, int32_t
     if (d_planes) if (int rc = check_ptr_align(d_planes, "d_planes")) return rc;
     DeviceGuard guard(h->device);
     Out2Ptrs out{d_planes, d_internal, d_reward, d_done};
-    wab2_turn_kernel<<<(unsigned)((h->n + h->bs - 1) / h->bs), h->bs, h->smem_turn, (cudaStream_t)stream>>>(
-        h->P, h->st, d_actions, out, h->stream_words);
+    if (h->grid)
+        wab2_grid_turn_kernel<<<(unsigned)((h->n + 3) / 4), 128, h->smem_turn, (cudaStream_t)stream>>>(
+            h->P, h->st, d_actions, out, h->stream_words);
+    else
+        wab2_turn_kernel<<<(unsigned)((h->n + h->bs - 1) / h->bs), h->bs, h->smem_turn, (cudaStream_t)stream>>>(
+            h->P, h->st, d_actions, out, h->stream_words);
     WAB_CUDA(cudaGetLastError());
     return WAB_OK;
 }
@@ -227,7 +253,9 @@ int wab2_export_state(Wab2World* h, int32_t* out9, int32_t* turn, void* stream) 
         for (size_t i = 0; i < n; ++i) {
             if (turn) turn[i] = (int32_t)tr[i];
             for (int k = 0; k < E; ++k) {
-                const uint32_t obj = ent[(size_t)(3 * k) * n + i], tab = ent[(size_t)(3 * k + 1) * n + i], food = ent[(size_t)(3 * k + 2) * n + i];
+                const size_t sw = (size_t)h->st.stride_word, si = (size_t)h->st.stride_world;
+                const uint32_t obj = ent[(size_t)(3 * k) * sw + i * si], tab = ent[(size_t)(3 * k + 1) * sw + i * si],
+                               food = ent[(size_t)(3 * k + 2) * sw + i * si];
                 int32_t* o = out9 + (i * E + k) * 9;
                 o[0] = (int32_t)entity_type(h->P, k); o[1] = unpack_x(obj); o[2] = unpack_y(obj);
                 o[3] = (int32_t)(tab & 0xFFu); o[4] = (int32_t)((tab >> 8) & 0xFFu); o[5] = (int32_t)((tab >> 16) & 1u);
