@@ -159,6 +159,8 @@ def test_vecworld2_matches_oracle(world, force_thread_kernel, monkeypatch):
         if no + nw + nb > 200:
             pytest.skip("thread-per-world kernel is too slow to be interesting here")
         monkeypatch.setenv("WAB2_NO_GRID", "1")
+    else:
+        monkeypatch.setenv("WAB2_GRID", "1")       # occupancy-plane kernel wherever the world allows it
     n_envs, n = (70 if no + nw + nb < 200 else 9), no + nw + nb
     env = VecWorld2(n_envs, W, H, no, nw, nb, seed=seed, env_id_base=base)
     oracles = [OracleWorld2(W, H, no, nw, nb, seed=seed, env_id=base + e) for e in range(n_envs)]

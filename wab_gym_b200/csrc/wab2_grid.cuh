@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(128) wab2_grid_turn_kernel(const __grid_consta
     uint32_t* cols = smem2 + warp * g.total + g.cols;
     uint32_t* stream = smem2 + warp * g.total + g.stream;
     const uint32_t* src = st.ent + idx * st.stride_world;
-    for (int k = lane; k < 3 * E; k += 32) obj[k] = src[k];          // world-major state: one coalesced read
+    for (int k = lane; k < 3 * E; k += 32) obj[(k % 3) * E + k / 3] = src[k];   // world-major [entity][obj, tab, food]: coalesced read, planar in smem
     for (int k = lane; k < 3 * W * 2; k += 32) cols[k] = 0u;
     const uint32_t env_id = (uint32_t)(P.env_id_base + (uint64_t)idx), episode = st.episode[idx];
     uint32_t turn = st.turn[idx];
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(128) wab2_grid_turn_kernel(const __grid_consta
     }
     turn += 1;
     uint32_t* dst = st.ent + idx * st.stride_world;
-    for (int k = lane; k < 3 * E; k += 32) dst[k] = obj[k];
+    for (int k = lane; k < 3 * E; k += 32) dst[k] = obj[(k % 3) * E + k / 3];
     if (lane == 0) st.turn[idx] = turn;
 }
 

@@ -170,7 +170,7 @@ int wab2_create(const Wab2Config* cfg, int64_t n_envs, uint64_t seed, uint64_t e
     const int rmax = rads[0] > rads[1] ? (rads[0] > rads[2] ? rads[0] : rads[2]) : (rads[1] > rads[2] ? rads[1] : rads[2]);
     // every window fits the world once -> occupancy-plane kernel, one warp per world
     h->grid = cfg->window_radius >= rmax && cfg->width >= S && cfg->height >= S && cfg->width <= 64 && cfg->height <= 64 &&
-              getenv("WAB2_NO_GRID") == nullptr;
+              (E > 96 || getenv("WAB2_GRID") != nullptr) && getenv("WAB2_NO_GRID") == nullptr;   // small worlds: thread per world is faster
     h->stream_words = h->grid ? (3 * S * S + 15 + 31) / 32 + 1 : (32 * 3 * S * S + 15 + 31) / 32 + 1;
     // threads per block: as many as shared memory allows (3E state words + one bit stream per thread)
     int max_smem = 48 * 1024;
