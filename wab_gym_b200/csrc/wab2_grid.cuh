@@ -93,7 +93,10 @@ __global__ void __launch_bounds__(128) wab2_grid_turn_kernel(const __grid_consta
     }
     __syncwarp();
     const int R = P.window_r, S = 2 * R + 1, obs_bytes = 3 * S * S;
-    for (int a = 0; a < E; ++a) {
+    // bushes never move: their "action" only refreshes a table position left stale by reset_world (World.py:353-356),
+    // i.e. it is a no-op except in the first turn of an episode
+    const int last = turn == 0u ? E : A;
+    for (int a = 0; a < last; ++a) {
         const bool acting = a < A;
         const uint32_t at = entity_type(P, a);
         const int64_t o = (int64_t)a * n + idx;
