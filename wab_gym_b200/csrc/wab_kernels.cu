@@ -545,10 +545,13 @@ int pick_lpe(const WabVec* h) {
     }
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device);
-    if (fits_one_wave<32>(h, n_sm)) return 32;
-    if (fits_one_wave<16>(h, n_sm)) return 16;
-    if (fits_one_wave<8>(h, n_sm)) return 8;
-    if (fits_one_wave<4>(h, n_sm)) return 4;
+    // measured on B200 (profiles/r1_tune_lpe.jsonl): the best variant keeps 32k-64k threads in flight, and more than
+    // 8 lanes per env only pays for very small batches (a step has 6 independent Philox calls to share out)
+    const int64_t n = h->n;
+    if (n * 32 <= 32768 && fits_one_wave<32>(h, n_sm)) return 32;
+    if (n * 16 <= 32768 && fits_one_wave<16>(h, n_sm)) return 16;
+    if (n * 8 <= 65536 && fits_one_wave<8>(h, n_sm)) return 8;
+    if (n * 4 <= 65536 && fits_one_wave<4>(h, n_sm)) return 4;
     return 1;
 }
 
