@@ -388,3 +388,42 @@ def test_outputs_never_touch_guard_bytes(lpe, n, monkeypatch):
         assert int((raw[:G] != 0xAB).sum()) == 0 and int((raw[-G:] != 0xAB).sum()) == 0, (k, lpe, n)
     assert int(out["grids"].max()) <= 1 and int(out["features"].max()) <= 40 and int(out["status"].max()) == 0
     env.close()
+
+
+@pytest.mark.parametrize("name", ["defaults", "six_actions_random_start", "dense"])
+def test_batch_without_auto_reset_keeps_reporting_done(name):
+    """VecEnv(auto_reset=False): the reference's behaviour after an episode ends (wab_env.py:328-340 — done is
+    returned again, the dead ostrich still moves, reveals bushes and can starve after being killed), for a batch;
+    fp64 food, masked reset of the finished envs every few steps."""
+    overrides, greedy = OPTION_SETS[name]
+    n, steps, seed = 48, 220, 13
+    env = _vec(n, overrides, seed=seed, auto_reset=False, wolf_cap=15)
+    assert env.game.food_mode == 0
+    oracles = [OracleEnv(overrides, seed=seed, env_id=i) for i in range(n)]
+    rng = np.random.default_rng(3)
+    obs = env.reset()
+    cur = [o.reset() for o in oracles]
+    done_now = np.zeros(n, bool)
+    for t in range(steps):
+        g, f, r, s = (x.cpu().numpy() for x in obs)
+        for i in range(n):
+            assert np.array_equal(g[i], cur[i][0]) and (int(f[i]), int(r[i]), int(s[i])) == cur[i][1:], (t, i)
+        if t % 7 == 6 and done_now.any():                       # reset only the envs that are done
+            mask = torch.from_numpy(done_now.astype(np.uint8)).cuda()
+            obs = env.reset(mask)
+            for i in np.nonzero(done_now)[0]:
+                cur[i] = oracles[i].reset()
+            done_now[:] = False
+            continue
+        acts = np.array([pick_action(rng, cur[i][0], env.n_actions, greedy) for i in range(n)], dtype=np.uint8)
+        obs, reward, done, _ = env.step(torch.from_numpy(acts).cuda())
+        reward, done = reward.cpu().numpy(), done.cpu().numpy()
+        for i, o in enumerate(oracles):
+            cur[i], rr, d = o.step(int(acts[i]))
+            assert np.float32(rr) == reward[i] and d == bool(done[i]), (t, i)
+            done_now[i] = d
+    st = env.export_state()
+    for i, o in enumerate(oracles):
+        hs = o.hidden_state()
+        assert st["food"][i] == hs["food"] and (st["x"][i], st["y"][i], st["status"][i]) == (hs["x"], hs["y"], hs["status"])
+    env.close()

@@ -171,20 +171,6 @@ WAB_HD uint32_t pick4(const uint32_t w[4], uint32_t lane) {
     return (lane & 2u) ? b : a;
 }
 
-// number of thresholds <= word  ==  round(U**power * max_berries)   (wab_env.py:631-635)
-WAB_HD int32_t bush_value(const Params& P, uint32_t word) {
-    int32_t lo = 0, hi = (int32_t)P.n_bush_thr;
-    while (lo < hi) {
-        int32_t mid = (lo + hi) >> 1;
-#if defined(__CUDA_ARCH__)
-        uint32_t t = __ldg(P.bush_thr + mid);
-#else
-        uint32_t t = P.bush_thr[mid];
-#endif
-        if (t <= word) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
 WAB_HD uint32_t bush_word(const Params& P, const Env& E, int32_t x, int32_t y) {
     uint32_t w[4];
     philox(P, E.env_id, E.episode, ctr2(SITE_BUSH, 0, 0), pack_xy(x >> 1, y >> 1), w);

@@ -498,6 +498,11 @@ struct WabVec {
     size_t stage_bytes;
     int lpe;          // lanes per env chosen at create (see pick_lpe)
     uint8_t* d_features;   // bound feature output, or null
+    // host-buffer step as one CUDA graph (H2D actions -> step kernel -> D2H block), rebuilt when the pointers change
+    cudaStream_t host_stream;
+    cudaGraphExec_t host_graph;
+    const void* g_actions; void* g_block; const void* g_features;
+    bool graph_unsupported;
 };
 
 namespace {
@@ -578,6 +583,7 @@ int launch_step(WabVec* h, int n_steps, const uint8_t* d_actions, const WabObs& 
 int ensure_stage(WabVec* h, size_t bytes) {
     if (h->stage_bytes >= bytes) return WAB_OK;
     if (h->stage) cudaFree(h->stage);
+    if (h->host_graph) { cudaGraphExecDestroy(h->host_graph); h->host_graph = nullptr; }
     h->stage = nullptr; h->stage_bytes = 0;
     WAB_CUDA(cudaMalloc(&h->stage, bytes));
     h->stage_bytes = bytes;
@@ -668,6 +674,8 @@ void wab_vec_destroy(WabVec* h) {
     if (h->slab) cudaFree(h->slab);
     if (h->d_thr) cudaFree(h->d_thr);
     if (h->stage) cudaFree(h->stage);
+    if (h->host_graph) cudaGraphExecDestroy(h->host_graph);
+    if (h->host_stream) cudaStreamDestroy(h->host_stream);
     delete h;
 }
 
@@ -744,8 +752,37 @@ int wab_vec_step_host_packed(WabVec* h, const uint8_t* h_actions, uint8_t* h_blo
     const StageLayout L = stage_layout(h->n);
     if (int rc = ensure_stage(h, L.total)) return rc;
     uint8_t* b = h->stage;
-    WAB_CUDA(cudaMemcpyAsync(b + L.actions, h_actions, (size_t)h->n, cudaMemcpyHostToDevice, s));
     WabObs obs{b + L.grids, b + L.food, b + L.role, b + L.status};
+    // Fast path: the three operations replayed as one graph launch on a private stream (saves two API round trips
+    // per step; needs pinned host buffers — anything else falls back to the plain sequence below).
+    if (!h->graph_unsupported) {
+        if (!h->host_stream && cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking) != cudaSuccess) {
+            cudaGetLastError(); h->graph_unsupported = true;
+        }
+        if (!h->graph_unsupported && (!h->host_graph || h->g_actions != h_actions || h->g_block != h_block ||
+                                      h->g_features != h->d_features)) {
+            if (h->host_graph) { cudaGraphExecDestroy(h->host_graph); h->host_graph = nullptr; }
+            cudaGraph_t graph = nullptr;
+            bool ok = cudaStreamBeginCapture(h->host_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) {
+                ok = cudaMemcpyAsync(b + L.actions, h_actions, (size_t)h->n, cudaMemcpyHostToDevice, h->host_stream) == cudaSuccess;
+                ok = ok && launch_step(h, 1, b + L.actions, obs, (float*)(b + L.reward), b + L.done, b + L.info, h->host_stream) == WAB_OK;
+                ok = ok && cudaMemcpyAsync(h_block, b + L.grids, L.total - L.grids, cudaMemcpyDeviceToHost, h->host_stream) == cudaSuccess;
+                ok = (cudaStreamEndCapture(h->host_stream, &graph) == cudaSuccess) && ok && graph;
+            }
+            if (ok) ok = cudaGraphInstantiate(&h->host_graph, graph, 0) == cudaSuccess;
+            if (graph) cudaGraphDestroy(graph);
+            if (!ok) { cudaGetLastError(); h->host_graph = nullptr; h->graph_unsupported = true; }
+            h->g_actions = h_actions; h->g_block = h_block; h->g_features = h->d_features;
+        }
+        if (h->host_graph) {
+            WAB_CUDA(cudaStreamSynchronize(s));                 // order after the caller's earlier work
+            WAB_CUDA(cudaGraphLaunch(h->host_graph, h->host_stream));
+            WAB_CUDA(cudaStreamSynchronize(h->host_stream));
+            return WAB_OK;
+        }
+    }
+    WAB_CUDA(cudaMemcpyAsync(b + L.actions, h_actions, (size_t)h->n, cudaMemcpyHostToDevice, s));
     if (int rc = launch_step(h, 1, b + L.actions, obs, (float*)(b + L.reward), b + L.done, b + L.info, s)) return rc;
     WAB_CUDA(cudaMemcpyAsync(h_block, b + L.grids, L.total - L.grids, cudaMemcpyDeviceToHost, s));   // one transfer
     WAB_CUDA(cudaStreamSynchronize(s));
