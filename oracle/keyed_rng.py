@@ -22,9 +22,21 @@ returns four 32-bit words. A *word draw* is ONE word ``w`` ("lane") and the unif
 reference is the exact double ``U = w * 2**-32``:
 
     site   turn  sub      payload                              lane          cite
-    BUSH   0     0        (x>>1 & 0xffff) | (y>>1 & 0xffff)<<16  (x&1)|(y&1)<<1  wab_env.py:627,631-635
     DESP   t     rank>>2  (wx & 0xffff) | (wy & 0xffff)<<16      rank & 3      wab_env.py:262-264
     START  0     0        0                                      0 food, 1 role  wab_env.py:596-599
+                                                                 2, 3 = the episode's bush key (ka, kb), below
+
+Bush values (wab_env.py:627, 631-635) are the highest-volume draws: 11 newly revealed cells on almost every step
+and a cell must get the same value whenever it is revealed. They come from ``philox2x32-10`` (same paper; half the
+multiplies of the 4x32 variant) keyed per episode: with B = (x>>1 & 0xffff) | (y>>1 & 0xffff)<<16 the 2x2 block of a
+cell and k2 = (seed ^ seed >> 32) & 0xffffffff,
+
+    (p0, p1) = philox2x32_10(counter = (B ^ ka,  kb), key = k2)     high half-words of the block's 4 cells
+    (q0, q1) = philox2x32_10(counter = (B ^ ka, ~kb), key = k2)     low half-words
+    word(x, y) = h << 16 | l,  half-word index (x&1) | (y&1)<<1 of (p0, p1) resp. (q0, q1)
+
+and U = word * 2**-32 as for every word draw. Whether a cell has a bush is decided by ``h`` alone unless it equals
+the top half of the first bush threshold (probability 2**-16), so the low half is evaluated lazily.
 
 The two sites that draw for MANY cells at once with a tiny success probability (48 ring cells per step,
 W*H cells per reset, p = chance/2 = 0.0005) are *binomial-first*: instead of n independent word draws,
@@ -82,6 +94,22 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
     return tuple(v.astype(np.uint32) for v in (c0, c1, c2, c3))
 
 
+_M2 = np.uint64(0xD256D193)
+
+
+def philox2x32_10(c0, c1, key):
+    """Vectorised Philox2x32-10 (Random123). Returns 2 uint32 arrays."""
+    c0 = np.asarray(c0, dtype=np.uint64) & _MASK
+    c1 = np.asarray(c1, dtype=np.uint64) & _MASK
+    c0, c1 = np.broadcast_arrays(c0, c1)
+    k = int(key) & 0xFFFFFFFF
+    for _ in range(10):
+        p = _M2 * c0
+        c0, c1 = (p >> _S32) ^ np.uint64(k) ^ c1, p & _MASK
+        k = (k + _W0) & 0xFFFFFFFF
+    return c0.astype(np.uint32), c1.astype(np.uint32)
+
+
 def _draw(seed, env_id, episode, site, turn, sub, payload, lane):
     """One 32-bit word per element of the broadcast (payload, lane, sub, turn) arrays."""
     payload = np.asarray(payload, dtype=np.int64) & 0xFFFFFFFF
@@ -108,10 +136,27 @@ def _pack_xy(x, y):
     return (x & 0xFFFF) | ((y & 0xFFFF) << 16)
 
 
+def bush_key(seed, env_id, episode):
+    """(ka, kb): words 2 and 3 of the episode's START call."""
+    w = _draw(seed, env_id, episode, SITE_START, 0, 0, np.zeros(2, dtype=np.int64), np.array([2, 3]))
+    return int(w[0]), int(w[1])
+
+
 def bush_words(seed, env_id, episode, x, y):
     x = np.asarray(x, dtype=np.int64)
     y = np.asarray(y, dtype=np.int64)
-    return _draw(seed, env_id, episode, SITE_BUSH, 0, 0, _pack_xy(x >> 1, y >> 1), (x & 1) | ((y & 1) << 1))
+    ka, kb = bush_key(seed, env_id, episode)
+    k2 = (int(seed) ^ (int(seed) >> 32)) & 0xFFFFFFFF
+    block = (_pack_xy(x >> 1, y >> 1) ^ ka) & 0xFFFFFFFF
+    lane = (x & 1) | ((y & 1) << 1)
+
+    def half(words):
+        w = np.where(lane >= 2, words[1], words[0]).astype(np.uint64)
+        return (w >> (np.uint64(16) * (lane & 1).astype(np.uint64))) & np.uint64(0xFFFF)
+
+    hi = half(philox2x32_10(block, kb, k2))
+    lo = half(philox2x32_10(block, (~kb) & 0xFFFFFFFF, k2))
+    return ((hi << np.uint64(16)) | lo).astype(np.uint32)
 
 
 BINOMIAL_TABLE = 32   # thresholds kept; configurations whose tail beyond this is not negligible are rejected

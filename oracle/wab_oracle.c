@@ -36,6 +36,18 @@ void wab_oracle_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+/* Philox2x32-10 (Random123) */
+void wab_oracle_philox2(const uint32_t ctr[2], uint32_t key, uint32_t out[2]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1];
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p = (uint64_t)0xD256D193u * c0;
+        uint32_t n0 = (uint32_t)(p >> 32) ^ key ^ c1;
+        c1 = (uint32_t)p; c0 = n0;
+        key += PHILOX_W0;
+    }
+    out[0] = c0; out[1] = c1;
+}
+
 enum { SITE_BUSH = 1, SITE_INIT = 2, SITE_SPAWN = 3, SITE_DESP = 4, SITE_START = 5 };
 
 typedef struct { int32_t x, y, food; } BushRec;
@@ -50,6 +62,7 @@ struct WabOracleEnv {
     int32_t *wx, *wy; int32_t nw, capw;                     /* self.wolves          */
     BushRec *recs; int32_t nrec, caprec;                    /* self.bushes          */
     int32_t *hslot; int64_t *hgen; uint32_t hmask;          /* (x,y) -> record index */
+    uint32_t bush_ka, bush_kb;   /* the episode's bush key: words 2, 3 of the START call (oracle/keyed_rng.py) */
     int32_t *snap;     /* window bush food as of the last update_master_df_and_distances */
     int32_t snap_status;                                    /* ostrich status in that frame */
     int32_t nw_snap;                                        /* wolves present in that frame */
@@ -148,15 +161,25 @@ static int32_t bush_value(const WabOracleEnv *e, uint32_t w) {
     return lo;
 }
 
+/* 32-bit bush draw of a cell (oracle/keyed_rng.py): two Philox2x32 calls on the cell's 2x2 block */
+static uint32_t bush_word(const WabOracleEnv *e, int32_t x, int32_t y) {
+    uint32_t k2 = (uint32_t)(e->seed ^ (e->seed >> 32));
+    uint32_t lane = ((uint32_t)x & 1u) | (((uint32_t)y & 1u) << 1);
+    uint32_t ctr[2] = { pack_xy(x >> 1, y >> 1) ^ e->bush_ka, e->bush_kb }, p[2], q[2];
+    wab_oracle_philox2(ctr, k2, p);
+    ctr[1] = ~e->bush_kb;
+    wab_oracle_philox2(ctr, k2, q);
+    uint32_t h = (p[lane >> 1] >> (16u * (lane & 1u))) & 0xFFFFu, l = (q[lane >> 1] >> (16u * (lane & 1u))) & 0xFFFFu;
+    return (h << 16) | l;
+}
+
 /* generate_bushes, wab_env.py:613-629 (visible_coords :510-525) */
 static void generate_bushes(WabOracleEnv *e) {
     const int32_t hw = e->cfg.width / 2, hh = e->cfg.height / 2;
     for (int32_t x = e->ox - hw; x <= e->ox + hw; ++x)
         for (int32_t y = e->oy - hh; y <= e->oy + hh; ++y) {
             if (bush_find(e, x, y) >= 0) continue;                       /* :624 */
-            uint32_t lane = ((uint32_t)x & 1u) | (((uint32_t)y & 1u) << 1);
-            uint32_t w = keyed_word(e, SITE_BUSH, 0, 0, pack_xy(x >> 1, y >> 1), lane);
-            bush_add(e, x, y, bush_value(e, w));                         /* :627-629 */
+            bush_add(e, x, y, bush_value(e, bush_word(e, x, y)));        /* :627-629 */
         }
 }
 
@@ -267,6 +290,8 @@ void wab_oracle_reset(WabOracleEnv *e, WabOracleObs *obs) {
     e->nrec = 0; e->nw = 0;            /* :234-238 (hash entries expire with the episode stamp) */
     /* spawn_ostriches :595-611 */
     e->ox = 0; e->oy = 0; e->status = 0;
+    e->bush_ka = keyed_word(e, SITE_START, 0, 0, 0, 2);
+    e->bush_kb = keyed_word(e, SITE_START, 0, 0, 0, 3);
     e->food = (e->cfg.starting_food < 0) ? unit(keyed_word(e, SITE_START, 0, 0, 0, 0)) : e->cfg.starting_food;
     e->role = (e->cfg.starting_role < 0) ? (int32_t)(keyed_word(e, SITE_START, 0, 0, 0, 1) >> 31)
                                          : e->cfg.starting_role;

@@ -72,6 +72,7 @@ def lib():
         L.wab_oracle_num_bushes.argtypes = [ctypes.c_void_p]
         L.wab_oracle_get_bushes.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.wab_oracle_philox.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.wab_oracle_philox2.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]
         L.wab_oracle_run.restype = ctypes.c_int64
         L.wab_oracle_run.argtypes = [ctypes.POINTER(OracleConfig), ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64,
                                      ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_uint64)]
@@ -180,6 +181,13 @@ def philox(ctr, key):
     k = np.ascontiguousarray(key, dtype=np.uint32)
     out = np.zeros(4, dtype=np.uint32)
     lib().wab_oracle_philox(c.ctypes.data, k.ctypes.data, out.ctypes.data)
+    return out
+
+
+def philox2(ctr, key):
+    c = np.ascontiguousarray(ctr, dtype=np.uint32)
+    out = np.zeros(2, dtype=np.uint32)
+    lib().wab_oracle_philox2(c.ctypes.data, int(key) & 0xFFFFFFFF, out.ctypes.data)
     return out
 
 

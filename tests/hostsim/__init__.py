@@ -49,6 +49,7 @@ def lib():
         L.hostsim2_observe.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
         L.hostsim2_act.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
         L.hostsim2_state.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.hostsim_philox2.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]
         L.hostsim_philox.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p]
         _lib = L
     return _lib
@@ -95,6 +96,13 @@ class HostSimEnv:
         return {"x": int(scal[0]), "y": int(scal[1]), "food": food.value, "role": int(scal[3]), "status": int(scal[4]),
                 "turn": int(scal[5]), "episode": int(scal[6]), "wolves": sorted((int(a), int(b)) for a, b in wolves[:nw]),
                 "n_log": int(scal[8]), "bush_mask": mask}
+
+
+def philox2(ctr, key):
+    c = np.ascontiguousarray(ctr, dtype=np.uint32)
+    out = np.zeros(2, dtype=np.uint32)
+    lib().hostsim_philox2(c.ctypes.data, int(key) & 0xFFFFFFFF, out.ctypes.data)
+    return out
 
 
 def philox(ctr, key):

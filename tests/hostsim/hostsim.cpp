@@ -68,7 +68,7 @@ static uint32_t do_reset(HostSim* h, uint32_t wm[4], uint32_t bm[4]) {
     uint32_t overflow = 0;
     if (h->f64) reset_scalars<true>(h->P, h->E); else reset_scalars<false>(h->P, h->E);
     uint32_t m[4] = {0, 0, 0, 0};
-    for (int blk = 0; blk < 36; ++blk) reset_bush_block(h->P, h->E.env_id, h->E.episode, blk, m);
+    for (int blk = 0; blk < 36; ++blk) reset_bush_block(h->P, h->E.bk_a, h->E.bk_b, blk, m);
     for (int w = 0; w < 4; ++w) h->E.m[w] = m[w];
     if (h->P.wolves) reset_init_wolves(h->P, h->E, h->S, overflow);
     wolf_plane(h->E, h->S, wm);
@@ -127,6 +127,13 @@ void hostsim_features(const uint8_t* wolf_grid, const uint8_t* bush_grid, int32_
     uint32_t f[7];
     pragmatic_features(wm, bm, (uint32_t)food, (uint32_t)role, (uint32_t)status, f);
     memcpy(out28, f, 28);
+}
+
+void hostsim_philox2(const uint32_t* ctr, uint32_t key, uint32_t* out) {
+    Params P;
+    memset(&P, 0, sizeof(P));
+    for (int r = 0; r < 10; ++r) { P.rk2[r] = key; key += PHILOX_W0; }
+    philox2(P, ctr[0], ctr[1], out);
 }
 
 void hostsim_philox(const uint32_t* ctr, uint32_t k0, uint32_t k1, uint32_t* out) {

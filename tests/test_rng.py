@@ -21,6 +21,20 @@ def test_philox_kat_numpy_oracle_hostsim(ctr, key, want):
     assert tuple(int(v) for v in hostsim.philox(ctr, key)) == want
 
 
+KAT2 = [   # Random123 kat_vectors, philox2x32 10
+    ((0, 0), 0, (0xFF1DAE59, 0x6CD10DF2)),
+    ((0xFFFFFFFF, 0xFFFFFFFF), 0xFFFFFFFF, (0x2C3F628B, 0xAB4FD7AD)),
+    ((0x243F6A88, 0x85A308D3), 0x13198A2E, (0xDD7CE038, 0xF62A4C12)),
+]
+
+
+@pytest.mark.parametrize("ctr,key,want", KAT2)
+def test_philox2x32_kat_numpy_oracle_hostsim(ctr, key, want):
+    assert tuple(int(v) for v in kr.philox2x32_10(ctr[0], ctr[1], key)) == want
+    assert tuple(int(v) for v in wab_oracle.philox2(ctr, key)) == want
+    assert tuple(int(v) for v in hostsim.philox2(ctr, key)) == want
+
+
 def test_three_implementations_agree_on_random_counters():
     rng = np.random.default_rng(7)
     ctrs = rng.integers(0, 2 ** 32, (64, 4), dtype=np.uint64)

@@ -59,7 +59,8 @@ template <int J, int W> struct ColMask { static constexpr uint32_t v = colmask_w
 
 // Rule constants + RNG schedule, passed to kernels by value (constant bank).
 struct Params {
-    uint32_t rk0[10], rk1[10];     // Philox round keys (key is uniform: the seed)
+    uint32_t rk0[10], rk1[10];     // Philox4x32 round keys (key is uniform: the seed)
+    uint32_t rk2[10];              // Philox2x32 round keys of the bush draws (key (seed ^ seed >> 32), uniform)
     uint32_t thr_bush1;            // food0 > 0  <=>  word >= thr_bush1   (bush_thr[0])
     uint32_t thr_bush2;            // food0 > 1  <=>  word >= thr_bush2   (bush_thr[1]; only read when n_bush_thr > 1)
     uint64_t spawn_cdf[32], init_cdf[32];  // binomial-first tables: K = #{k : v >= cdf[k]} (oracle/keyed_rng.py)
@@ -83,6 +84,7 @@ struct Params {
 struct Env {
     int32_t x, y;
     uint32_t turn, role, status, nw, nlog, episode, env_id;
+    uint32_t bk_a, bk_b;  // the episode's bush key (words 2, 3 of the START call, oracle/keyed_rng.py)
     uint32_t logsig; // 32-bit Bloom signature of the cells in the depletion log (a clear bit proves absence)
     uint32_t dep;    // 1 once some logged cell has been eaten empty (re-entering cells must consult the log)
     uint32_t m[4];   // bush occupancy of the window (food > 0), current
@@ -171,10 +173,41 @@ WAB_HD uint32_t pick4(const uint32_t w[4], uint32_t lane) {
     return (lane & 2u) ? b : a;
 }
 
+// Philox2x32-10 (same paper; half the multiplies): the bush draws, keyed per episode through the counter.
+constexpr uint32_t PHILOX2_M = 0xD256D193u;
+WAB_HD void philox2(const Params& P, uint32_t c0, uint32_t c1, uint32_t out[2]) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p = (uint64_t)PHILOX2_M * c0;
+        const uint32_t n0 = (uint32_t)(p >> 32) ^ c1 ^ P.rk2[r];
+        c1 = (uint32_t)p; c0 = n0;
+    }
+    out[0] = c0; out[1] = c1;
+}
+WAB_HD uint32_t half4(const uint32_t p[2], uint32_t lane) {     // half-word `lane` (0..3) of a 2-word call
+    return (((lane & 2u) ? p[1] : p[0]) >> (16u * (lane & 1u))) & 0xFFFFu;
+}
+WAB_HD uint32_t bush_lane(int32_t x, int32_t y) { return ((uint32_t)x & 1u) | (((uint32_t)y & 1u) << 1); }
+// low half-word of a cell's draw (second Philox2x32 call of its block); `c0` = block ^ ka
+WAB_HD uint32_t bush_low(const Params& P, uint32_t c0, uint32_t kb, uint32_t lane) {
+    uint32_t q[2];
+    philox2(P, c0, ~kb, q);
+    return half4(q, lane);
+}
+// has the cell a bush at first reveal?  word >= thr_bush1 with word = h << 16 | low, low evaluated only on a tie
+WAB_HD uint32_t bush_present(const Params& P, uint32_t h, uint32_t c0, uint32_t kb, uint32_t lane) {
+    const uint32_t t_hi = P.thr_bush1 >> 16, t_lo = P.thr_bush1 & 0xFFFFu;
+    if (h != t_hi) return h > t_hi ? 1u : 0u;
+    return (t_lo == 0u || bush_low(P, c0, kb, lane) >= t_lo) ? 1u : 0u;
+}
+// full 32-bit draw of cell (x, y) (needed for the bush VALUE: eating, re-revealing an eaten cell)
 WAB_HD uint32_t bush_word(const Params& P, const Env& E, int32_t x, int32_t y) {
-    uint32_t w[4];
-    philox(P, E.env_id, E.episode, ctr2(SITE_BUSH, 0, 0), pack_xy(x >> 1, y >> 1), w);
-    return pick4(w, ((uint32_t)x & 1u) | (((uint32_t)y & 1u) << 1));
+    const uint32_t c0 = pack_xy(x >> 1, y >> 1) ^ E.bk_a, lane = bush_lane(x, y);
+    uint32_t p[2];
+    philox2(P, c0, E.bk_b, p);
+    return (half4(p, lane) << 16) | bush_low(P, c0, E.bk_b, lane);
 }
 WAB_HD uint32_t cell_sig(uint32_t cell) { return 1u << ((cell * 0x9E3779B1u) >> 27); }
 // log slot of a cell, or -1. The signature answers "never eaten here" without touching memory; the
@@ -197,12 +230,12 @@ WAB_HD uint32_t alive_after(const Params& P, uint32_t word, uint32_t eats) {
     return word >= P.bush_thr[eats] ? 1u : 0u;
 #endif
 }
-// bush at (x, y) still has food, given its first-reveal draw `word` (only called when word >= thr_bush1)
-WAB_HD uint32_t bush_alive(const Params& P, const Env& E, const Slots& S, int32_t x, int32_t y, uint32_t word) {
+// bush at (x, y) — known to exist at first reveal — still has food? (rare path: only when something was eaten empty)
+WAB_HD uint32_t bush_alive(const Params& P, const Env& E, const Slots& S, int32_t x, int32_t y) {
     if (!E.dep) return 1u;                      // nothing has been eaten empty this episode
     int32_t l = log_find(E, S, pack_xy(x, y));
     if (l < 0) return 1u;
-    return alive_after(P, word, (uint32_t)S.logcnt[(int64_t)l * S.lstride]);
+    return alive_after(P, bush_word(P, E, x, y), (uint32_t)S.logcnt[(int64_t)l * S.lstride]);
 }
 
 // ---- binomial-first sites (oracle/keyed_rng.py): the spawn ring of a step and the window of a reset.
@@ -280,19 +313,17 @@ WAB_HD void slide_window(const Params& P, Env& E, const Slots& S, int32_t dx, in
 #endif
     for (int b = (int)coop.sub; b < 6; b += LPE) {
         const int32_t vb = vb0 + b;
-        uint32_t w[4];
-        const uint32_t payload = along_y ? pack_xy(fixed >> 1, vb) : pack_xy(vb, fixed >> 1);
-        philox(P, E.env_id, E.episode, ctr2(SITE_BUSH, 0, 0), payload, w);
-        // lane = (x&1) | (y&1)<<1 ; the two cells of this block on our line differ in the along bit
-        const uint32_t we0 = along_y ? (fb ? w[1] : w[0]) : (fb ? w[2] : w[0]);
-        const uint32_t we1 = along_y ? (fb ? w[3] : w[2]) : (fb ? w[3] : w[1]);
-        for (int e = 0; e < 2; ++e) {
-            const int32_t v = 2 * vb + e;
+        uint32_t p[2];
+        const uint32_t c0 = (along_y ? pack_xy(fixed >> 1, vb) : pack_xy(vb, fixed >> 1)) ^ E.bk_a;
+        philox2(P, c0, E.bk_b, p);
+        for (uint32_t e = 0; e < 2u; ++e) {
+            // half-word index = (x&1) | (y&1)<<1 ; the two cells of this block on our line differ in the along bit
+            const uint32_t lane = along_y ? (fb | (e << 1)) : (e | (fb << 1));
+            const int32_t v = 2 * vb + (int32_t)e;
             const int32_t g = vmax - v;
-            const uint32_t word = e ? we1 : we0;
-            uint32_t on = (g >= 0 && g <= 10 && word >= P.thr_bush1 && P.n_bush_thr > 0) ? 1u : 0u;
+            uint32_t on = (g >= 0 && g <= 10 && P.n_bush_thr > 0) ? bush_present(P, half4(p, lane), c0, E.bk_b, lane) : 0u;
             if (on && E.dep)
-                on = along_y ? bush_alive(P, E, S, fixed, v, word) : bush_alive(P, E, S, v, fixed, word);
+                on = along_y ? bush_alive(P, E, S, fixed, v) : bush_alive(P, E, S, v, fixed);
             line |= on << (g & 15);
         }
     }
@@ -497,17 +528,18 @@ WAB_HD void env_step(const Params& P, Env& E, const Slots& S, uint32_t action, S
 // bush block blk (0..35) of the reset window -> occupancy bits (generate_bushes at reset, :244).
 // The block's four cells are bits base, base+1, base+11, base+12 of the window (base = the cell with
 // the larger x and y), so they are deposited as one 13-bit pattern.
-WAB_HD void reset_bush_block(const Params& P, uint32_t env_id, uint32_t episode, int blk, uint32_t part[4]) {
+WAB_HD void reset_bush_block(const Params& P, uint32_t ka, uint32_t kb, int blk, uint32_t part[4]) {
     const int32_t xb = blk / 6 - 3, yb = blk % 6 - 3;       // x >> 1 for x in [-5, 5] is [-3, 2]
-    uint32_t w[4];
-    philox(P, env_id, episode, ctr2(SITE_BUSH, 0, 0), pack_xy(xb, yb), w);
+    uint32_t p[2];
+    const uint32_t c0 = pack_xy(xb, yb) ^ ka;
+    philox2(P, c0, kb, p);
     const bool has = P.n_bush_thr > 0;
     const bool x0 = xb > -3, y0 = yb > -3;                   // x = 2*xb (resp. y = 2*yb) is -6 when xb = -3: outside
-    // lane l = (x&1) | (y&1)<<1 ; [i][j] = [5 - x][5 - y]
-    const uint32_t b11 = (has && w[3] >= P.thr_bush1) ? 1u : 0u;                 // x = 2xb+1, y = 2yb+1 -> base
-    const uint32_t b10 = (has && y0 && w[1] >= P.thr_bush1) ? 1u : 0u;           // x = 2xb+1, y = 2yb   -> base + 1
-    const uint32_t b01 = (has && x0 && w[2] >= P.thr_bush1) ? 1u : 0u;           // x = 2xb,   y = 2yb+1 -> base + 11
-    const uint32_t b00 = (has && x0 && y0 && w[0] >= P.thr_bush1) ? 1u : 0u;     // x = 2xb,   y = 2yb   -> base + 12
+    // half-word index l = (x&1) | (y&1)<<1 ; [i][j] = [5 - x][5 - y]
+    const uint32_t b11 = has ? bush_present(P, half4(p, 3u), c0, kb, 3u) : 0u;                // x = 2xb+1, y = 2yb+1 -> base
+    const uint32_t b10 = (has && y0) ? bush_present(P, half4(p, 1u), c0, kb, 1u) : 0u;        // x = 2xb+1, y = 2yb   -> base + 1
+    const uint32_t b01 = (has && x0) ? bush_present(P, half4(p, 2u), c0, kb, 2u) : 0u;        // x = 2xb,   y = 2yb+1 -> base + 11
+    const uint32_t b00 = (has && x0 && y0) ? bush_present(P, half4(p, 0u), c0, kb, 0u) : 0u;  // x = 2xb,   y = 2yb   -> base + 12
     const uint32_t pat = b11 | (b10 << 1) | (b01 << 11) | (b00 << 12);
     const int base = 11 * (4 - 2 * xb) + (4 - 2 * yb);       // 0 .. 120
     const uint32_t r = (uint32_t)base & 31u;
@@ -553,12 +585,11 @@ WAB_HD void reset_scalars(const Params& P, Env& E) {
     E.role = (uint32_t)(P.starting_role < 0 ? 0 : P.starting_role);
     E.food_i = P.food_int_start;
     E.food_f = P.food_start;
-    if (P.starting_role < 0 || P.food_random) {
-        uint32_t w[4];
-        philox(P, E.env_id, E.episode, ctr2(SITE_START, 0, 0), 0u, w);
-        if (P.starting_role < 0) E.role = w[1] >> 31;                 // np.random.randint(2), :598-599
-        if (P.food_random) E.food_f = (double)w[0] * (1.0 / 4294967296.0);   // np.random.random(), :596-597
-    }
+    uint32_t w[4];
+    philox(P, E.env_id, E.episode, ctr2(SITE_START, 0, 0), 0u, w);
+    E.bk_a = w[2]; E.bk_b = w[3];                                         // bush key of the new episode
+    if (P.starting_role < 0) E.role = w[1] >> 31;                         // np.random.randint(2), :598-599
+    if (P.food_random) E.food_f = (double)w[0] * (1.0 / 4294967296.0);    // np.random.random(), :596-597
     (void)F64;
 }
 

@@ -53,6 +53,7 @@ struct StatePtrs {
     uint4* bush;         // [N]  121-bit window occupancy
     uint8_t* nlog;       // [N]
     uint32_t* logsig;    // [N]  Bloom signature of the depletion log
+    uint2* bkey;         // [N]  the episode's bush key
     double* food;        // [N]  F64 mode only
     uint32_t* wolves;    // [wolf_cap][N]
     uint32_t* logcell;   // [log_cap][N]
@@ -80,6 +81,7 @@ __device__ __forceinline__ void load_env(const Params& P, const StatePtrs& st, i
     E.m[0] = b.x; E.m[1] = b.y; E.m[2] = b.z; E.m[3] = b.w;
     E.nlog = st.nlog[idx];
     E.logsig = st.logsig[idx];
+    { const uint2 bk = st.bkey[idx]; E.bk_a = bk.x; E.bk_b = bk.y; }
     E.food_f = F64 ? st.food[idx] : 0.0;
     E.env_id = (uint32_t)(P.env_id_base + (uint64_t)idx);
     WAB_ROLLED
@@ -96,6 +98,7 @@ __device__ __forceinline__ void store_env(const StatePtrs& st, int64_t idx, cons
     st.bush[idx] = make_uint4(E.m[0], E.m[1], E.m[2], E.m[3]);
     st.nlog[idx] = (uint8_t)E.nlog;
     st.logsig[idx] = E.logsig;
+    st.bkey[idx] = make_uint2(E.bk_a, E.bk_b);
     if (F64) st.food[idx] = E.food_f;
     WAB_ROLLED
     for (uint32_t k = 0; k < E.nw; ++k) st.wolves[(int64_t)k * st.n + idx] = wolves_s[k * wstride];
@@ -114,11 +117,11 @@ __device__ __forceinline__ void warp_reset(const Params& P, Env& E, const Slots&
         const int r = __ffs((int)todo) - 1;                       // first lane of the group to reset
         todo &= (LPE == 32) ? 0u : ~(((1u << (LPE & 31)) - 1u) << r);
         const bool mine = (lane / LPE) == (r / LPE);
-        const uint32_t eid = __shfl_sync(FULL, E.env_id, r);
-        const uint32_t ep = __shfl_sync(FULL, E.episode, r);
+        const uint32_t ka = __shfl_sync(FULL, E.bk_a, r);
+        const uint32_t kb = __shfl_sync(FULL, E.bk_b, r);
         uint32_t part[4] = {0u, 0u, 0u, 0u};
 #pragma unroll 1
-        for (int blk = lane; blk < 36; blk += 32) reset_bush_block(P, eid, ep, blk, part);   // 36 blocks over 32 lanes
+        for (int blk = lane; blk < 36; blk += 32) reset_bush_block(P, ka, kb, blk, part);    // 36 blocks over 32 lanes
         const uint32_t m0 = __reduce_or_sync(FULL, part[0]);
         const uint32_t m1 = __reduce_or_sync(FULL, part[1]);
         const uint32_t m2 = __reduce_or_sync(FULL, part[2]);
@@ -641,6 +644,7 @@ int wab_vec_create(const WabConfig* cfg, const uint32_t* bush_thr, int32_t n_bus
     const size_t o_bush = o; o = align_up(o + 16 * n, 256);
     const size_t o_nlog = o; o = align_up(o + n, 256);
     const size_t o_lsig = o; o = align_up(o + 4 * n, 256);
+    const size_t o_bkey = o; o = align_up(o + 8 * n, 256);
     const size_t o_food = o; o = align_up(o + 8 * n, 256);
     const size_t o_wolves = o; o = align_up(o + 4 * n * (size_t)cfg->wolf_cap, 256);
     const size_t o_lcell = o; o = align_up(o + 4 * n * (size_t)cfg->log_cap, 256);
@@ -660,7 +664,7 @@ int wab_vec_create(const WabConfig* cfg, const uint32_t* bush_thr, int32_t n_bus
     P.bush_thr = h->d_thr;
     StatePtrs& st = h->st;
     st.pos = (uint32_t*)(base + o_pos); st.misc = (uint32_t*)(base + o_misc); st.episode = (uint32_t*)(base + o_ep);
-    st.bush = (uint4*)(base + o_bush); st.nlog = base + o_nlog; st.logsig = (uint32_t*)(base + o_lsig); st.food = (double*)(base + o_food);
+    st.bush = (uint4*)(base + o_bush); st.nlog = base + o_nlog; st.logsig = (uint32_t*)(base + o_lsig); st.bkey = (uint2*)(base + o_bkey); st.food = (double*)(base + o_food);
     st.wolves = (uint32_t*)(base + o_wolves); st.logcell = (uint32_t*)(base + o_lcell); st.logcnt = base + o_lcnt;
     st.stats = (unsigned long long*)(base + o_stats); st.n = n_envs;
     h->lpe = pick_lpe(h);

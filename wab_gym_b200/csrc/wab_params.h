@@ -52,6 +52,10 @@ inline void params_from_config(const WabConfig& c, const uint32_t* bush_thr_host
     const uint32_t* bush_thr = bush_thr_host;
     memset(&P, 0, sizeof(P));
     fill_round_keys(P, (uint32_t)seed, (uint32_t)(seed >> 32));
+    {
+        uint32_t k2 = (uint32_t)(seed ^ (seed >> 32));
+        for (int r = 0; r < 10; ++r) { P.rk2[r] = k2; k2 += PHILOX_W0; }
+    }
     P.n_bush_thr = (uint32_t)n_bush_thr;
     P.thr_bush1 = n_bush_thr > 0 ? bush_thr[0] : 0xFFFFFFFFu;
     P.thr_bush2 = n_bush_thr > 1 ? bush_thr[1] : 0xFFFFFFFFu;
