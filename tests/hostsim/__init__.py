@@ -49,6 +49,7 @@ def lib():
         L.hostsim2_observe.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
         L.hostsim2_act.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
         L.hostsim2_state.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.hostsim_reveal_probe.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int64, ctypes.c_void_p]
         L.hostsim_philox2.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]
         L.hostsim_philox.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p]
         _lib = L
@@ -96,6 +97,13 @@ class HostSimEnv:
         return {"x": int(scal[0]), "y": int(scal[1]), "food": food.value, "role": int(scal[3]), "status": int(scal[4]),
                 "turn": int(scal[5]), "episode": int(scal[6]), "wolves": sorted((int(a), int(b)) for a, b in wolves[:nw]),
                 "n_log": int(scal[8]), "bush_mask": mask}
+
+
+def reveal_probe(seed, thr, iters):
+    """(tied cells, mismatching cells, cells checked) of the reveal paths against full-word draws."""
+    out = np.zeros(3, dtype=np.int64)
+    lib().hostsim_reveal_probe(int(seed), int(thr), int(iters), out.ctypes.data)
+    return tuple(int(v) for v in out)
 
 
 def philox2(ctr, key):

@@ -129,6 +129,69 @@ void hostsim_features(const uint8_t* wolf_grid, const uint8_t* bush_grid, int32_
     memcpy(out28, f, 28);
 }
 
+// Volume probe of the reveal paths (slide_window, reset_bush_block) against the draw contract evaluated cell by
+// cell on full 32-bit words. A tie of a cell's high half-word with the threshold's (2^-16 per cell) takes a rare
+// branch that whole-episode tests almost never reach; this loop reaches it hundreds of times.
+// out3 = {cells whose high half-word tied, mismatching cells, cells checked}
+static uint32_t exact_bush(const Params& P, uint32_t ka, uint32_t kb, int32_t wx, int32_t wy, uint32_t* tie) {
+    const uint32_t c0 = pack_xy(wx >> 1, wy >> 1) ^ ka;
+    uint32_t p[2], q[2];
+    philox2(P, c0, kb, p);
+    philox2(P, c0, ~kb, q);
+    const uint32_t hw = (wy & 1) ? p[1] : p[0], lw = (wy & 1) ? q[1] : q[0];
+    const uint32_t h = (wx & 1) ? (hw >> 16) : (hw & 0xFFFFu), l = (wx & 1) ? (lw >> 16) : (lw & 0xFFFFu);
+    if (h == (P.thr_bush1 >> 16)) *tie += 1;
+    return ((h << 16) | l) >= P.thr_bush1 ? 1u : 0u;
+}
+
+void hostsim_reveal_probe(uint64_t seed, uint32_t thr, int64_t iters, int64_t* out3) {
+    Params P;
+    memset(&P, 0, sizeof(P));
+    uint32_t k2 = (uint32_t)(seed ^ (seed >> 32));
+    for (int r = 0; r < 10; ++r) { P.rk2[r] = k2; k2 += PHILOX_W0; }
+    P.thr_bush1 = thr; P.thr_bush2 = 0xFFFFFFFFu; P.n_bush_thr = 1;
+    Slots S;
+    memset(&S, 0, sizeof(S));
+    uint64_t lcg = seed * 6364136223846793005ull + 1442695040888963407ull;
+    auto next = [&lcg]() { lcg = lcg * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(lcg >> 32); };
+    uint32_t ties = 0;
+    int64_t bad = 0, checked = 0;
+    const Coop<1> coop{0u, 1u};
+    for (int64_t it = 0; it < iters; ++it) {
+        Env E;
+        memset(&E, 0, sizeof(E));
+        E.bk_a = next(); E.bk_b = next();
+        if (it % 8 == 7) {                       // a reset window around the origin
+            uint32_t m[4] = {0, 0, 0, 0};
+            for (int blk = 0; blk < 36; ++blk) reset_bush_block(P, E.bk_a, E.bk_b, blk, m);
+            for (int i = 0; i < 11; ++i)
+                for (int j = 0; j < 11; ++j) {
+                    const uint32_t want = exact_bush(P, E.bk_a, E.bk_b, 5 - i, 5 - j, &ties);
+                    const int b = 11 * i + j;
+                    bad += ((m[b >> 5] >> (b & 31)) & 1u) != want;
+                    ++checked;
+                }
+            bad += (m[3] >> 25) != 0u;
+            continue;
+        }
+        E.x = (int32_t)(next() % 4001u) - 2000; E.y = (int32_t)(next() % 4001u) - 2000;
+        const uint32_t d = next() & 3u;
+        const int32_t dx = d == 0 ? 1 : d == 1 ? -1 : 0, dy = d == 2 ? 1 : d == 3 ? -1 : 0;
+        slide_window<1>(P, E, S, dx, dy, coop);
+        uint32_t seen[4] = {0, 0, 0, 0};
+        for (int g = 0; g < 11; ++g) {
+            const int32_t wx = dx ? E.x + HALF * dx : E.x + HALF - g, wy = dx ? E.y + HALF - g : E.y + HALF * dy;
+            const uint32_t want = exact_bush(P, E.bk_a, E.bk_b, wx, wy, &ties);
+            const int b = 11 * (5 - (wx - E.x)) + (5 - (wy - E.y));
+            bad += ((E.m[b >> 5] >> (b & 31)) & 1u) != want;
+            seen[b >> 5] |= 1u << (b & 31);
+            ++checked;
+        }
+        for (int w = 0; w < 4; ++w) bad += (E.m[w] & ~seen[w]) != 0u;      // nothing outside the new line
+    }
+    out3[0] = ties; out3[1] = bad; out3[2] = checked;
+}
+
 void hostsim_philox2(const uint32_t* ctr, uint32_t key, uint32_t* out) {
     Params P;
     memset(&P, 0, sizeof(P));

@@ -92,3 +92,13 @@ def test_wolf_and_log_overflow_are_reported():
     for _ in range(5):
         seen |= sim.step(4)[4]
     assert seen == 1
+
+
+@pytest.mark.parametrize("thr", [0x80008000, 0x12340000, 0xFFFF0001, 0x0000FFFF, 0xE6666667])
+def test_reveal_paths_settle_half_word_ties_on_the_full_draw(thr):
+    """slide_window / reset_bush_block compare 16-bit half-words and fall back to the full 32-bit draw on a tie
+    with the threshold's upper half (2^-16 per cell): 300k reveals reach that branch hundreds of times."""
+    from tests import hostsim
+    ties, bad, checked = hostsim.reveal_probe(seed=thr ^ 0x5DEECE66D, thr=thr, iters=300_000)
+    assert checked > 7_000_000 and ties > 60, (ties, checked)
+    assert bad == 0, (bad, ties, checked)

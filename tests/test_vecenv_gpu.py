@@ -251,11 +251,14 @@ def test_host_buffer_path_and_masked_reset():
     assert np.array_equal(loose["grids"].numpy(), o.grids.cpu().numpy()) and np.array_equal(loose["reward"].numpy(), r.cpu().numpy())
     # masked reset: only the selected envs start a new episode
     before = b.export_state()
+    prev = [t.cpu().numpy().copy() for t in o]
     mask = torch.zeros(n, dtype=torch.uint8, device="cuda")
     mask[::3] = 1
-    b.reset(mask)
+    again = [t.cpu().numpy() for t in b.reset(mask)]
     after = b.export_state()
     sel = mask.cpu().numpy().astype(bool)
+    for was, now in zip(prev, again):         # the others get their last observation again (bush just eaten included)
+        assert np.array_equal(was[~sel], now[~sel])
     assert np.array_equal(after["episode"][sel], before["episode"][sel] + 1) and np.all(after["turn"][sel] == 0)
     assert np.array_equal(after["episode"][~sel], before["episode"][~sel]) and np.array_equal(after["x"][~sel], before["x"][~sel])
     a.close(), b.close()

@@ -87,6 +87,8 @@ struct Env {
     uint32_t bk_a, bk_b;  // the episode's bush key (words 2, 3 of the START call, oracle/keyed_rng.py)
     uint32_t logsig; // 32-bit Bloom signature of the cells in the depletion log (a clear bit proves absence)
     uint32_t dep;    // 1 once some logged cell has been eaten empty (re-entering cells must consult the log)
+    uint32_t stale;  // 1 iff the last step ate the bush under the ostrich empty: that step's observation still
+                     // showed it (the frame of :266 predates the eat), and so must a re-emitted one
     uint32_t m[4];   // bush occupancy of the window (food > 0), current
     int32_t food_i;  // INT mode
     double food_f;   // F64 mode
@@ -186,28 +188,34 @@ WAB_HD void philox2(const Params& P, uint32_t c0, uint32_t c1, uint32_t out[2]) 
     }
     out[0] = c0; out[1] = c1;
 }
-WAB_HD uint32_t half4(const uint32_t p[2], uint32_t lane) {     // half-word `lane` (0..3) of a 2-word call
-    return (((lane & 2u) ? p[1] : p[0]) >> (16u * (lane & 1u))) & 0xFFFFu;
-}
+// Cell (x, y) of a 2x2 block owns half-word lane = (x & 1) | (y & 1) << 1 of the block's two words:
+// word (y & 1), upper half iff (x & 1).
 WAB_HD uint32_t bush_lane(int32_t x, int32_t y) { return ((uint32_t)x & 1u) | (((uint32_t)y & 1u) << 1); }
-// low half-word of a cell's draw (second Philox2x32 call of its block); `c0` = block ^ ka
-WAB_HD uint32_t bush_low(const Params& P, uint32_t c0, uint32_t kb, uint32_t lane) {
-    uint32_t q[2];
-    philox2(P, c0, ~kb, q);
-    return half4(q, lane);
+WAB_HD uint32_t half_sel(uint32_t upper) { return upper ? 0x4432u : 0x4410u; }      // byte-permute selector
+WAB_HD uint32_t half_of(uint32_t w, uint32_t sel) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(w, 0u, sel);
+#else
+    return sel == 0x4432u ? (w >> 16) : (w & 0xFFFFu);
+#endif
 }
-// has the cell a bush at first reveal?  word >= thr_bush1 with word = h << 16 | low, low evaluated only on a tie
-WAB_HD uint32_t bush_present(const Params& P, uint32_t h, uint32_t c0, uint32_t kb, uint32_t lane) {
-    const uint32_t t_hi = P.thr_bush1 >> 16, t_lo = P.thr_bush1 & 0xFFFFu;
-    if (h != t_hi) return h > t_hi ? 1u : 0u;
-    return (t_lo == 0u || bush_low(P, c0, kb, lane) >= t_lo) ? 1u : 0u;
+// Full 32-bit draw of a cell: high half-word from the block call (counter (c0, kb)), low half-word from the
+// block's second call (counter (c0, ~kb)); c0 = block ^ ka. Needed for bush VALUES (eating, re-revealing an
+// eaten cell) and on a 2^-16 tie of the high half-word with the threshold's, so it is an out-of-line call
+// taking scalars only (a Params reference would turn the constant-bank operands into generic loads).
+WAB_HD_RARE uint32_t bush_word_rare(uint32_t c0, uint32_t kb, uint32_t key, uint32_t lane) {
+    uint32_t a0 = c0, a1 = kb, b0 = c0, b1 = ~kb;
+    WAB_ROLLED
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t pa = (uint64_t)PHILOX2_M * a0, pb = (uint64_t)PHILOX2_M * b0;
+        const uint32_t na = (uint32_t)(pa >> 32) ^ a1 ^ key, nb = (uint32_t)(pb >> 32) ^ b1 ^ key;
+        a1 = (uint32_t)pa; a0 = na; b1 = (uint32_t)pb; b0 = nb; key += PHILOX_W0;
+    }
+    const uint32_t sel = half_sel(lane & 1u);
+    return (half_of((lane & 2u) ? a1 : a0, sel) << 16) | half_of((lane & 2u) ? b1 : b0, sel);
 }
-// full 32-bit draw of cell (x, y) (needed for the bush VALUE: eating, re-revealing an eaten cell)
 WAB_HD uint32_t bush_word(const Params& P, const Env& E, int32_t x, int32_t y) {
-    const uint32_t c0 = pack_xy(x >> 1, y >> 1) ^ E.bk_a, lane = bush_lane(x, y);
-    uint32_t p[2];
-    philox2(P, c0, E.bk_b, p);
-    return (half4(p, lane) << 16) | bush_low(P, c0, E.bk_b, lane);
+    return bush_word_rare(pack_xy(x >> 1, y >> 1) ^ E.bk_a, E.bk_b, P.rk2[0], bush_lane(x, y));
 }
 WAB_HD uint32_t cell_sig(uint32_t cell) { return 1u << ((cell * 0x9E3779B1u) >> 27); }
 // log slot of a cell, or -1. The signature answers "never eaten here" without touching memory; the
@@ -307,26 +315,55 @@ WAB_HD void slide_window(const Params& P, Env& E, const Slots& S, int32_t dx, in
     const int32_t vmax = (along_y ? E.y : E.x) + HALF;    // cell g of the line has coordinate vmax - g
     const int32_t vb0 = (vmax - 10) >> 1;
     const uint32_t fb = (uint32_t)fixed & 1u;
-    uint32_t line = 0;
+    // The 6 blocks hold 12 cells, g + 1 = top, top - 1, ..., top - 11 with top = 11 or 12: bit g + 1 of `acc`.
+    const int32_t top = vmax - 2 * vb0 + 1;
+    const uint32_t t_hi = P.thr_bush1 >> 16;
+    // a line along y meets word e (cell parity e) at half fb; a line along x meets word fb at half e
+    const uint32_t sel0 = half_sel(along_y ? fb : 0u), sel1 = half_sel(along_y ? fb : 1u);
+    uint32_t acc = 0, tie = 0;
+    if (P.n_bush_thr > 0) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll kSlideUnroll
 #endif
-    for (int b = (int)coop.sub; b < 6; b += LPE) {
-        const int32_t vb = vb0 + b;
-        uint32_t p[2];
-        const uint32_t c0 = (along_y ? pack_xy(fixed >> 1, vb) : pack_xy(vb, fixed >> 1)) ^ E.bk_a;
-        philox2(P, c0, E.bk_b, p);
-        for (uint32_t e = 0; e < 2u; ++e) {
-            // half-word index = (x&1) | (y&1)<<1 ; the two cells of this block on our line differ in the along bit
-            const uint32_t lane = along_y ? (fb | (e << 1)) : (e | (fb << 1));
-            const int32_t v = 2 * vb + (int32_t)e;
-            const int32_t g = vmax - v;
-            uint32_t on = (g >= 0 && g <= 10 && P.n_bush_thr > 0) ? bush_present(P, half4(p, lane), c0, E.bk_b, lane) : 0u;
-            if (on && E.dep)
-                on = along_y ? bush_alive(P, E, S, fixed, v) : bush_alive(P, E, S, v, fixed);
-            line |= on << (g & 15);
+        for (int b = (int)coop.sub; b < 6; b += LPE) {
+            uint32_t p[2];
+            const uint32_t c0 = (along_y ? pack_xy(fixed >> 1, vb0 + b) : pack_xy(vb0 + b, fixed >> 1)) ^ E.bk_a;
+            philox2(P, c0, E.bk_b, p);
+            const uint32_t h0 = half_of((along_y || !fb) ? p[0] : p[1], sel0);
+            const uint32_t h1 = half_of((along_y || fb) ? p[1] : p[0], sel1);
+            const uint32_t bit = 1u << (top - 2 * b);
+            acc |= (h0 > t_hi ? bit : 0u) | (h1 > t_hi ? (bit >> 1) : 0u);
+            tie |= (h0 == t_hi ? 1u : 0u) | (h1 == t_hi ? 1u : 0u);
+        }
+        if (tie) {                 // 2^-15 per block: settle this lane's cells on their full 32-bit draws
+            acc = 0;
+            WAB_ROLLED
+            for (int b = (int)coop.sub; b < 6; b += LPE) {
+                const uint32_t c0 = (along_y ? pack_xy(fixed >> 1, vb0 + b) : pack_xy(vb0 + b, fixed >> 1)) ^ E.bk_a;
+                WAB_ROLLED
+                for (uint32_t e = 0; e < 2u; ++e) {
+                    const uint32_t lane = along_y ? (fb | (e << 1)) : (e | (fb << 1));
+                    if (bush_word_rare(c0, E.bk_b, P.rk2[0], lane) >= P.thr_bush1) acc |= 1u << (top - 2 * b - (int32_t)e);
+                }
+            }
+        }
+        acc &= 0xFFEu;             // cells g = 0..10
+        if (E.dep) {               // something was eaten empty this episode: revealed cells consult the log
+            uint32_t bits = acc;
+            WAB_ROLLED
+            while (bits) {
+#if defined(__CUDA_ARCH__)
+                const int k = __ffs((int)bits) - 1;
+#else
+                const int k = __builtin_ctz(bits);
+#endif
+                bits &= bits - 1u;
+                const int32_t v = vmax - (k - 1);
+                if (!(along_y ? bush_alive(P, E, S, fixed, v) : bush_alive(P, E, S, v, fixed))) acc &= ~(1u << k);
+            }
         }
     }
+    uint32_t line = acc >> 1;
     line = group_or(coop, line);
     if (along_y) {                                // row i = 0 (dx > 0) or i = 10 (dx < 0): bits 11*i + g
         E.m[0] |= (dx > 0) ? line : 0u;
@@ -437,6 +474,7 @@ WAB_HD void env_step(const Params& P, Env& E, const Slots& S, uint32_t action, S
 
     // ---- :300-313 eat (bush and status as of the frame above; role is fresh)
     O.ate = 0;
+    E.stale = 0u;
     if (((O.bm[1] >> 28) & 1u) && (E.role == 1u || P.lookout_only) && status_pre == 0u) {   // bit 60 = [5][5]
         O.ate = 1u;
         if (F64) {
@@ -463,7 +501,7 @@ WAB_HD void env_step(const Params& P, Env& E, const Slots& S, uint32_t action, S
         } else {
             eats = 1u; O.overflow = 1u;            // counted, never silent (WAB_STAT_OVERFLOWS)
         }
-        if (!alive_after(P, bush_word(P, E, E.x, E.y), eats)) { E.m[1] &= ~(1u << 28); E.dep = 1u; }
+        if (!alive_after(P, bush_word(P, E, E.x, E.y), eats)) { E.m[1] &= ~(1u << 28); E.dep = 1u; E.stale = 1u; }
     }
 
     // ---- :316-322 hunger, starvation (overrides killed)
@@ -533,13 +571,25 @@ WAB_HD void reset_bush_block(const Params& P, uint32_t ka, uint32_t kb, int blk,
     uint32_t p[2];
     const uint32_t c0 = pack_xy(xb, yb) ^ ka;
     philox2(P, c0, kb, p);
+    // half-word lane = (x&1) | (y&1)<<1 : word (y&1), upper half iff (x&1)
+    uint32_t h[4] = {p[0] & 0xFFFFu, p[0] >> 16, p[1] & 0xFFFFu, p[1] >> 16};
+    const uint32_t t_hi = P.thr_bush1 >> 16;
+    uint32_t on[4];
+    on[0] = h[0] > t_hi; on[1] = h[1] > t_hi; on[2] = h[2] > t_hi; on[3] = h[3] > t_hi;
+    if (h[0] == t_hi || h[1] == t_hi || h[2] == t_hi || h[3] == t_hi) {      // tie: full 32-bit draws decide
+        WAB_ROLLED
+        for (uint32_t l = 0; l < 4u; ++l) {
+            const uint32_t v = bush_word_rare(c0, kb, P.rk2[0], l) >= P.thr_bush1 ? 1u : 0u;
+            if (l == 0u) on[0] = v; else if (l == 1u) on[1] = v; else if (l == 2u) on[2] = v; else on[3] = v;
+        }
+    }
     const bool has = P.n_bush_thr > 0;
     const bool x0 = xb > -3, y0 = yb > -3;                   // x = 2*xb (resp. y = 2*yb) is -6 when xb = -3: outside
-    // half-word index l = (x&1) | (y&1)<<1 ; [i][j] = [5 - x][5 - y]
-    const uint32_t b11 = has ? bush_present(P, half4(p, 3u), c0, kb, 3u) : 0u;                // x = 2xb+1, y = 2yb+1 -> base
-    const uint32_t b10 = (has && y0) ? bush_present(P, half4(p, 1u), c0, kb, 1u) : 0u;        // x = 2xb+1, y = 2yb   -> base + 1
-    const uint32_t b01 = (has && x0) ? bush_present(P, half4(p, 2u), c0, kb, 2u) : 0u;        // x = 2xb,   y = 2yb+1 -> base + 11
-    const uint32_t b00 = (has && x0 && y0) ? bush_present(P, half4(p, 0u), c0, kb, 0u) : 0u;  // x = 2xb,   y = 2yb   -> base + 12
+    // [i][j] = [5 - x][5 - y]
+    const uint32_t b11 = has ? on[3] : 0u;                   // x = 2xb+1, y = 2yb+1 -> base
+    const uint32_t b10 = (has && y0) ? on[1] : 0u;           // x = 2xb+1, y = 2yb   -> base + 1
+    const uint32_t b01 = (has && x0) ? on[2] : 0u;           // x = 2xb,   y = 2yb+1 -> base + 11
+    const uint32_t b00 = (has && x0 && y0) ? on[0] : 0u;     // x = 2xb,   y = 2yb   -> base + 12
     const uint32_t pat = b11 | (b10 << 1) | (b01 << 11) | (b00 << 12);
     const int base = 11 * (4 - 2 * xb) + (4 - 2 * yb);       // 0 .. 120
     const uint32_t r = (uint32_t)base & 31u;
@@ -581,7 +631,7 @@ WAB_HD void reset_init_wolves(const Params& P, Env& E, const Slots& S, uint32_t&
 template <bool F64>
 WAB_HD void reset_scalars(const Params& P, Env& E) {
     E.episode += 1;                 // first reset -> episode 0 (state is created with 0xFFFFFFFF)
-    E.turn = 0; E.x = 0; E.y = 0; E.status = 0; E.nw = 0; E.nlog = 0; E.dep = 0; E.logsig = 0;
+    E.turn = 0; E.x = 0; E.y = 0; E.status = 0; E.nw = 0; E.nlog = 0; E.dep = 0; E.stale = 0; E.logsig = 0;
     E.role = (uint32_t)(P.starting_role < 0 ? 0 : P.starting_role);
     E.food_i = P.food_int_start;
     E.food_f = P.food_start;

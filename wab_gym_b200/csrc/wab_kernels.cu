@@ -51,7 +51,7 @@ struct StatePtrs {
     uint32_t* misc;      // [N]  food_i:8 | role:1 | status:2 | nw:4 | -:1 | turn:16
     uint32_t* episode;   // [N]
     uint4* bush;         // [N]  121-bit window occupancy
-    uint8_t* nlog;       // [N]
+    uint16_t* nlog;      // [N]  entries in the depletion log : 8 | stale centre bush : 1
     uint32_t* logsig;    // [N]  Bloom signature of the depletion log
     uint2* bkey;         // [N]  the episode's bush key
     double* food;        // [N]  F64 mode only
@@ -79,7 +79,7 @@ __device__ __forceinline__ void load_env(const Params& P, const StatePtrs& st, i
     E.episode = st.episode[idx];
     const uint4 b = st.bush[idx];
     E.m[0] = b.x; E.m[1] = b.y; E.m[2] = b.z; E.m[3] = b.w;
-    E.nlog = st.nlog[idx];
+    { const uint32_t nl = st.nlog[idx]; E.nlog = nl & 0xFFu; E.stale = nl >> 8; }
     E.logsig = st.logsig[idx];
     { const uint2 bk = st.bkey[idx]; E.bk_a = bk.x; E.bk_b = bk.y; }
     E.food_f = F64 ? st.food[idx] : 0.0;
@@ -96,7 +96,7 @@ __device__ __forceinline__ void store_env(const StatePtrs& st, int64_t idx, cons
                    (E.turn << 16);
     st.episode[idx] = E.episode;
     st.bush[idx] = make_uint4(E.m[0], E.m[1], E.m[2], E.m[3]);
-    st.nlog[idx] = (uint8_t)E.nlog;
+    st.nlog[idx] = (uint16_t)(E.nlog | (E.stale << 8));
     st.logsig[idx] = E.logsig;
     st.bkey[idx] = make_uint2(E.bk_a, E.bk_b);
     if (F64) st.food[idx] = E.food_f;
@@ -387,7 +387,7 @@ wab_reset_kernel(const __grid_constant__ Params P, const StatePtrs st, const uin
     uint32_t cnt[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
     if (c.active && !need) {
         wolf_plane(E, S, O.wm);
-        O.bm[0] = E.m[0]; O.bm[1] = E.m[1]; O.bm[2] = E.m[2]; O.bm[3] = E.m[3];
+        O.bm[0] = E.m[0]; O.bm[1] = E.m[1] | (E.stale << 28); O.bm[2] = E.m[2]; O.bm[3] = E.m[3];   // as last observed
     }
     warp_reset<F64, LPE>(P, E, S, need, c.lane, O.wm, O.bm, O.overflow);
     if (c.active) {
@@ -642,7 +642,7 @@ int wab_vec_create(const WabConfig* cfg, const uint32_t* bush_thr, int32_t n_bus
     const size_t o_misc = o; o = align_up(o + 4 * n, 256);
     const size_t o_ep = o; o = align_up(o + 4 * n, 256);
     const size_t o_bush = o; o = align_up(o + 16 * n, 256);
-    const size_t o_nlog = o; o = align_up(o + n, 256);
+    const size_t o_nlog = o; o = align_up(o + 2 * n, 256);
     const size_t o_lsig = o; o = align_up(o + 4 * n, 256);
     const size_t o_bkey = o; o = align_up(o + 8 * n, 256);
     const size_t o_food = o; o = align_up(o + 8 * n, 256);
@@ -664,7 +664,7 @@ int wab_vec_create(const WabConfig* cfg, const uint32_t* bush_thr, int32_t n_bus
     P.bush_thr = h->d_thr;
     StatePtrs& st = h->st;
     st.pos = (uint32_t*)(base + o_pos); st.misc = (uint32_t*)(base + o_misc); st.episode = (uint32_t*)(base + o_ep);
-    st.bush = (uint4*)(base + o_bush); st.nlog = base + o_nlog; st.logsig = (uint32_t*)(base + o_lsig); st.bkey = (uint2*)(base + o_bkey); st.food = (double*)(base + o_food);
+    st.bush = (uint4*)(base + o_bush); st.nlog = (uint16_t*)(base + o_nlog); st.logsig = (uint32_t*)(base + o_lsig); st.bkey = (uint2*)(base + o_bkey); st.food = (double*)(base + o_food);
     st.wolves = (uint32_t*)(base + o_wolves); st.logcell = (uint32_t*)(base + o_lcell); st.logcnt = base + o_lcnt;
     st.stats = (unsigned long long*)(base + o_stats); st.n = n_envs;
     h->lpe = pick_lpe(h);
@@ -838,13 +838,13 @@ int wab_vec_export_state(WabVec* h, int32_t* x, int32_t* y, double* food, int32_
     const size_t n = (size_t)h->n;
     const int wc = h->cfg.wolf_cap, lc = h->cfg.log_cap;
     uint32_t* pos = new uint32_t[n]; uint32_t* misc = new uint32_t[n]; uint32_t* ep = new uint32_t[n];
-    uint32_t* bush = new uint32_t[4 * n]; uint8_t* nl = new uint8_t[n]; double* fd = new double[n];
+    uint32_t* bush = new uint32_t[4 * n]; uint16_t* nl = new uint16_t[n]; double* fd = new double[n];
     uint32_t* wv = new uint32_t[n * wc]; uint32_t* lcell = new uint32_t[n * lc]; uint8_t* lcnt = new uint8_t[n * lc];
     cudaError_t e = cudaMemcpy(pos, h->st.pos, 4 * n, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(misc, h->st.misc, 4 * n, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(ep, h->st.episode, 4 * n, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(bush, h->st.bush, 16 * n, cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess) e = cudaMemcpy(nl, h->st.nlog, n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(nl, h->st.nlog, 2 * n, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(fd, h->st.food, 8 * n, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(wv, h->st.wolves, 4 * n * wc, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(lcell, h->st.logcell, 4 * n * lc, cudaMemcpyDeviceToHost);
@@ -868,11 +868,11 @@ int wab_vec_export_state(WabVec* h, int32_t* x, int32_t* y, double* food, int32_
                     wolves_xy[(i * wc + k) * 2 + 1] = k < nw ? unpack_y(p) : 0;
                 }
             if (bush_mask) for (int w = 0; w < 4; ++w) bush_mask[4 * i + w] = bush[4 * i + w];
-            if (n_log) n_log[i] = nl[i];
+            if (n_log) n_log[i] = nl[i] & 0xFF;
             if (log_xyc)
                 for (int k = 0; k < lc; ++k) {
                     const uint32_t c = lcell[(size_t)k * n + i];
-                    const bool live = k < (int)nl[i];
+                    const bool live = k < (int)(nl[i] & 0xFF);
                     log_xyc[(i * lc + k) * 3] = live ? unpack_x(c) : 0;
                     log_xyc[(i * lc + k) * 3 + 1] = live ? unpack_y(c) : 0;
                     log_xyc[(i * lc + k) * 3 + 2] = live ? (int32_t)lcnt[(size_t)k * n + i] : 0;
