@@ -258,16 +258,17 @@ def run_ours(args):
     host_actions = actions[:min(K, 2048)].cpu().pin_memory()
     Ke = host_actions.shape[0]
     env.reset_host(hb)
+    acts_np, hnp = host_actions.numpy(), hb["np"]     # numpy views of the pinned buffers: no per-step torch dispatch
     for t in range(min(W, Ke)):
-        hb["actions"].copy_(host_actions[t])
+        hnp["actions"][:] = acts_np[t]
         env.step_host(hb)
     barrier()
     t0 = time.perf_counter()
     acc = 0.0
     for t in range(Ke):
-        hb["actions"].copy_(host_actions[t])
+        hnp["actions"][:] = acts_np[t]           # this step's inputs, host memory
         env.step_host(hb)
-        acc += float(hb["reward"][0])          # the step's result is read on the host
+        acc += float(hnp["reward"][0])           # the step's result is read on the host
     torch.cuda.synchronize(dev)
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
     h2d = n

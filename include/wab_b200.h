@@ -133,7 +133,9 @@ int wab_vec_step_host(WabVec *h, const uint8_t *h_actions, uint8_t *h_grids, uin
                       uint8_t *h_info, void *stream);
 /* Same step with ONE contiguous host block for every output (one device-to-host transfer instead of
  * seven): wab_vec_host_block_layout gives the byte offsets of grids, food, role, status, reward,
- * done, info inside the block (each 256-byte aligned) and its total size. */
+ * done, info inside the block (each 256-byte aligned) and its total size. With PINNED buffers and a batch
+ * of at most 16,384 envs the kernel reads the actions from, and writes the block into, host memory directly
+ * (no staging copy); either way the block is complete when the call returns. */
 int wab_vec_host_block_layout(const WabVec *h, int64_t *offsets7, int64_t *total_bytes);
 int wab_vec_step_host_packed(WabVec *h, const uint8_t *h_actions, uint8_t *h_block, void *stream);
 int wab_vec_reset_host(WabVec *h, uint8_t *h_grids, uint8_t *h_food, uint8_t *h_role, uint8_t *h_status,

@@ -227,7 +227,11 @@ def test_full_size_checksum_against_oracle():
     env.close()
 
 
-def test_host_buffer_path_and_masked_reset():
+@pytest.mark.parametrize("mapped", ["0", "1", "2"])
+def test_host_buffer_path_and_masked_reset(mapped, monkeypatch):
+    """Host entry points: staged copies (0), the kernel writing the pinned block directly (1), the same with the
+    thread-per-env kernel (2, the default for small batches) — all equal to the device path."""
+    monkeypatch.setenv("WAB_HOST_MAPPED", mapped)
     n = 300
     a, b = _vec(n, seed=9), _vec(n, seed=9)
     hb = a.alloc_host_buffers(pinned=True)
@@ -243,7 +247,7 @@ def test_host_buffer_path_and_masked_reset():
         assert np.array_equal(hb["grids"].numpy(), o.grids.cpu().numpy()) and np.array_equal(hb["reward"].numpy(), r.cpu().numpy())
         assert np.array_equal(hb["done"].numpy().astype(bool), d.cpu().numpy()) and np.array_equal(hb["food"].numpy(), o.food.cpu().numpy())
     # the seven-pointer entry point (no packed block) gives the same answers
-    loose = {k: v.clone() for k, v in hb.items() if k != "block"}
+    loose = {k: v.clone() for k, v in hb.items() if isinstance(v, torch.Tensor) and k != "block"}
     acts = rng.integers(0, 5, n).astype(np.uint8)
     loose["actions"].copy_(torch.from_numpy(acts))
     a.step_host(loose)

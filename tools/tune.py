@@ -27,6 +27,9 @@ VARIANTS = {
     "spawn2": ["-DWAB_SPAWN_UNROLL=2"],
     "spawn3": ["-DWAB_SPAWN_UNROLL=3"],
     "slide2": ["-DWAB_SLIDE_UNROLL=2"],
+    "slide6": ["-DWAB_SLIDE_UNROLL=6"],
+    "slide2mb5": ["-DWAB_SLIDE_UNROLL=2", "-DWAB_MIN_BLOCKS_LPE1=5"],
+    "slide3mb5": ["-DWAB_SLIDE_UNROLL=3", "-DWAB_MIN_BLOCKS_LPE1=5"],
     "s2s2": ["-DWAB_SLIDE_UNROLL=2", "-DWAB_SPAWN_UNROLL=2"],
     "s3s3": ["-DWAB_SLIDE_UNROLL=3", "-DWAB_SPAWN_UNROLL=3"],
     "s2s2mb5": ["-DWAB_SLIDE_UNROLL=2", "-DWAB_SPAWN_UNROLL=2", "-DWAB_MIN_BLOCKS_LPE1=5"],

@@ -28,7 +28,7 @@
 #endif
 
 #ifndef WAB_SLIDE_UNROLL
-#define WAB_SLIDE_UNROLL 1
+#define WAB_SLIDE_UNROLL 2
 #endif
 #ifndef WAB_SPAWN_UNROLL
 #define WAB_SPAWN_UNROLL 1

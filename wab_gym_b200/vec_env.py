@@ -35,6 +35,9 @@ class ObsBatch(NamedTuple):
     status: torch.Tensor
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)   # the current stream's handle without a Stream object
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
@@ -44,12 +47,14 @@ class VecEnv:
                  env_id_base: int = 0, auto_reset: bool = True, wolf_cap: int = 8, log_cap: Optional[int] = None,
                  force_f64_food: bool = False, features: bool = False):
         self._h = None
+        self._bound = None     # feature buffer currently bound in the handle
         self.lib = _lib.load()  # raises if the CUDA library is unavailable — no fallback
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise ValueError("VecEnv runs on CUDA devices only (got %r)" % (device,))
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
+        self._dev_index = self.device.index
         self.num_envs = int(num_envs)
         self.game = game_options if isinstance(game_options, GameConfig) else GameConfig.from_options(
             game_options, auto_reset=auto_reset, force_f64_food=force_f64_food, wolf_cap=wolf_cap, log_cap=log_cap)
@@ -90,7 +95,9 @@ class VecEnv:
 
     def _bind(self, buf):
         """Point the fused PragmaticObsWrapper feature output at this call's buffer (or switch it off)."""
-        _lib.check(self.lib.wab_vec_bind_features(self._h, _ptr(buf.get("features"))))
+        f = buf.get("features")
+        self._bound = f
+        _lib.check(self.lib.wab_vec_bind_features(self._h, _ptr(f)))
 
     def _info(self, buf):
         info = {"info": buf["info"]}
@@ -99,6 +106,8 @@ class VecEnv:
         return info
 
     def _stream(self):
+        if _raw_stream is not None:
+            return ctypes.c_void_p(_raw_stream(self._dev_index))
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _actions_u8(self, actions: torch.Tensor, shape) -> torch.Tensor:
@@ -186,15 +195,24 @@ class VecEnv:
         _lib.check(self.lib.wab_vec_host_block_layout(self._h, offs.ctypes.data, ctypes.addressof(total)))
         block = torch.empty(total.value, dtype=torch.uint8, pin_memory=pinned)
         view = lambda k, nbytes: block[int(offs[k]):int(offs[k]) + nbytes]
-        return {"actions": torch.empty(n, dtype=torch.uint8, pin_memory=pinned), "block": block,
-                "grids": view(0, n * 363).view(n, 3, 11, 11), "food": view(1, n), "role": view(2, n), "status": view(3, n),
-                "reward": view(4, 4 * n).view(torch.float32), "done": view(5, n), "info": view(6, n)}
+        hb = {"actions": torch.empty(n, dtype=torch.uint8, pin_memory=pinned), "block": block,
+              "grids": view(0, n * 363).view(n, 3, 11, 11), "food": view(1, n), "role": view(2, n), "status": view(3, n),
+              "reward": view(4, 4 * n).view(torch.float32), "done": view(5, n), "info": view(6, n)}
+        # numpy views of the same memory (cheap per-step access from Python) and the two pointers a step passes
+        hb["np"] = {k: v.numpy() for k, v in hb.items() if k != "block"}
+        hb["_c"] = (_ptr(hb["actions"]), _ptr(block))
+        return hb
 
     def step_host(self, hb: dict):
         """One step with HOST buffers (``hb`` from ``alloc_host_buffers``; ``hb['actions']`` filled by the
         caller): H2D actions, kernel, D2H of every output, stream sync — the whole C-ABI host path."""
-        self._bind({})
-        if "block" in hb:
+        if self._bound is not None:
+            self._bind({})
+        if "_c" in hb:
+            rc = self.lib.wab_vec_step_host_packed(self._h, hb["_c"][0], hb["_c"][1], self._stream())
+            if rc:
+                _lib.check(rc)
+        elif "block" in hb:
             _lib.check(self.lib.wab_vec_step_host_packed(self._h, _ptr(hb["actions"]), _ptr(hb["block"]), self._stream()))
         else:
             _lib.check(self.lib.wab_vec_step_host(self._h, _ptr(hb["actions"]), _ptr(hb["grids"]), _ptr(hb["food"]),
