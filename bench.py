@@ -275,7 +275,10 @@ def run_ours(args):
     d2h = n * (363 + 1 + 1 + 1 + 4 + 1 + 1)
     e2e = {"value": world * n * Ke / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "steps": Ke, "ms_per_step": e2e_ms / Ke,
-           "path": "wab_vec_step_host_packed: pinned host actions -> H2D -> wab_step_kernel -> one D2H of grids/food/role/status/reward/done/info into a pinned block -> stream sync"}
+           "path": ("wab_vec_step_host_packed, <= 16,384 envs: wab_step_kernel reads the pinned host actions and streams grids/food/"
+                    "role/status/reward/done/info straight into the pinned host block over PCIe -> stream sync" if n <= 16384 else
+                    "wab_vec_step_host_packed: pinned host actions -> H2D -> wab_step_kernel -> one D2H of grids/food/role/status/"
+                    "reward/done/info into a pinned block -> stream sync")}
 
     return finish(args, env, world, rank, n, K, W, T, fused_ms, kernel_ms, launches, clocks, percall, e2e, stats_all, dist)
 
