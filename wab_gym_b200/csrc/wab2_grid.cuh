@@ -109,19 +109,25 @@ __global__ void __launch_bounds__(128) wab2_grid_turn_kernel(const __grid_consta
             const int ax = (int)(atab & 0xFFu), ay = (int)((atab >> 8) & 0xFFu);
             const int rsel = at == T_WOLF ? 2 : (((atab >> 17) & 1u) ? 1 : 0);
             const int r = rsel == 2 ? P.wolf_r : (rsel == 1 ? P.gatherer_r : P.lookout_r);
-            const int sy = ((ay - R) % H + H) % H;
+            // no division anywhere below: 0 <= ax < W, 0 <= ay < H and R < W, H, so one conditional add wraps
+            const int sy = ay - R + (ay < R ? H : 0);
+            const uint64_t smask = (1ull << S) - 1ull;
+#pragma unroll 1
             for (int p = lane; p < 3 * S; p += 32) {
-                const int type_p = p / S, dxi = p - type_p * S, dx = dxi - R, adx = dx < 0 ? -dx : dx;
+                const int type_p = (p >= S ? 1 : 0) + (p >= 2 * S ? 1 : 0), dxi = p - type_p * S, dx = dxi - R;
+                const int adx = dx < 0 ? -dx : dx;
                 if (adx > r) continue;
-                const int x = ((ax + dx) % W + W) % W;
-                const uint32_t* c = cols + ((type_p * W + x) << 1);
-                uint64_t bits = rot_window((uint64_t)c[0] | ((uint64_t)c[1] << 32), sy, H) & ((1ull << S) - 1ull);
+                int x = ax + dx;
+                x += x < 0 ? W : 0;
+                x -= x >= W ? W : 0;
+                const uint2 cw = *reinterpret_cast<const uint2*>(cols + ((type_p * W + x) << 1));
+                uint64_t bits = rot_window((uint64_t)cw.x | ((uint64_t)cw.y << 32), sy, H) & smask;
                 const int m = (int)P.halfwidth[rsel][adx];           // |dy| <= m  <=>  dx^2 + dy^2 <= r^2
-                bits &= ((1ull << (2 * m + 1)) - 1ull) << (R - m);
+                bits &= ((2ull << (2 * m)) - 1ull) << (R - m);
                 if (dx == r && ax + r == W) bits = 0;                // World.py:264 strict test: this image is missed
                 if (dx == 0 && ay + r == H) bits &= ~(1ull << (R + r));   // World.py:285, same on the y axis
                 if (bits) {
-                    const int pos = off + (type_p * S + dxi) * S;
+                    const int pos = off + p * S;
                     const uint64_t sh = bits << (pos & 31);
                     atomicOr(stream + (pos >> 5), (uint32_t)sh);
                     if (sh >> 32) atomicOr(stream + (pos >> 5) + 1, (uint32_t)(sh >> 32));
@@ -145,7 +151,15 @@ __global__ void __launch_bounds__(128) wab2_grid_turn_kernel(const __grid_consta
             if (action == 0u) y += 1; else if (action == 1u) x += 1; else if (action == 2u) y -= 1; else if (action == 3u) x -= 1;
             else if (at == T_OSTRICH && action == 4u) role = 0u; else if (at == T_OSTRICH && action == 5u) role = 1u;
         }
-        const uint32_t tx = (uint32_t)pymod(x, W), ty = (uint32_t)pymod(y, H);
+        uint32_t tx, ty;
+        if (turn == 0u) {          // tables may be stale after reset_world: the full wrap of the object coordinates
+            tx = (uint32_t)pymod(x, W); ty = (uint32_t)pymod(y, H);
+        } else {                   // afterwards the table follows the object one cell at a time
+            int nx = (int)(atab & 0xFFu) + (x - unpack_x(obj[a])), ny = (int)((atab >> 8) & 0xFFu) + (y - unpack_y(obj[a]));
+            nx += nx < 0 ? W : 0; nx -= nx >= W ? W : 0;
+            ny += ny < 0 ? H : 0; ny -= ny >= H ? H : 0;
+            tx = (uint32_t)nx; ty = (uint32_t)ny;
+        }
         const uint32_t old_cell = atab & 0xFFFFu, new_cell = tx | (ty << 8);
         const uint32_t vis = (atab >> 16) & 1u;
         atab = tab_pack(tx, ty, vis, role, (atab >> 18) & 3u);
