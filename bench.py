@@ -143,14 +143,19 @@ def run_reference(args):
         return
     budget_env_steps = 2.0e8
     n_envs = args.num_envs
-    steps = args.steps
-    if n_envs * (steps + args.warmup) > budget_env_steps:
-        steps = max(1, int(budget_env_steps / n_envs) - args.warmup)
-    res = cpu_reference_run(n_envs, steps, args.warmup, args.seed)
-    sample = "%d envs x %d lockstep steps (reset on done), actions uniform 0-4, obs materialised every step" % (n_envs, res["steps"])
+    # A timed run of only a few lockstep steps would mostly measure creating and resetting the envs and waking the
+    # OpenMP threads, i.e. understate the CPU arm: time at least 512 lockstep steps after at least 16 warm-up steps.
+    steps = max(args.steps, 512)
+    warmup = max(args.warmup, 16)
+    if n_envs * (steps + warmup) > budget_env_steps:
+        steps = max(1, int(budget_env_steps / n_envs) - warmup)
+    res = cpu_reference_run(n_envs, steps, warmup, args.seed)
+    sample = "%d envs x %d lockstep steps (reset on done) after %d warm-up steps, actions uniform 0-4, obs materialised every step" % (
+        n_envs, res["steps"], warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": "env-steps/s", "n_gpus": args.gpus,
-        "steps": res["steps"], "warmup": args.warmup, "ms_per_step": 1e3 * res["seconds"] / res["steps"],
+        "steps": args.steps, "warmup": args.warmup, "timed_lockstep_steps": res["steps"],
+        "ms_per_step": 1e3 * res["seconds"] / res["steps"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 food / integer rules (CPU)",
         "data": "synthetic", "config": {"workload": WORKLOAD, "num_envs_per_gpu": n_envs},
         "cpu_baseline": {"value": res["value"], "unit": "env-steps/s", "cores": res["cores"], "kind": "port", "sample": sample},
