@@ -326,6 +326,11 @@ def finish(args, env, world, rank, n, K, W, T, fused_ms, kernel_ms, launches, cl
             line["cpu_baseline"] = {"value": cb["value"], "unit": "env-steps/s", "cores": cb["cores"], "kind": "port",
                                     "sample": "%d envs x %d lockstep steps, %.1f s of %d-thread CPU work" % (
                                         cb["n_envs"], cb["steps"], cb["seconds"], cb["cores"])}
+            one = cpu_reference_run(n, 10 ** 9, 4, args.seed, threads=1, budget_s=min(3.0, args.cpu_seconds))
+            line["cpu_baseline"]["single_thread"] = {"value": one["value"], "unit": "env-steps/s", "cores": 1,
+                                                     "sample": "%d envs x %d lockstep steps, %.1f s" % (one["n_envs"], one["steps"], one["seconds"])}
+            line["cpu_baseline"]["pandas_reference"] = ("the pandas reference itself, timed in the build container: 16.6 steps/s "
+                                                        "single process, 125 steps/s over 8 cores (profiles/r1_reference_cpu_timing.json)")
         except Exception as exc:  # the oracle is test infrastructure; its absence must not hide the GPU numbers
             line["cpu_baseline"] = {"value": None, "unit": "env-steps/s", "cores": 0, "kind": "port", "sample": "failed: %s" % exc}
         print(json.dumps(line), flush=True)

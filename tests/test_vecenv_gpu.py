@@ -434,3 +434,46 @@ def test_batch_without_auto_reset_keeps_reporting_done(name):
         hs = o.hidden_state()
         assert st["food"][i] == hs["food"] and (st["x"][i], st["y"][i], st["status"][i]) == (hs["x"], hs["y"], hs["status"])
     env.close()
+
+
+@pytest.mark.parametrize("case", range(12))
+def test_random_option_sets_match_oracle_on_device(case):
+    """Randomised game options (tests/test_fuzz_options.random_options): 96 lockstep envs x 160 steps per case, the
+    CUDA path against one oracle env per env (observations, reward, done every step) and, over 2,048 envs x 96 steps,
+    against the oracle's batch checksum."""
+    from tests.test_fuzz_options import random_options
+    rng = np.random.default_rng(1000 + case)
+    opts = random_options(rng)
+    n, steps, seed = 96, 160, 40 + case
+    env = _vec(n, opts, seed=seed, wolf_cap=15, force_f64_food=bool(case & 1))
+    oracles = [OracleEnv(opts, seed=seed, env_id=i) for i in range(n)]
+    obs = env.reset()
+    cur = [o.reset() for o in oracles]
+    for t in range(steps):
+        g, f, r, s = (x.cpu().numpy() for x in obs)
+        for i in range(n):
+            assert np.array_equal(g[i], cur[i][0]) and (int(f[i]), int(r[i]), int(s[i])) == cur[i][1:], (case, t, i, opts)
+        acts = rng.integers(0, env.n_actions, n).astype(np.uint8)
+        obs, reward, done, _ = env.step(torch.from_numpy(acts).cuda())
+        reward, done = reward.cpu().numpy(), done.cpu().numpy()
+        for i, o in enumerate(oracles):
+            cur[i], rr, d = o.step(int(acts[i]))
+            assert np.float32(rr) == reward[i] and d == bool(done[i]), (case, t, i, opts)
+            if d:
+                cur[i] = o.reset()
+    assert env.stats()["overflows"] == 0
+    env.close()
+    # batch checksum at a larger size (thread-per-env and lanes-per-env kernels alike)
+    n2, steps2 = 2048, 96
+    big = _vec(n2, opts, seed=seed, wolf_cap=15)
+    acts = torch.randint(0, big.n_actions, (steps2, n2), dtype=torch.uint8, device="cuda",
+                         generator=torch.Generator("cuda").manual_seed(case))
+    big.reset()
+    o, r, d, _ = big.step_many(acts)
+    w = torch.arange(1, 364, device="cuda", dtype=torch.int64)
+    cs = (o.grids.view(steps2, n2, 363).long() * w).sum() + 1000 * o.food.long().sum() + 100000 * o.role.long().sum() \
+        + 200000 * o.status.long().sum() + 400000 * d.long().sum()
+    n_steps, want = wab_oracle.run(opts, seed, n2, steps2, acts.cpu().numpy())
+    if big.stats()["overflows"] == 0:                    # a full wolf table is counted, not silently wrong
+        assert n_steps == n2 * steps2 and int(cs.item()) == want, (case, opts)
+    big.close()
