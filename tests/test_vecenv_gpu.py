@@ -150,6 +150,19 @@ def test_lanes_per_env_variants_agree_on_a_full_batch(monkeypatch):
                 assert torch.equal(x, y), lpe
             assert ref[-1] == got[-1]
         env.close()
+    # the thread-per-env kernel built for 7 and 8 resident CTAs per SM (tighter register caps, picked for batches of
+    # just over one wave) gives the same answers
+    monkeypatch.setenv("WAB_LPE", "1")
+    for mb in (7, 8):
+        monkeypatch.setenv("WAB_MB", str(mb))
+        env = _vec(n, seed=12)
+        env.reset()
+        o, r, d, i = env.step_many(acts)
+        for x, y in zip(ref[:-1], (o.grids, o.food, o.role, o.status, r, d, i["info"])):
+            assert torch.equal(x, y), mb
+        assert ref[-1] == env.stats()
+        env.close()
+    monkeypatch.delenv("WAB_MB")
     monkeypatch.delenv("WAB_LPE")
     auto = _vec(n, seed=12)
     assert auto.lanes_per_env in (4, 8, 16)         # a 4096-env batch is spread over several lanes per env

@@ -20,6 +20,7 @@ VARIANTS = {
     "base": [],
     "mb5": ["-DWAB_MIN_BLOCKS_LPE1=5"],
     "mb8": ["-DWAB_MIN_BLOCKS_LPE1=8"],
+    "mb7": ["-DWAB_MIN_BLOCKS_LPE1=7"],
     "slide1": ["-DWAB_SLIDE_UNROLL=1"],
     "slide3": ["-DWAB_SLIDE_UNROLL=3"],
     "spawn1": ["-DWAB_SPAWN_UNROLL=1"],

@@ -285,8 +285,10 @@ __device__ __forceinline__ void emit_obs(uint32_t* stream, const uint2* lut, con
 }
 
 // T lockstep steps of every env; observation, reward, done and info are written for every step.
-template <bool F64, int LPE>
-__global__ void __launch_bounds__(Geo<LPE>::THREADS, Geo<LPE>::MIN_BLOCKS)
+// MB = resident CTAs per SM the register budget is capped for (the thread-per-env kernel also exists for 7 and 8,
+// picked at create when that makes a batch fit in ONE wave: 131,072 envs are 1.15 waves of 6 CTAs per SM).
+template <bool F64, int LPE, int MB = Geo<LPE>::MIN_BLOCKS>
+__global__ void __launch_bounds__(Geo<LPE>::THREADS, MB)
 wab_step_kernel(const __grid_constant__ Params P, const StatePtrs st, const uint8_t* __restrict__ actions,
                 const int n_steps, const OutPtrs out) {
     extern __shared__ uint32_t smem[];
@@ -500,6 +502,7 @@ struct WabVec {
     uint8_t* stage;
     size_t stage_bytes;
     int lpe;          // lanes per env chosen at create (see pick_lpe)
+    int mb;           // CTAs per SM the thread-per-env kernel is built for (see pick_mb)
     uint8_t* d_features;   // bound feature output, or null
     // host-buffer step as one CUDA graph (H2D actions -> step kernel -> D2H block), rebuilt when the pointers change
     cudaStream_t host_stream;
@@ -528,7 +531,12 @@ int check_ptr_align(const void* p, const char* name) {
 template <bool F64, int LPE>
 void launch_step_t(const WabVec* h, const uint8_t* a, int T, const OutPtrs& out, cudaStream_t s) {
     const unsigned grid = (unsigned)((h->n + Geo<LPE>::EPB - 1) / Geo<LPE>::EPB);
-    wab_step_kernel<F64, LPE><<<grid, Geo<LPE>::THREADS, smem_bytes_for<LPE>(h->P), s>>>(h->P, h->st, a, T, out);
+    if (LPE == 1 && h->mb == 7)
+        wab_step_kernel<F64, LPE, LPE == 1 ? 7 : Geo<LPE>::MIN_BLOCKS><<<grid, Geo<LPE>::THREADS, smem_bytes_for<LPE>(h->P), s>>>(h->P, h->st, a, T, out);
+    else if (LPE == 1 && h->mb == 8)
+        wab_step_kernel<F64, LPE, LPE == 1 ? 8 : Geo<LPE>::MIN_BLOCKS><<<grid, Geo<LPE>::THREADS, smem_bytes_for<LPE>(h->P), s>>>(h->P, h->st, a, T, out);
+    else
+        wab_step_kernel<F64, LPE><<<grid, Geo<LPE>::THREADS, smem_bytes_for<LPE>(h->P), s>>>(h->P, h->st, a, T, out);
 }
 template <bool F64, int LPE>
 void launch_reset_t(const WabVec* h, const uint8_t* mask, const OutPtrs& out, cudaStream_t s) {
@@ -562,6 +570,22 @@ int pick_lpe(const WabVec* h) {
     if (n * 8 <= 65536 && fits_one_wave<8>(h, n_sm)) return 8;
     if (n * 4 <= 65536 && fits_one_wave<4>(h, n_sm)) return 4;
     return 1;
+}
+
+// Thread-per-env batches of a little more than one wave of 6 CTAs per SM (113,664 envs on 148 SMs) run as ONE wave
+// of 7 or 8 CTAs per SM with a tighter register cap: measured at 131,072 envs 1.05e10 (7) / 1.03e10 (8) against
+// 0.94e10 env-steps/s (6); with two or more waves the cap only costs (profiles/r1f_wave_quantization.txt).
+int pick_mb(const WabVec* h) {
+    if (const char* e = getenv("WAB_MB")) {
+        const int v = atoi(e);
+        if (v >= 6 && v <= 8) return v;
+    }
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device);
+    const int64_t grid = (h->n + Geo<1>::EPB - 1) / Geo<1>::EPB;
+    for (int mb = WAB_MIN_BLOCKS_LPE1; mb <= 8; ++mb)
+        if (grid <= (int64_t)mb * n_sm) return mb;
+    return WAB_MIN_BLOCKS_LPE1;
 }
 
 #define WAB_DISPATCH(FN, ...) WAB_DISPATCH_LPE(h->lpe, FN, __VA_ARGS__)
@@ -670,6 +694,7 @@ int wab_vec_create(const WabConfig* cfg, const uint32_t* bush_thr, int32_t n_bus
     st.wolves = (uint32_t*)(base + o_wolves); st.logcell = (uint32_t*)(base + o_lcell); st.logcnt = base + o_lcnt;
     st.stats = (unsigned long long*)(base + o_stats); st.n = n_envs;
     h->lpe = pick_lpe(h);
+    h->mb = pick_mb(h);
     *out = h;
     return WAB_OK;
 }
