@@ -109,6 +109,17 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+_REAL_STDOUT = []     # fd of the process's real stdout once C-level stdout has been pointed at stderr
+
+
+def emit(text):
+    if _REAL_STDOUT:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT[0], (text + "\n").encode())
+    else:
+        print(text, flush=True)
+
+
 def cpu_reference_run(n_envs, steps, warmup, seed, threads=0, budget_s=None):
     """The oracle's C restatement of the reference step on the host cores (the reference itself is pure
     Python on pandas, ~14-18 steps/s per core in the build container, and cannot travel to this box)."""
@@ -181,8 +192,13 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
+        # keep stdout to the one JSON line: NCCL prints its version banner on fd 1 (NCCL_DEBUG=VERSION may come from
+        # the environment or from a conf file), so C-level stdout goes to stderr and the line is written to the real one
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        sys.stdout.flush()
+        _REAL_STDOUT.append(os.dup(1))
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
     n, K, W, T = args.num_envs, args.steps, max(args.warmup, 3), max(1, min(args.fuse, args.steps))
@@ -333,7 +349,7 @@ def finish(args, env, world, rank, n, K, W, T, fused_ms, kernel_ms, launches, cl
                                                         "single process, 125 steps/s over 8 cores (profiles/r1_reference_cpu_timing.json)")
         except Exception as exc:  # the oracle is test infrastructure; its absence must not hide the GPU numbers
             line["cpu_baseline"] = {"value": None, "unit": "env-steps/s", "cores": 0, "kind": "port", "sample": "failed: %s" % exc}
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
