@@ -21,6 +21,9 @@ VARIANTS = {
     "mb5": ["-DWAB_MIN_BLOCKS_LPE1=5"],
     "mb8": ["-DWAB_MIN_BLOCKS_LPE1=8"],
     "mb7": ["-DWAB_MIN_BLOCKS_LPE1=7"],
+    "cta64": ["-DWAB_THREADS_LPE1=64"],
+    "cta32": ["-DWAB_THREADS_LPE1=32"],
+    "cta256": ["-DWAB_THREADS_LPE1=256"],
     "slide1": ["-DWAB_SLIDE_UNROLL=1"],
     "slide3": ["-DWAB_SLIDE_UNROLL=3"],
     "spawn1": ["-DWAB_SPAWN_UNROLL=1"],

@@ -42,9 +42,15 @@ constexpr int kFlushUnroll = WAB_FLUSH_UNROLL;
 #ifndef WAB_MIN_BLOCKS_LPEN
 #define WAB_MIN_BLOCKS_LPEN 1         // lanes-per-env kernels: no register cap (one wave of few CTAs anyway)
 #endif
-#ifndef WAB_MIN_BLOCKS_LPE1
-#define WAB_MIN_BLOCKS_LPE1 6         // thread-per-env kernel: cap registers at 80 so 6 CTAs (24 warps) fit an SM
+#ifndef WAB_THREADS_LPE1
+#define WAB_THREADS_LPE1 32           // thread-per-env kernel: one warp per CTA (no intra-CTA imbalance over a T-step launch:
+                                      // 1.32e10 vs 1.29e10 env-steps/s at 1M envs with 128-thread CTAs, profiles/r1f_wave_quantization.txt)
 #endif
+#ifndef WAB_MIN_BLOCKS_LPE1
+#define WAB_MIN_BLOCKS_LPE1 (768 / WAB_THREADS_LPE1)   // cap registers at 80 so 24 warps (6 CTAs of 128) fit an SM
+#endif
+// h->mb counts resident CTAs per SM in units of 128 threads (6, 7, 8 = 24, 28, 32 warps)
+constexpr int kMbScale = 128 / WAB_THREADS_LPE1;
 
 struct StatePtrs {
     uint32_t* pos;       // [N]  x:i16 | y:i16 << 16
@@ -237,7 +243,7 @@ __device__ __forceinline__ void build_lut(uint2* lut) {
 // Geometry: a warp owns EPW = 32 / LPE envs. Thread-per-env uses 128-thread CTAs; the lanes-per-env variants
 // serve small batches where the grid is about one wave, so they use 64-thread CTAs to spread evenly over 148 SMs.
 template <int LPE> struct Geo {
-    static constexpr int THREADS = LPE == 1 ? 128 : WAB_THREADS_LPEN;
+    static constexpr int THREADS = LPE == 1 ? WAB_THREADS_LPE1 : WAB_THREADS_LPEN;
     static constexpr int EPW = 32 / LPE;
     static constexpr int EPB = THREADS / LPE;
     static constexpr int STREAM = ((THREADS / 32) * WarpStream<EPW>::WORDS + 1) & ~1;   // even: keeps the LUT 8-byte aligned
@@ -532,9 +538,9 @@ template <bool F64, int LPE>
 void launch_step_t(const WabVec* h, const uint8_t* a, int T, const OutPtrs& out, cudaStream_t s) {
     const unsigned grid = (unsigned)((h->n + Geo<LPE>::EPB - 1) / Geo<LPE>::EPB);
     if (LPE == 1 && h->mb == 7)
-        wab_step_kernel<F64, LPE, LPE == 1 ? 7 : Geo<LPE>::MIN_BLOCKS><<<grid, Geo<LPE>::THREADS, smem_bytes_for<LPE>(h->P), s>>>(h->P, h->st, a, T, out);
+        wab_step_kernel<F64, LPE, LPE == 1 ? 7 * kMbScale : Geo<LPE>::MIN_BLOCKS><<<grid, Geo<LPE>::THREADS, smem_bytes_for<LPE>(h->P), s>>>(h->P, h->st, a, T, out);
     else if (LPE == 1 && h->mb == 8)
-        wab_step_kernel<F64, LPE, LPE == 1 ? 8 : Geo<LPE>::MIN_BLOCKS><<<grid, Geo<LPE>::THREADS, smem_bytes_for<LPE>(h->P), s>>>(h->P, h->st, a, T, out);
+        wab_step_kernel<F64, LPE, LPE == 1 ? 8 * kMbScale : Geo<LPE>::MIN_BLOCKS><<<grid, Geo<LPE>::THREADS, smem_bytes_for<LPE>(h->P), s>>>(h->P, h->st, a, T, out);
     else
         wab_step_kernel<F64, LPE><<<grid, Geo<LPE>::THREADS, smem_bytes_for<LPE>(h->P), s>>>(h->P, h->st, a, T, out);
 }
@@ -583,9 +589,9 @@ int pick_mb(const WabVec* h) {
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device);
     const int64_t grid = (h->n + Geo<1>::EPB - 1) / Geo<1>::EPB;
-    for (int mb = WAB_MIN_BLOCKS_LPE1; mb <= 8; ++mb)
-        if (grid <= (int64_t)mb * n_sm) return mb;
-    return WAB_MIN_BLOCKS_LPE1;
+    for (int mb = 6; mb <= 8; ++mb)
+        if (grid <= (int64_t)mb * kMbScale * n_sm) return mb;
+    return 6;
 }
 
 #define WAB_DISPATCH(FN, ...) WAB_DISPATCH_LPE(h->lpe, FN, __VA_ARGS__)
