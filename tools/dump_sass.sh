@@ -10,7 +10,7 @@ tag = sys.argv[1]
 txt = open('/tmp/wab_all.sass').read()
 for f in re.split(r'\n\s*Function : ', txt)[1:]:
     name = f.split('\n', 1)[0]
-    for key, out in (('wab_step_kernelILb0ELi1E', 'step_lpe1'), ('wab_step_kernelILb0ELi16E', 'step_lpe16'), ('wab2_turn_kernel', 'v2_turn')):
+    for key, out in (('wab_step_kernelILb0ELi1ELi24E', 'step_lpe1'), ('wab_step_kernelILb0ELi16E', 'step_lpe16'), ('wab2_turn_kernel', 'v2_turn')):
         if key in name:
             body = 'Function : ' + f
             n = len(re.findall(r'^\s+/\*[0-9a-f]{4,5}\*/', body, flags=re.M))
