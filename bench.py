@@ -225,6 +225,8 @@ def run_ours(args):
     chunks = [(s, min(T, K - s)) for s in range(0, K, T)]
     for s in range(0, W, T):
         env.step_many(actions[K + s:K + min(W, s + T)], out={k: v[:min(T, W - s)] for k, v in out.items()})
+    if world > 1:
+        reduce_stats(env.stats_tensor())      # warm-up of the one collective too (NCCL sets its channels up on first use)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in chunks]
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
