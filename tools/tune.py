@@ -49,6 +49,8 @@ VARIANTS = {
     "lpen5": ["-DWAB_MIN_BLOCKS_LPEN=5"],
     "lpen6": ["-DWAB_MIN_BLOCKS_LPEN=6"],
     "lpen8": ["-DWAB_MIN_BLOCKS_LPEN=8"],
+    "lpen12": ["-DWAB_MIN_BLOCKS_LPEN=12"],
+    "lpen14": ["-DWAB_MIN_BLOCKS_LPEN=14"],
     "s1s1": ["-DWAB_SLIDE_UNROLL=1", "-DWAB_SPAWN_UNROLL=1"],
     "s1s1mb8": ["-DWAB_SLIDE_UNROLL=1", "-DWAB_SPAWN_UNROLL=1", "-DWAB_MIN_BLOCKS_LPE1=8"],
 }

@@ -104,7 +104,8 @@ __global__ void __launch_bounds__(128) wab2_grid_turn_kernel(const __grid_consta
         if (acting && out.planes) {                                  // get_observations(a), World.py:360-377
             const int64_t first_byte = o * obs_bytes;
             const int off = (int)(first_byte & 15);
-            for (int k = lane; k < stream_words; k += 32) stream[k] = 0u;
+#pragma unroll 1
+            for (int k = lane; k < stream_words; k += 32) stream[k] = 0u;     // rolled: the unrolled form cost ~70 instructions
             __syncwarp();
             const int ax = (int)(atab & 0xFFu), ay = (int)((atab >> 8) & 0xFFu);
             const int rsel = at == T_WOLF ? 2 : (((atab >> 17) & 1u) ? 1 : 0);
@@ -113,24 +114,26 @@ __global__ void __launch_bounds__(128) wab2_grid_turn_kernel(const __grid_consta
             const int sy = ay - R + (ay < R ? H : 0);
             const uint64_t smask = (1ull << S) - 1ull;
 #pragma unroll 1
-            for (int p = lane; p < 3 * S; p += 32) {
-                const int type_p = (p >= S ? 1 : 0) + (p >= 2 * S ? 1 : 0), dxi = p - type_p * S, dx = dxi - R;
-                const int adx = dx < 0 ? -dx : dx;
+            for (int dxi = lane; dxi < S; dxi += 32) {               // one lane per column offset: the three type
+                const int dx = dxi - R, adx = dx < 0 ? -dx : dx;     // planes share x, rotation, circle mask and quirks
                 if (adx > r) continue;
                 int x = ax + dx;
                 x += x < 0 ? W : 0;
                 x -= x >= W ? W : 0;
-                const uint2 cw = *reinterpret_cast<const uint2*>(cols + ((type_p * W + x) << 1));
-                uint64_t bits = rot_window((uint64_t)cw.x | ((uint64_t)cw.y << 32), sy, H) & smask;
                 const int m = (int)P.halfwidth[rsel][adx];           // |dy| <= m  <=>  dx^2 + dy^2 <= r^2
-                bits &= ((2ull << (2 * m)) - 1ull) << (R - m);
-                if (dx == r && ax + r == W) bits = 0;                // World.py:264 strict test: this image is missed
-                if (dx == 0 && ay + r == H) bits &= ~(1ull << (R + r));   // World.py:285, same on the y axis
-                if (bits) {
-                    const int pos = off + p * S;
-                    const uint64_t sh = bits << (pos & 31);
-                    atomicOr(stream + (pos >> 5), (uint32_t)sh);
-                    if (sh >> 32) atomicOr(stream + (pos >> 5) + 1, (uint32_t)(sh >> 32));
+                uint64_t mask = (((2ull << (2 * m)) - 1ull) << (R - m)) & smask;
+                if (dx == r && ax + r == W) mask = 0;                // World.py:264 strict test: this image is missed
+                if (dx == 0 && ay + r == H) mask &= ~(1ull << (R + r));   // World.py:285, same on the y axis
+#pragma unroll
+                for (int type_p = 0; type_p < 3; ++type_p) {
+                    const uint2 cw = *reinterpret_cast<const uint2*>(cols + ((type_p * W + x) << 1));
+                    const uint64_t bits = rot_window((uint64_t)cw.x | ((uint64_t)cw.y << 32), sy, H) & mask;
+                    if (bits) {
+                        const int pos = off + (type_p * S + dxi) * S;
+                        const uint64_t sh = bits << (pos & 31);
+                        atomicOr(stream + (pos >> 5), (uint32_t)sh);
+                        if (sh >> 32) atomicOr(stream + (pos >> 5) + 1, (uint32_t)(sh >> 32));
+                    }
                 }
             }
             __syncwarp();
