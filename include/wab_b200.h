@@ -113,7 +113,9 @@ int wab_vec_create(const WabConfig *cfg, const uint32_t *bush_thr, int32_t n_bus
 
 /* Replaces reset() (wab_env.py:231-248). d_mask: NULL = all envs, else u8[N], nonzero = reset. Each
  * reset env starts its next episode (first reset -> episode 0). Observations are written for EVERY
- * env (unreset ones get their current state's fresh observation). */
+ * env: the others get the observation their last step returned again — including the bush under the
+ * ostrich if that step ate it empty, which the reference's observation still shows because its frame
+ * (wab_env.py:266) predates the eat (:300-313) and is only rebuilt by the next step. */
 int wab_vec_reset(WabVec *h, const uint8_t *d_mask, WabObs obs, void *stream);
 
 /* Replaces step(action) (wab_env.py:250-342) for all envs. d_actions u8[N]; outputs: obs, d_reward
