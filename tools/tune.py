@@ -21,6 +21,7 @@ VARIANTS = {
     "mb5": ["-DWAB_MIN_BLOCKS_LPE1=5"],
     "mb8": ["-DWAB_MIN_BLOCKS_LPE1=8"],
     "mb7": ["-DWAB_MIN_BLOCKS_LPE1=7"],
+    "eat_rare": ["-DWAB_EAT_RARE"],
     "cta64": ["-DWAB_THREADS_LPE1=64"],
     "cta32": ["-DWAB_THREADS_LPE1=32"],
     "cta256": ["-DWAB_THREADS_LPE1=256"],

@@ -217,6 +217,16 @@ WAB_HD_RARE uint32_t bush_word_rare(uint32_t c0, uint32_t kb, uint32_t key, uint
 WAB_HD uint32_t bush_word(const Params& P, const Env& E, int32_t x, int32_t y) {
     return bush_word_rare(pack_xy(x >> 1, y >> 1) ^ E.bk_a, E.bk_b, P.rk2[0], bush_lane(x, y));
 }
+// The same draw with both calls unrolled in line, for the eat path: rare per env (5 % of steps) but taken by some
+// lane of a 32-env warp on 82 % of its steps, where the rolled out-of-line version costs three times the instructions.
+WAB_HD uint32_t bush_word_inline(const Params& P, const Env& E, int32_t x, int32_t y) {
+    const uint32_t c0 = pack_xy(x >> 1, y >> 1) ^ E.bk_a, lane = bush_lane(x, y);
+    uint32_t p[2], q[2];
+    philox2(P, c0, E.bk_b, p);
+    philox2(P, c0, ~E.bk_b, q);
+    const uint32_t sel = half_sel(lane & 1u);
+    return (half_of((lane & 2u) ? p[1] : p[0], sel) << 16) | half_of((lane & 2u) ? q[1] : q[0], sel);
+}
 WAB_HD uint32_t cell_sig(uint32_t cell) { return 1u << ((cell * 0x9E3779B1u) >> 27); }
 // log slot of a cell, or -1. The signature answers "never eaten here" without touching memory; the
 // search runs newest-first because repeated eats hit the most recent entry.
@@ -501,7 +511,12 @@ WAB_HD void env_step(const Params& P, Env& E, const Slots& S, uint32_t action, S
         } else {
             eats = 1u; O.overflow = 1u;            // counted, never silent (WAB_STAT_OVERFLOWS)
         }
-        if (!alive_after(P, bush_word(P, E, E.x, E.y), eats)) { E.m[1] &= ~(1u << 28); E.dep = 1u; E.stale = 1u; }
+#ifdef WAB_EAT_RARE   /* tuning A/B only */
+        const uint32_t eaten_word = bush_word(P, E, E.x, E.y);
+#else
+        const uint32_t eaten_word = bush_word_inline(P, E, E.x, E.y);
+#endif
+        if (!alive_after(P, eaten_word, eats)) { E.m[1] &= ~(1u << 28); E.dep = 1u; E.stale = 1u; }
     }
 
     // ---- :316-322 hunger, starvation (overrides killed)
