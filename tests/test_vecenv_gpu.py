@@ -240,6 +240,28 @@ def test_full_size_checksum_against_oracle():
     env.close()
 
 
+def test_million_env_checksum_against_oracle():
+    """BASELINE's largest v1 batch: 1,048,576 envs x 12 lockstep steps (12.6 M env-steps, thread-per-env kernel, every
+    observation byte of every step) against the CPU oracle's checksum of the same run."""
+    n, steps, seed = 1 << 20, 12, 3
+    acts = torch.randint(0, 5, (steps, n), dtype=torch.uint8, device="cuda", generator=torch.Generator("cuda").manual_seed(8))
+    env = _vec(n, seed=seed)
+    assert env.lanes_per_env == 1
+    env.reset()
+    o, r, d, _ = env.step_many(acts)
+    w = torch.arange(1, 364, device="cuda", dtype=torch.int64)
+    cs = 0
+    for t in range(steps):                                  # per step: keeps the int64 temporaries at 3 GB
+        cs += int((o.grids[t].view(n, 363).long() * w).sum().item())
+    cs += int((1000 * o.food.long().sum() + 100000 * o.role.long().sum() + 200000 * o.status.long().sum()
+               + 400000 * d.long().sum()).item())
+    n_steps, want = wab_oracle.run(None, seed, n, steps, acts.cpu().numpy())
+    assert n_steps == n * steps and cs == want
+    st = env.stats()
+    assert st["steps"] == n * steps and st["overflows"] == 0 and st["episodes"] == int(d.sum())
+    env.close()
+
+
 @pytest.mark.parametrize("mapped", ["0", "1", "2"])
 def test_host_buffer_path_and_masked_reset(mapped, monkeypatch):
     """Host entry points: staged copies (0), the kernel writing the pinned block directly (1), the same with the
