@@ -112,6 +112,7 @@ def summary(path):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workers", type=int, default=6)
+    ap.add_argument("--worker-offset", type=int, default=0, help="first worker id (a second run appends new streams)")
     ap.add_argument("--hours", type=float, default=3.0)
     ap.add_argument("--chunk-steps", type=int, default=600)
     ap.add_argument("--out", default=os.path.join(REPO, "profiles", "r1_reference_parity_volume.jsonl"))
@@ -121,7 +122,8 @@ def main():
         return summary(args.summary)
     deadline = time.time() + args.hours * 3600
     lock = mp.Lock()
-    procs = [mp.Process(target=worker, args=(w, deadline, args.out, args.chunk_steps, lock)) for w in range(args.workers)]
+    procs = [mp.Process(target=worker, args=(args.worker_offset + w, deadline, args.out, args.chunk_steps, lock))
+             for w in range(args.workers)]
     for p in procs:
         p.start()
     for p in procs:

@@ -516,6 +516,8 @@ struct WabVec {
     const void* g_actions; void* g_block; const void* g_features;
     bool graph_unsupported;
     int host_mapped;   // -1 unknown, 0 staged copies, 1 kernel writes the pinned host block directly
+    const void* m_actions; const void* m_block;        // host buffer pair whose device aliases are cached below
+    const uint8_t* m_dactions; uint8_t* m_dblock;
 };
 
 namespace {
@@ -801,17 +803,24 @@ int wab_vec_step_host_packed(WabVec* h, const uint8_t* h_actions, uint8_t* h_blo
         h->host_mapped = e ? atoi(e) : (h->n <= 16384 ? 2 : 0);
     }
     if (h->host_mapped) {
-        cudaPointerAttributes pa, pb;
-        if (cudaPointerGetAttributes(&pa, h_actions) == cudaSuccess && cudaPointerGetAttributes(&pb, h_block) == cudaSuccess &&
-            pa.type == cudaMemoryTypeHost && pb.type == cudaMemoryTypeHost && pa.devicePointer && pb.devicePointer) {
-            uint8_t* m = (uint8_t*)pb.devicePointer - L.grids;       // block offsets are relative to L.grids
+        if (h->m_actions != h_actions || h->m_block != h_block) {      // resolve the device aliases once per buffer pair
+            cudaPointerAttributes pa, pb;
+            h->m_actions = h_actions; h->m_block = h_block; h->m_dactions = nullptr; h->m_dblock = nullptr;
+            if (cudaPointerGetAttributes(&pa, h_actions) == cudaSuccess && cudaPointerGetAttributes(&pb, h_block) == cudaSuccess &&
+                pa.type == cudaMemoryTypeHost && pb.type == cudaMemoryTypeHost && pa.devicePointer && pb.devicePointer) {
+                h->m_dactions = (const uint8_t*)pa.devicePointer; h->m_dblock = (uint8_t*)pb.devicePointer;
+            } else {
+                cudaGetLastError();                // pageable memory: staged copies below
+            }
+        }
+        if (h->m_dblock) {
+            uint8_t* m = h->m_dblock - L.grids;                        // block offsets are relative to L.grids
             WabObs mo{m + L.grids, m + L.food, m + L.role, m + L.status};
-            if (int rc = launch_step(h, 1, (const uint8_t*)pa.devicePointer, mo, (float*)(m + L.reward), m + L.done,
-                                     m + L.info, s, h->host_mapped == 2 ? 1 : 0)) return rc;
+            if (int rc = launch_step(h, 1, h->m_dactions, mo, (float*)(m + L.reward), m + L.done, m + L.info, s,
+                                     h->host_mapped == 2 ? 1 : 0)) return rc;
             WAB_CUDA(cudaStreamSynchronize(s));
             return WAB_OK;
         }
-        cudaGetLastError();                    // pageable memory: staged copies below
     }
     // Fast path: the three operations replayed as one graph launch on a private stream (saves two API round trips
     // per step; needs pinned host buffers — anything else falls back to the plain sequence below).
