@@ -179,6 +179,18 @@ int wab_pragmatic_features(const uint8_t *d_grids, const uint8_t *d_food, const 
  * one-hot vectors (449 for default options) including the role's view mask. */
 int wab_vec_flatten_features(WabVec *h, const uint8_t *d_features, int64_t n_rows, float *d_out, void *stream);
 int wab_vec_flat_dim(const WabVec *h);
+/* The policy input of actor_critic.py:188-189 in one pass: the same one-hot rows plus noise_scale * U[0,1) per element
+ * (the reference adds np.random.rand(...) / 100), written as f32 (out_bf16 = 0) or bf16 (1). The draws are keyed by
+ * the handle's seed, the element index and the 64-bit value at d_counter (device memory, may be NULL = 0), which
+ * the caller advances between calls — so a captured CUDA graph gets fresh noise on every replay. */
+int wab_vec_flatten_features_noisy(WabVec *h, const uint8_t *d_features, int64_t n_rows, void *d_out,
+                                   int32_t out_bf16, float noise_scale, const uint64_t *d_counter, void *stream);
+
+/* Categorical(probs).sample() of the reference's select_action (actor_critic.py:117-120) for n rows of n_actions <= 8
+ * probabilities (f32, or bf16 when probs_bf16 = 1), one u8 action per row, on the device: inverse CDF on one
+ * uniform per row keyed by (seed, row, *d_counter) — d_counter as in wab_vec_flatten_features_noisy. */
+int wab_sample_categorical(const void *d_probs, int32_t probs_bf16, int64_t n, int32_t n_actions, uint64_t seed,
+                           const uint64_t *d_counter, uint8_t *d_actions, void *stream);
 
 /* ---- Environment 2.0 ("/root/reference/Environment 2.0"): a toroidal W x H world of ostriches, wolves and
  * bushes per environment. One call = one world turn: every entity, in id order (ostriches, wolves, bushes),

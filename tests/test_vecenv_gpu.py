@@ -360,6 +360,18 @@ def test_fused_and_standalone_features(name):
             vm = (GATHERER_TILE_MASK if r[i] == 1 else LOOKOUT_TILE_MASK).reshape(-1).astype(np.float32)
         want.append(vm)
         assert np.array_equal(flat[i], np.concatenate(want)), (t, i)
+        if t % 40 == 0:                                   # the fused policy-input kernel: flatten + noise + cast
+            ctr = torch.full((1,), 5 + t, dtype=torch.int64, device="cuda")
+            for dt in (torch.float32, torch.bfloat16):
+                buf = torch.empty(n, env.flat_dim, dtype=dt, device="cuda")
+                assert np.array_equal(env.flatten_features_noisy(feats, buf, 0.0, ctr).float().cpu().numpy(), flat)
+            a1 = env.flatten_features_noisy(feats, torch.empty(n, env.flat_dim, device="cuda"), 0.01, ctr).cpu().numpy()
+            a2 = env.flatten_features_noisy(feats, torch.empty(n, env.flat_dim, device="cuda"), 0.01, ctr).cpu().numpy()
+            ctr += 1
+            a3 = env.flatten_features_noisy(feats, torch.empty(n, env.flat_dim, device="cuda"), 0.01, ctr).cpu().numpy()
+            noise = a1 - flat
+            assert np.array_equal(a1, a2) and not np.array_equal(a1, a3)
+            assert noise.min() >= 0.0 and noise.max() < 0.01 + 1e-6 and abs(float(noise.mean()) - 0.005) < 2e-4
         acts = np.array([pick_action(rng, g[j], env.n_actions, greedy) for j in range(n)], dtype=np.uint8)
         obs, _, _, info = env.step(torch.from_numpy(acts).cuda())
         feats = info["features"]
@@ -386,6 +398,27 @@ def test_actor_critic_rollout_runs_on_device():
     rg.run(20)
     assert env2.stats()["steps"] >= 512 * 20 and env2.stats()["bad_actions"] == 0
     env2.close()
+
+
+def test_device_categorical_sampler_follows_the_probabilities():
+    env = _vec(64, seed=1)
+    n = 1 << 20
+    p = torch.tensor([0.1, 0.2, 0.3, 0.25, 0.15], device="cuda")
+    ctr = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for dt, tol in ((torch.float32, 2e-3), (torch.bfloat16, 6e-3)):
+        probs = p.to(dt).expand(n, 5).contiguous()
+        a = env.sample_actions(probs, torch.empty(n, dtype=torch.uint8, device="cuda"), ctr, seed=7)
+        freq = torch.bincount(a.long(), minlength=5).float() / n
+        want = probs[0].float() / probs[0].float().sum()
+        assert int(a.max()) <= 4 and float((freq - want).abs().max()) < tol, (dt, freq)
+        again = env.sample_actions(probs, torch.empty(n, dtype=torch.uint8, device="cuda"), ctr, seed=7)
+        assert torch.equal(a, again)                        # keyed: same counter, same draws
+        ctr += 1
+        assert not torch.equal(a, env.sample_actions(probs, torch.empty(n, dtype=torch.uint8, device="cuda"), ctr, seed=7))
+    onehot = torch.eye(5, device="cuda")[torch.arange(n, device="cuda") % 5].contiguous()
+    a = env.sample_actions(onehot, torch.empty(n, dtype=torch.uint8, device="cuda"), ctr)
+    assert torch.equal(a.long(), torch.arange(n, device="cuda") % 5)
+    env.close()
 
 
 def test_batched_a2c_update_trains_on_device():

@@ -11,6 +11,7 @@
 //     stream 16 bits -> 16 bytes per lane and issues fully coalesced 16-byte streaming stores.
 //   * per-(env, episode, turn, cell) Philox4x32-10 counters make every draw order-free
 //     (oracle/keyed_rng.py states the contract).
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -430,36 +431,104 @@ __global__ void wab_features_kernel(const uint8_t* __restrict__ grids, const uin
 }
 
 // gym.spaces.flatten of the wrapper's observation space (wab_env.py:710-724, actor_critic.py:188):
-// one-hot of every Discrete, then the 121-cell view mask. One thread per output element.
+// one-hot of every Discrete, then the 121-cell view mask. Column k of a row whose 28 feature bytes are f.
+__device__ __forceinline__ float flat_column(const Params& P, const uint8_t* f, int k, int food_dim) {
+#pragma unroll
+    for (int species = 0; species < 2; ++species) {
+        const int base = species * 12;
+        if (k < 96) return f[base + k / 12] == k % 12 ? 1.f : 0.f;                   // nearest, second: 8 x one-hot(12)
+        if (k < 140) return f[base + 8 + (k - 96) / 11] == (k - 96) % 11 ? 1.f : 0.f;   // counts: 4 x one-hot(11)
+        k -= 140;
+    }
+    if (k < 2) return f[24] == k ? 1.f : 0.f;
+    if (k < 2 + food_dim) return f[25] == k - 2 ? 1.f : 0.f;
+    if (k < 4 + food_dim) return f[26] == k - 2 - food_dim ? 1.f : 0.f;
+    if (k < 7 + food_dim) return f[27] == k - 4 - food_dim ? 1.f : 0.f;
+    const int c = k - 7 - food_dim;                                                     // view mask (obs[6])
+    const uint32_t w = P.restrict_view ? (f[26] == 1 ? P.mask_gath[c >> 5] : P.mask_look[c >> 5]) : 0u;
+    return (float)((w >> (c & 31)) & 1u);
+}
+__device__ __forceinline__ int flat_dim_of(int food_dim) { return 2 * (2 * 4 * (MAX_DISTANCE + 1) + 4 * 11) + 2 + food_dim + 2 + 3 + CELLS; }
+
+// One thread per output element.
 __global__ void wab_flatten_kernel(const __grid_constant__ Params P, const uint8_t* __restrict__ features, int64_t rows,
                                    int food_dim, float* __restrict__ outp) {
-    const int dim = 2 * (2 * 4 * (MAX_DISTANCE + 1) + 4 * 11) + 2 + food_dim + 2 + 3 + CELLS;
+    const int dim = flat_dim_of(food_dim);
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= rows * dim) return;
     const int64_t row = e / dim;
-    int k = (int)(e - row * dim);
-    const uint8_t* f = features + row * FEAT_BYTES;
-    float v = 0.f;
+    outp[e] = flat_column(P, features + row * FEAT_BYTES, (int)(e - row * dim), food_dim);
+}
+
+// The policy input of actor_critic.py:188-189 in one pass: flatten + noise_scale * U[0,1) + cast, four elements per
+// thread (one Philox call; the 64-bit draw counter lives in device memory so a captured graph gets fresh noise on
+// every replay). BF16 = 0: f32 output, 1: bf16 output. Replaces five elementwise passes over the f32 matrix.
+template <int BF16>
+__global__ void wab_flatten_noisy_kernel(const __grid_constant__ Params P, const uint8_t* __restrict__ features, int64_t rows,
+                                         int food_dim, void* __restrict__ outp, float noise_scale,
+                                         const unsigned long long* __restrict__ d_counter) {
+    const int dim = flat_dim_of(food_dim);
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, total = rows * dim, e0 = q * 4;
+    if (e0 >= total) return;
+    const unsigned long long ctr = d_counter ? *d_counter : 0ull;
+    uint32_t w[4];
+    philox(P, (uint32_t)q, (uint32_t)(q >> 32), (uint32_t)ctr, (uint32_t)(ctr >> 32) ^ 0x464C4154u, w);
+    int64_t row = e0 / dim;
+    int k = (int)(e0 - row * dim);
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        v[j] = 0.f;
+        if (e0 + j < total) v[j] = flat_column(P, features + row * FEAT_BYTES, k, food_dim) + noise_scale * ((float)(w[j] >> 8) * (1.0f / 16777216.0f));
+        if (++k == dim) { k = 0; ++row; }
+    }
+    if (BF16) {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(outp) + e0;
+        if (e0 + 3 < total) {
+            __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b2 = __floats2bfloat162_rn(v[2], v[3]);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b2);
+            *reinterpret_cast<uint2*>(o) = pk;
+        } else {
+            for (int j = 0; e0 + j < total; ++j) o[j] = __float2bfloat16_rn(v[j]);
+        }
+    } else {
+        float* o = reinterpret_cast<float*>(outp) + e0;
+        if (e0 + 3 < total) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        else for (int j = 0; e0 + j < total; ++j) o[j] = v[j];
+    }
+}
+
+// Categorical(probs).sample() of actor_critic.py:117-120 for n rows of up to 8 probabilities: inverse CDF on one keyed
+// uniform per row (rows share a Philox call four at a time). BF16 = 1: probs are bf16.
+template <int BF16>
+__global__ void wab_sample_kernel(const __grid_constant__ Params P, const void* __restrict__ probs, int64_t n, int n_actions,
+                                  const unsigned long long* __restrict__ d_counter, uint8_t* __restrict__ actions) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long ctr = d_counter ? *d_counter : 0ull;
+    uint32_t w[4];
+    philox(P, (uint32_t)(i >> 2), (uint32_t)(i >> 34), (uint32_t)ctr, (uint32_t)(ctr >> 32) ^ 0x53414D50u, w);
+    const float u = (float)(pick4(w, (uint32_t)i & 3u) >> 8) * (1.0f / 16777216.0f);
+    float p[8], total = 0.f;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        p[a] = 0.f;
+        if (a < n_actions)
+            p[a] = BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(probs)[i * n_actions + a])
+                        : reinterpret_cast<const float*>(probs)[i * n_actions + a];
+        total += p[a];
+    }
+    const float target = u * total;            // probs need not be normalised exactly (bf16 softmax)
+    float cum = 0.f;
+    int pick = n_actions - 1;
     bool found = false;
 #pragma unroll
-    for (int species = 0; species < 2 && !found; ++species) {
-        const int base = species * 12;
-        if (k < 96) { v = f[base + k / 12] == k % 12 ? 1.f : 0.f; found = true; }              // nearest, second: 8 x one-hot(12)
-        else if (k < 140) { v = f[base + 8 + (k - 96) / 11] == (k - 96) % 11 ? 1.f : 0.f; found = true; }   // counts: 4 x one-hot(11)
-        else k -= 140;
+    for (int a = 0; a < 8; ++a) {              // smallest a with target < p[0] + ... + p[a]
+        cum += p[a];
+        if (!found && a < n_actions && target < cum) { pick = a; found = true; }
     }
-    if (!found) {
-        if (k < 2) v = f[24] == k ? 1.f : 0.f;
-        else if (k < 2 + food_dim) v = f[25] == k - 2 ? 1.f : 0.f;
-        else if (k < 4 + food_dim) v = f[26] == k - 2 - food_dim ? 1.f : 0.f;
-        else if (k < 7 + food_dim) v = f[27] == k - 4 - food_dim ? 1.f : 0.f;
-        else {                                                                                   // view mask (obs[6])
-            const int c = k - 7 - food_dim;
-            const uint32_t w = P.restrict_view ? (f[26] == 1 ? P.mask_gath[c >> 5] : P.mask_look[c >> 5]) : 0u;
-            v = (float)((w >> (c & 31)) & 1u);
-        }
-    }
-    outp[e] = v;
+    actions[i] = (uint8_t)pick;
 }
 
 __global__ void wab_philox_kernel(const __grid_constant__ Params P, const uint32_t* __restrict__ ctr, int64_t n,
@@ -978,6 +1047,40 @@ int wab_vec_flatten_features(WabVec* h, const uint8_t* d_features, int64_t n_row
     const int64_t total = n_rows * wab_vec_flat_dim(h);
     wab_flatten_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         h->P, d_features, n_rows, (int)h->cfg.food_obs_scale + 1, d_out);
+    WAB_CUDA(cudaGetLastError());
+    return WAB_OK;
+}
+
+int wab_vec_flatten_features_noisy(WabVec* h, const uint8_t* d_features, int64_t n_rows, void* d_out, int32_t out_bf16,
+                                   float noise_scale, const uint64_t* d_counter, void* stream) {
+    if (!h || !d_features || !d_out) return fail(WAB_E_NULL, "null argument");
+    if (n_rows <= 0) return WAB_OK;
+    if (((uintptr_t)d_out & 15u) != 0) return fail(WAB_E_CONFIG, "d_out must be 16-byte aligned");
+    DeviceGuard guard(h->device);
+    const int64_t quads = (n_rows * wab_vec_flat_dim(h) + 3) / 4;
+    const unsigned grid = (unsigned)((quads + 255) / 256);
+    const int food_dim = (int)h->cfg.food_obs_scale + 1;
+    const unsigned long long* ctr = reinterpret_cast<const unsigned long long*>(d_counter);
+    if (out_bf16)
+        wab_flatten_noisy_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(h->P, d_features, n_rows, food_dim, d_out, noise_scale, ctr);
+    else
+        wab_flatten_noisy_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(h->P, d_features, n_rows, food_dim, d_out, noise_scale, ctr);
+    WAB_CUDA(cudaGetLastError());
+    return WAB_OK;
+}
+
+int wab_sample_categorical(const void* d_probs, int32_t probs_bf16, int64_t n, int32_t n_actions, uint64_t seed,
+                           const uint64_t* d_counter, uint8_t* d_actions, void* stream) {
+    if (!d_probs || !d_actions) return fail(WAB_E_NULL, "null argument");
+    if (n_actions < 1 || n_actions > 8) return fail(WAB_E_CONFIG, "n_actions must be in [1, 8]");
+    if (n <= 0) return WAB_OK;
+    Params P;
+    memset(&P, 0, sizeof(P));
+    fill_round_keys(P, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    const unsigned long long* ctr = reinterpret_cast<const unsigned long long*>(d_counter);
+    if (probs_bf16) wab_sample_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(P, d_probs, n, n_actions, ctr, d_actions);
+    else wab_sample_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(P, d_probs, n, n_actions, ctr, d_actions);
     WAB_CUDA(cudaGetLastError());
     return WAB_OK;
 }

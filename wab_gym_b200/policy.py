@@ -52,7 +52,9 @@ class Rollout:
             raise ValueError("Rollout needs VecEnv(features=True)")
         self.env, self.noise, self.dtype = env, noise, dtype
         self.policy = (policy or Policy(env.flat_dim, env.n_actions)).to(env.device).to(dtype).eval()
-        self.flat = torch.empty(env.num_envs, env.flat_dim, dtype=torch.float32, device=env.device)
+        self.flat = torch.empty(env.num_envs, env.flat_dim, dtype=dtype, device=env.device)   # policy input, its dtype
+        self.noise_ctr = torch.zeros(1, dtype=torch.int64, device=env.device)                  # draw counter (graph-safe)
+        self.sample_seed = int(torch.initial_seed()) & (2 ** 63 - 1)
         self.actions = torch.zeros(env.num_envs, dtype=torch.uint8, device=env.device)
         self.values = torch.zeros(env.num_envs, dtype=torch.float32, device=env.device)
         self.reward_sum = torch.zeros((), dtype=torch.float64, device=env.device)
@@ -73,13 +75,11 @@ class Rollout:
     @torch.no_grad()
     def _step_eager(self):
         env = self.env
-        env.flatten_features(env.last_features, out=self.flat)            # gym.spaces.flatten, actor_critic.py:188
-        x = self.flat
-        if self.noise:
-            x = x + torch.rand_like(x) / 100                              # actor_critic.py:189
-        probs, value = self.policy(x.to(self.dtype))
-        sample = torch.multinomial(probs.float(), 1).squeeze(1)           # Categorical(probs).sample(), :117-120
-        self.actions.copy_(sample)
+        # gym.spaces.flatten (actor_critic.py:188) + U[0,1)/100 input noise (:189) + cast, one kernel
+        env.flatten_features_noisy(env.last_features, self.flat, 0.01 if self.noise else 0.0, self.noise_ctr)
+        self.noise_ctr += 1
+        probs, value = self.policy(self.flat)
+        env.sample_actions(probs, self.actions, self.noise_ctr, seed=self.sample_seed)   # Categorical(probs).sample(), :117-120
         self.values.copy_(value.squeeze(1))
         _, reward, _, _ = env.step(self.actions)
         self.reward_sum += reward.sum(dtype=torch.float64)

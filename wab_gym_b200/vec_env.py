@@ -185,6 +185,32 @@ class VecEnv:
                                                      self._stream()))
         return out
 
+    def flatten_features_noisy(self, features: torch.Tensor, out: torch.Tensor, noise_scale: float = 0.01,
+                               counter: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The policy input of ``actor_critic.py:188-189`` in one kernel: flatten + ``noise_scale * U[0,1)`` + cast to
+        ``out.dtype`` (float32 or bfloat16). ``counter`` is an int64[1] device tensor the caller advances between
+        calls (fresh noise per call, also under CUDA-graph replay)."""
+        features = features.contiguous()
+        rows = features.numel() // 28
+        if out.dtype not in (torch.float32, torch.bfloat16) or out.numel() != rows * self.flat_dim or not out.is_contiguous():
+            raise ValueError("out must be a contiguous float32 or bfloat16 tensor of rows x flat_dim elements")
+        _lib.check(self.lib.wab_vec_flatten_features_noisy(self._h, _ptr(features), rows, _ptr(out),
+                                                           int(out.dtype == torch.bfloat16), float(noise_scale),
+                                                           _ptr(counter), self._stream()))
+        return out
+
+    def sample_actions(self, probs: torch.Tensor, out: torch.Tensor, counter: Optional[torch.Tensor] = None,
+                       seed: int = 0) -> torch.Tensor:
+        """``Categorical(probs).sample()`` (``actor_critic.py:117-120``) for every row of ``probs`` ([N, A], float32 or
+        bfloat16, A <= 8) into the uint8 tensor ``out`` — one small kernel instead of torch.multinomial."""
+        probs = probs.contiguous()
+        if probs.dtype not in (torch.float32, torch.bfloat16) or out.dtype != torch.uint8 or out.numel() != probs.shape[0]:
+            raise ValueError("probs must be float32/bfloat16 [N, A] and out uint8[N]")
+        _lib.check(self.lib.wab_sample_categorical(_ptr(probs), int(probs.dtype == torch.bfloat16), probs.shape[0],
+                                                   probs.shape[1], int(seed) & (2 ** 64 - 1), _ptr(counter), _ptr(out),
+                                                   self._stream()))
+        return out
+
     # ------------------------------------------------------------------ host-buffer entry points
     def alloc_host_buffers(self, pinned: bool = True) -> dict:
         """Host-side buffers for the host entry points: every output is a view into ONE (pinned) block laid out by
