@@ -12,10 +12,14 @@ Printed JSON (rank 0, one line):
   value        device-resident throughput: actions for all K steps already in HBM, K steps executed
                by the multi-step kernel in launches of <= --fuse steps, every step's outputs written.
   per_call     the same K steps as K single-step launches replayed from one CUDA graph.
-  e2e          K steps through the C-ABI host-buffer call (wab_vec_step_host): pinned host actions
-               in, every output copied back to pinned host memory, stream sync per step.
+  e2e          K steps (at most 2,048) through the C-ABI host-buffer call (wab_vec_step_host_packed): pinned
+               host actions in, every output in pinned host memory when the call returns (up to 16,384 envs
+               the kernel streams them there itself, above that H2D + kernel + D2H), stream sync per step.
   roofline     dominant kernel (wab_step_kernel) vs the measured HBM copy bandwidth.
-  cpu_baseline the oracle's C restatement of the reference step on the host cores (bounded sample).
+  cpu_baseline the oracle's C restatement of the reference step on all host cores (bounded sample), plus the
+               same on one thread.
+--impl reference times that C restatement alone (the reference itself is pure Python on pandas, ~16 steps/s per
+core, and its sources do not travel to the GPU box); rank 0 only, at least 512 lockstep steps.
 """
 import argparse
 import json
