@@ -1,21 +1,34 @@
 #!/usr/bin/env python
 """bench.py — env-steps/s including observation materialisation (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--num-envs E]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--num-envs E] [--legs all|none|a,b]
 
-A "step" is one lockstep step of the whole batch: every environment advances one turn and its
-observation (u8[3,11,11] + food, role, status), reward and done are written to HBM. Workload at
-N = 1: BASELINE.json configs[1] — 4,096 lockstep default-grid v1 environments with fused
-observation output (weak scaling: 4,096 envs per GPU, global env ids, no data-path collective).
+A "step" is one lockstep step of the whole batch: every environment advances one turn and its observation
+(u8[3,11,11] + food, role, status), reward and done are written to HBM. Workload at N = 1: BASELINE.json
+configs[1] — 4,096 lockstep default-grid v1 environments with fused observation output (weak scaling: 4,096 envs
+per GPU, global env ids, no data-path collective).
+
+How the timed region is built (every leg): W (>= 3) untimed warm-up steps; then the K steps are replayed
+`repeats` times back to back so that the window is at least --min-window-ms long (a 20-step launch of 4,096 envs
+is 60 us — one such launch is not a measurement); the launches of one replay are captured in a CUDA graph so the
+host never throttles the queue; the outputs rotate through a ring of buffers larger than twice the L2; the window
+is bracketed by barrier + synchronize on both sides, timed with CUDA events on the launching stream, max over
+ranks. The one collective of the data-parallel run — the 64-byte all-reduce of the episode statistics — is issued
+a few times during the window on a SIDE stream (wab_gym_b200.sharding.AsyncStatsReducer): the compute stream never
+waits for it and nothing is read on the host before the stop event; its latency is reported as `collective_us`.
 
 Printed JSON (rank 0, one line):
-  value        device-resident throughput: actions for all K steps already in HBM, K steps executed
-               by the multi-step kernel in launches of <= --fuse steps, every step's outputs written.
-  per_call     the same K steps as K single-step launches replayed from one CUDA graph.
-  e2e          K steps (at most 2,048) through the C-ABI host-buffer call (wab_vec_step_host_packed): pinned
-               host actions in, every output in pinned host memory when the call returns (up to 16,384 envs
-               the kernel streams them there itself, above that H2D + kernel + D2H), stream sync per step.
-  roofline     dominant kernel (wab_step_kernel) vs the measured HBM copy bandwidth.
+  value        configs[1], device-resident: actions already in HBM, K steps per pass executed by the multi-step
+               kernel in launches of <= --fuse steps, every step's outputs written.
+  per_call     the same workload as single-step launches (what a policy in the loop gets), CUDA-graph replayed.
+  e2e          the C-ABI host-buffer call (wab_vec_step_host_packed): pinned host actions in, every output in
+               pinned host memory when the call returns, stream sync per step.
+  roofline     dominant kernel of `value` (wab_step_kernel) vs the measured HBM copy bandwidth: `frac` uses the
+               ALGORITHMIC 436 B/env-step, `frac_dram` the bytes the kernel really moves (ncu).
+  legs         the other BASELINE.json configs, each with its own roofline: large_batch (v1, 131,072 envs per GPU =
+               the 8-GPU share of 1M), batch_1m (v1, 1,048,576 envs per GPU), v2_config3 (65,536 worlds 20x20),
+               v2_config4 (131,072 worlds 64x64 per GPU = the 8-GPU share of configs[3]'s 1,048,576),
+               rollout_fp32 (configs[4]: fp32 actor-critic policy in the loop, 32,768 envs per GPU).
   cpu_baseline the oracle's C restatement of the reference step on all host cores (bounded sample), plus the
                same on one thread.
 --impl reference times that C restatement alone (the reference itself is pure Python on pandas, ~16 steps/s per
@@ -23,6 +36,7 @@ core, and its sources do not travel to the GPU box); rank 0 only, at least 512 l
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -35,7 +49,19 @@ if REPO not in sys.path:
 
 B_ALG = 436  # algorithmic bytes per env-step, SURVEY.md §8(d): 363 obs + 8 scalars + 1 action + 2x32 state
 METRIC = "env-steps/sec incl. obs"
-WORKLOAD = "configs[1]: wab_env v1 default 11x11 viewport, 4096 lockstep envs per GPU, fused u8 observation output"
+ALL_LEGS = ("large_batch", "batch_1m", "v2_config3", "v2_config4", "rollout_fp32")
+RING_BYTES = 256 << 20   # output ring per leg: > 2 x the 126 MB L2
+
+
+def workload_name(n):
+    tag = "configs[1]: " if n == 4096 else ""
+    return "%swab_env v1 default 11x11 viewport, %d lockstep envs per GPU, fused u8 observation output" % (tag, n)
+
+
+def config_dict(n, world):
+    """The workload, in the same words for both arms (the driver compares the two `config`s)."""
+    return {"workload": workload_name(n), "num_envs_per_gpu": n, "global_envs": world * n, "parallelism": "dp%d" % world,
+            "actions": "uniform 0-4, pre-generated u8[K,N]", "auto_reset": True}
 
 
 def parse_args():
@@ -46,6 +72,9 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--num-envs", type=int, default=4096, help="environments per GPU")
     ap.add_argument("--fuse", type=int, default=256, help="steps per launch of the multi-step kernel")
+    ap.add_argument("--min-window-ms", type=float, default=500.0, help="shortest timed window of the headline leg")
+    ap.add_argument("--leg-window-ms", type=float, default=60.0, help="shortest timed window of every other leg")
+    ap.add_argument("--legs", default="all", help="all | none | comma list of " + ",".join(ALL_LEGS))
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--skip-e2e", action="store_true", help="sweeps only: skip the host-buffer leg")
@@ -62,8 +91,27 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def dram_bytes_per_env_step(n, T):
+    """DRAM bytes the step kernel really moves per env-step, from the `ncu --set full` captures under profiles/
+    (dram__bytes_read.sum + dram__bytes_write.sum per launch): the multi-step kernel keeps state in registers, so a
+    launch writes 372 B per env-step of outputs (363 grid + 9 scalar bytes; every 32-byte sector it touches is
+    fully written) and reads 1 action byte; state (38 B + wolves, read and written once per LAUNCH) and the
+    read side of partially written sectors add the rest. Table: (n, T) -> bytes per env-step as measured;
+    otherwise the model 372 + 1 + 2 * 40 / T, which the captures match within 1 %."""
+    table_path = os.path.join(REPO, "profiles", "dram_traffic_table.json")
+    try:
+        with open(table_path) as fh:
+            tab = json.load(fh)
+        hit = tab.get("%d,%d" % (n, T))
+        if hit:
+            return float(hit["bytes_per_env_step"]), "ncu (%s)" % hit["source"]
+    except Exception:
+        pass
+    return 373.0 + 80.0 / T, "model 372 out + 1 action + 2 x 40 state / T (ncu-calibrated, profiles/dram_traffic_table.json)"
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -76,7 +124,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
@@ -85,21 +133,26 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def __exit__(self, *exc):
         if self.proc is not None:
-            time.sleep(0.25)
+            time.sleep(0.15)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
 
-    def summary(self):
+    def summary(self, window=None):
+        """Median SM clock and throttle reasons of the samples taken inside `window` = (t0, t1) wall-clock seconds of
+        the timed region (every sample when fewer than two fall inside it)."""
         sm, mx, reasons = [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for r in self.rows:
+        rows = [r for (t, r) in self.rows if window is None or window[0] <= t <= window[1] + 0.05]
+        if len(rows) < 2:
+            rows = [r for (_, r) in self.rows]
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for name, val in zip(names, r[3:7]):
@@ -124,6 +177,7 @@ def emit(text):
         print(text, flush=True)
 
 
+# ------------------------------------------------------------------------------------------ CPU arm
 def cpu_reference_run(n_envs, steps, warmup, seed, threads=0, budget_s=None):
     """The oracle's C restatement of the reference step on the host cores (the reference itself is pure
     Python on pandas, ~14-18 steps/s per core in the build container, and cannot travel to this box)."""
@@ -154,6 +208,7 @@ def cpu_reference_run(n_envs, steps, warmup, seed, threads=0, budget_s=None):
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     budget_env_steps = 2.0e8
@@ -172,178 +227,366 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "timed_lockstep_steps": res["steps"],
         "ms_per_step": 1e3 * res["seconds"] / res["steps"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 food / integer rules (CPU)",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "num_envs_per_gpu": n_envs},
+        "data": "synthetic", "config": config_dict(n_envs, max(world, args.gpus)),
         "cpu_baseline": {"value": res["value"], "unit": "env-steps/s", "cores": res["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": res["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "oracle C port of wab_env.py step+obs with OpenMP over envs; the pandas reference itself: 16.6 steps/s single process, 125 steps/s over 8 cores in the build container (profiles/r1_reference_cpu_timing.json)",
+        "note": "oracle C port of wab_env.py step+obs with OpenMP over envs, all host threads, one process (whatever --gpus is); "
+                "the pandas reference itself: 16.6 steps/s single process, 125 steps/s over 8 cores in the build container "
+                "(profiles/r1_reference_cpu_timing.json)",
     }
     print(json.dumps(line), flush=True)
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from wab_gym_b200 import VecEnv
-    from wab_gym_b200.sharding import reduce_stats
+# ------------------------------------------------------------------------------------------ GPU arm
+class Ctx:
+    """Device, process group and the timing discipline shared by every leg."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # keep stdout to the one JSON line: NCCL prints its version banner on fd 1 (NCCL_DEBUG=VERSION may come from
-        # the environment or from a conf file), so C-level stdout goes to stderr and the line is written to the real one
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
-        sys.stdout.flush()
-        _REAL_STDOUT.append(os.dup(1))
-        os.dup2(2, 1)
-        dist.init_process_group("nccl", device_id=dev)
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            # keep stdout to the one JSON line: NCCL prints its version banner on fd 1 (NCCL_DEBUG=VERSION may come from
+            # the environment or from a conf file), so C-level stdout goes to stderr and the line is written to the real one
+            if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+                os.environ["NCCL_DEBUG"] = "WARN"
+            sys.stdout.flush()
+            _REAL_STDOUT.append(os.dup(1))
+            os.dup2(2, 1)
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.peak, self.peak_src = measured_peak()
 
-    n, K, W, T = args.num_envs, args.steps, max(args.warmup, 3), max(1, min(args.fuse, args.steps))
-    env = VecEnv(n, seed=args.seed, device=dev, env_id_base=rank * n)
-    env_lpe = env.lanes_per_env
-    gen = torch.Generator(device=dev).manual_seed(1 + rank)
-    actions = torch.randint(0, env.n_actions, (K + W, n), dtype=torch.uint8, device=dev, generator=gen)
-    env.reset()
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def max_over_ranks(ms):
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    def max_over_ranks(self, ms):
+        if self.world > 1:
+            t = self.torch.tensor([ms], dtype=self.torch.float64, device=self.dev)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
             return float(t.item())
         return ms
 
-    # ---------------- device-resident, multi-step kernel (value) ----------------
-    out = env._alloc(T)
-    chunks = [(s, min(T, K - s)) for s in range(0, K, T)]
-    for s in range(0, W, T):
-        env.step_many(actions[K + s:K + min(W, s + T)], out={k: v[:min(T, W - s)] for k, v in out.items()})
-    if world > 1:
-        reduce_stats(env.stats_tensor())      # warm-up of the one collective too (NCCL sets its channels up on first use)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in chunks]
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
-        barrier()
-        try:                                  # keep the GPU busy ~0.2 ms while the host enqueues the timed launches, so
-            torch.cuda._sleep(400_000)        # that a short run (small K) times the K steps and not the enqueue gap
+    def timed_window(self, enqueue, launches_per_unit, min_ms, between=None):
+        """Time `repeats` replays of one unit (= `launches_per_unit` calls enqueue(j), captured in a CUDA graph)
+        such that the window is >= min_ms. `between(r, repeats)` runs on the host after replay r was enqueued (side-stream
+        work only). Returns (window_ms max over ranks, repeats)."""
+        torch = self.torch
+        side = torch.cuda.Stream(device=self.dev)
+        graph = torch.cuda.CUDAGraph()
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            for j in range(launches_per_unit):
+                enqueue(j)                                    # eager once: warm + every lazy allocation done
+            side.synchronize()
+            with torch.cuda.graph(graph, stream=side):
+                for j in range(launches_per_unit):
+                    enqueue(j)
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(self.dev)
+        e0.record(); graph.replay(); graph.replay(); e1.record()          # calibration (also warm-up of the replay)
+        torch.cuda.synchronize(self.dev)
+        unit_ms = self.max_over_ranks(e0.elapsed_time(e1) / 2.0)
+        repeats = max(1, int(math.ceil(min_ms / max(unit_ms, 1e-4))))
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        try:                                  # keep the GPU busy ~0.2 ms while the host enqueues the first replays
+            torch.cuda._sleep(400_000)
         except Exception:
             pass
+        t_wall = time.time()
         start.record()
-        for (s, c), (e0, e1) in zip(chunks, ev):
-            e0.record()
-            env.step_many(actions[s:s + c], out={k: v[:c] for k, v in out.items()})
-            e1.record()
-        stats_local = env.stats_tensor()
-        stats_all = reduce_stats(stats_local) if world > 1 else None   # the only collective: 64 bytes
+        for r in range(repeats):
+            graph.replay()
+            if between is not None:
+                between(r, repeats)
         stop.record()
-        barrier()
-        fused_ms = max_over_ranks(start.elapsed_time(stop))
-        kernel_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
-        if fused_ms < 400.0:   # keep the GPU busy long enough for >= 2 clock samples
-            t_end = time.perf_counter() + 0.6
-            while time.perf_counter() < t_end:
-                env.step_many(actions[:chunks[0][1]], out={k: v[:chunks[0][1]] for k, v in out.items()})
-            torch.cuda.synchronize(dev)
-    launches = len(chunks)
-    del out
+        self.barrier()
+        self.last_window = (t_wall, time.time())
+        return self.max_over_ranks(start.elapsed_time(stop)), repeats
 
-    # ---------------- device-resident, one launch per step from a CUDA graph (per_call) ----------------
-    G = 64 if K >= 64 else K
+
+def v1_fused_leg(ctx, n, K, W, T, min_ms, with_collective):
+    """K lockstep steps of n v1 envs per pass through wab_vec_step_many (launches of <= T steps), replayed."""
+    torch = ctx.torch
+    from wab_gym_b200 import VecEnv
+    from wab_gym_b200.sharding import AsyncStatsReducer
+    env = VecEnv(n, seed=ctx.args.seed, device=ctx.dev, env_id_base=ctx.rank * n)
+    chunks = [(s, min(T, K - s)) for s in range(0, K, T)]                 # launches of one pass
+    slots = max(1, int(math.ceil(RING_BYTES / float(T * n * 372))))       # output ring > 2 x L2
+    passes = max(1, int(math.ceil(slots / float(len(chunks)))))           # passes per graph
+    ring = [env._alloc(T) for _ in range(slots)]
+    gen = torch.Generator(device=ctx.dev).manual_seed(1 + ctx.rank)
+    actions = torch.randint(0, env.n_actions, (passes * K + W, n), dtype=torch.uint8, device=ctx.dev, generator=gen)
     env.reset()
-    side = torch.cuda.Stream(device=dev)
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.stream(side):
-        for t in range(3):
-            env.step(actions[K + t % W])
-        side.synchronize()
-        with torch.cuda.graph(graph, stream=side):
-            for t in range(G):
-                env.step(actions[t])
-    torch.cuda.synchronize(dev)
-    reps = max(1, K // G)
-    barrier()
-    start.record()
-    for _ in range(reps):
-        graph.replay()
-    stop.record()
-    barrier()
-    percall_ms = max_over_ranks(start.elapsed_time(stop))
-    percall = {"value": world * n * reps * G / (percall_ms * 1e-3), "unit": "env-steps/s", "ms_per_step": percall_ms / (reps * G),
-               "mode": "1 launch per step, %d-step CUDA graph replayed %d times (actions repeat per replay)" % (G, reps)}
+    for s in range(0, W, T):                                              # W untimed warm-up steps
+        c = min(T, W - s)
+        env.step_many(actions[passes * K + s:passes * K + s + c], out={k: v[:c] for k, v in ring[0].items()})
+    launches = [(p * K + s, c) for p in range(passes) for (s, c) in chunks]
 
-    # ---------------- end to end through the host-buffer C-ABI call (e2e) ----------------
-    if args.skip_e2e:
-        return finish(args, env, world, rank, n, K, W, T, fused_ms, kernel_ms, launches, clocks, percall, None, stats_all, dist)
+    def enqueue(j):
+        s, c = launches[j]
+        buf = ring[j % slots]
+        env.step_many(actions[s:s + c], out={k: v[:c] for k, v in buf.items()})
+
+    reducer = AsyncStatsReducer(ctx.dev) if with_collective else None
+
+    def between(r, repeats):           # SURVEY §8(e): the statistics all-reduce, every few launches, on a side stream
+        if r % max(1, repeats // 16) == 0:
+            reducer.submit(env.stats_tensor)
+
+    if reducer is not None:
+        reducer.submit(env.stats_tensor)                                  # NCCL sets its channels up on first use
+        reducer.result()
+    window_ms, repeats = ctx.timed_window(enqueue, len(launches), min_ms, between=between if reducer is not None else None)
+    total_steps = repeats * passes * K
+    n_launch = repeats * len(launches)
+    collective_us = None
+    stats_all = None
+    if reducer is not None:
+        reducer.submit(env.stats_tensor)
+        stats_all = reducer.result()                                      # host read AFTER the stop event
+        if ctx.world > 1:
+            t = env.stats_tensor()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            samples = []
+            for _ in range(5):
+                torch.cuda.synchronize(ctx.dev)
+                e0.record(); ctx.dist.all_reduce(t); e1.record()
+                torch.cuda.synchronize(ctx.dev)
+                samples.append(e0.elapsed_time(e1) * 1e3)
+            collective_us = sorted(samples)[2]
+    stats = env.stats()
+    lpe = env.lanes_per_env
+    env.close()
+    del ring
+    torch.cuda.empty_cache()
+    per_launch_ms = window_ms / n_launch
+    steps_per_launch = total_steps / n_launch
+    achieved = B_ALG * n * total_steps / (window_ms * 1e-3) / 1e9
+    bpe, bpe_src = dram_bytes_per_env_step(n, int(round(steps_per_launch)))
+    roof = {"bound": "hbm", "achieved": achieved, "peak": ctx.peak, "unit": "GB/s", "frac": achieved / ctx.peak,
+            "traffic": bpe * n * steps_per_launch, "traffic_source": bpe_src,
+            "frac_dram": achieved / B_ALG * bpe / ctx.peak,
+            "kernel": "wab_step_kernel<false, LPE=%d>" % lpe, "peak_source": ctx.peak_src,
+            "bytes_per_env_step": B_ALG, "dram_bytes_per_env_step": bpe, "env_steps_per_launch": n * steps_per_launch,
+            "avg_launch_ms": per_launch_ms,
+            "how": "algorithmic bytes of all launches of the timed window / the window (CUDA events on the launching stream; "
+                   "launches are back to back in a graph, so inter-launch gaps count against the kernel)"}
+    return {"value": ctx.world * n * total_steps / (window_ms * 1e-3), "unit": "env-steps/s", "window_ms": window_ms,
+            "repeats": repeats * passes, "steps_per_pass": K, "steps_per_launch": steps_per_launch, "launches": n_launch,
+            "ms_per_step": window_ms / total_steps, "num_envs_per_gpu": n, "global_envs": ctx.world * n,
+            "ring": "%d output buffers of %d MB (ring of %d MB > 2 x L2), rotated per launch" % (
+                slots, int(T * n * 372 / 1e6), int(slots * T * n * 372 / 1e6)),
+            "roofline": roof, "collective_us": collective_us,
+            "collectives_in_window": (reducer.submitted - 2) if reducer is not None else 0,
+            "episode_stats": stats_all or stats}
+
+
+def v1_percall_leg(ctx, n, K, W, min_ms):
+    """Single-step launches (what a policy in the loop gets), G of them per CUDA graph."""
+    torch = ctx.torch
+    from wab_gym_b200 import VecEnv
+    env = VecEnv(n, seed=ctx.args.seed, device=ctx.dev, env_id_base=ctx.rank * n)
+    G = max(1, min(64, K))
+    gen = torch.Generator(device=ctx.dev).manual_seed(101 + ctx.rank)
+    actions = torch.randint(0, env.n_actions, (G, n), dtype=torch.uint8, device=ctx.dev, generator=gen)
+    env.reset()
+    for t in range(W):
+        env.step(actions[t % G])
+    window_ms, repeats = ctx.timed_window(lambda j: env.step(actions[j]), G, min_ms)
+    lpe = env.lanes_per_env
+    env.close()
+    steps = repeats * G
+    achieved = B_ALG * n * steps / (window_ms * 1e-3) / 1e9
+    return {"value": ctx.world * n * steps / (window_ms * 1e-3), "unit": "env-steps/s", "ms_per_step": window_ms / steps,
+            "window_ms": window_ms, "launches": steps,
+            "mode": "1 launch per step, %d-step CUDA graph replayed %d times (actions repeat per replay; outputs "
+                    "rewritten in place: %d KB per step, L2-resident)" % (G, repeats, n * 372 // 1024),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": ctx.peak, "unit": "GB/s", "frac": achieved / ctx.peak,
+                         "kernel": "wab_step_kernel<false, LPE=%d>, 1 step per launch" % lpe}}
+
+
+def v2_leg(ctx, n, dims, min_ms, name):
+    """Environment 2.0 world turns: n lockstep worlds per GPU, contiguous world-id shards."""
+    torch = ctx.torch
+    from wab_gym_b200.world2 import VecWorld2
+    Wd, Hd, no, nw, nb = dims
+    A, E = no + nw, no + nw + nb
+    env = VecWorld2(n, Wd, Hd, no, nw, nb, seed=ctx.args.seed, env_id_base=ctx.rank * n, device=ctx.dev)
+    env.reset_environment()
+    gen = torch.Generator(device=ctx.dev).manual_seed(7 + ctx.rank)
+    acts = torch.empty((8, A, n), dtype=torch.uint8, device=ctx.dev)       # entity-major, like every v2 array
+    acts[:, :no] = torch.randint(0, 6, (8, no, n), dtype=torch.uint8, device=ctx.dev, generator=gen)
+    acts[:, no:] = torch.randint(0, 5, (8, nw, n), dtype=torch.uint8, device=ctx.dev, generator=gen)
+    for t in range(3):
+        env.turn(acts[t])
+    window_ms, repeats = ctx.timed_window(lambda j: env.turn(acts[j]), 8, min_ms)
+    turns = repeats * 8
+    S = 2 * env.R + 1
+    bytes_per_turn = A * (3 * S * S + 9) + 2 * E * 8
+    kernel = env.kernel_name() if hasattr(env, "kernel_name") else "wab2 turn kernel"
+    env.close()
+    del env
+    torch.cuda.empty_cache()
+    tps = n * turns / (window_ms * 1e-3)
+    achieved = tps * bytes_per_turn / 1e9
+    return {"workload": "%s: Environment 2.0 World(%d,%d), %d ostriches %d wolves %d bushes, %d lockstep worlds per GPU" % (
+                name, Wd, Hd, no, nw, nb, n),
+            "value": ctx.world * tps, "unit": "world-turns/s", "entity_steps_per_s": ctx.world * tps * E,
+            "ms_per_turn": window_ms / turns, "window_ms": window_ms, "turns": turns, "launches": turns,
+            "num_worlds_per_gpu": n, "global_worlds": ctx.world * n,
+            "outputs": "per acting entity a %dx%dx3 u8 window + 5 int32 + reward + done, rewritten per turn (%d MB > L2)" % (
+                S, S, int(A * n * 3 * S * S / 1e6)),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": ctx.peak, "unit": "GB/s", "frac": achieved / ctx.peak,
+                         "bytes_per_world_turn": bytes_per_turn, "kernel": kernel, "traffic": None}}
+
+
+def rollout_leg(ctx, n, K, min_ms):
+    """configs[4]: the reference's actor-critic policy (actor_critic.py:54-97), fp32, consuming device-resident
+    observations: features -> policy -> Categorical sample -> env.step, nothing leaves the GPU."""
+    torch = ctx.torch
+    from wab_gym_b200 import VecEnv
+    from wab_gym_b200.policy import Policy, Rollout
+    torch.manual_seed(0)
+    env = VecEnv(n, seed=ctx.args.seed, device=ctx.dev, env_id_base=ctx.rank * n, features=True)
+    ro = Rollout(env, Policy(env.flat_dim, env.n_actions), use_graph=True, dtype=torch.float32)
+    ro.run(10)
+    torch.cuda.synchronize(ctx.dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); ro.run(8); e1.record()
+    torch.cuda.synchronize(ctx.dev)
+    step_ms = ctx.max_over_ranks(e0.elapsed_time(e1) / 8.0)
+    steps = max(K if K <= 512 else 512, int(math.ceil(min_ms / max(step_ms, 1e-4))))
+    ctx.barrier()
+    e0.record(); ro.run(steps); e1.record()
+    ctx.barrier()
+    ms = ctx.max_over_ranks(e0.elapsed_time(e1))
+    st = env.stats()
+    desc = ro.describe() if hasattr(ro, "describe") else "flatten+noise kernel -> torch fp32 MLP (cuBLAS) -> sampling kernel -> wab_step_kernel"
+    env.close()
+    flops = 2.0 * (env.flat_dim * 128 + 128 * 150 + 150 * 128 + 128 * (env.n_actions + 1))
+    v = n * steps / (ms * 1e-3)
+    return {"workload": "configs[4]: actor_critic.py rollout, policy %d-128-150-128-{%d,1} fp32 in the loop, %d v1 envs per GPU" % (
+                env.flat_dim, env.n_actions, n),
+            "value": ctx.world * v, "unit": "env-steps/s", "ms_per_step": ms / steps, "window_ms": ms, "steps": steps,
+            "dtype": "fp32 policy", "num_envs_per_gpu": n, "global_envs": ctx.world * n, "path": desc,
+            "policy_flops_per_env_step": flops, "policy_tflops": v * flops / 1e12,
+            "mean_episode_length": st["steps"] / max(st["episodes"], 1)}
+
+
+def e2e_leg(ctx, n, K, W):
+    """K (at least 100 ms worth of) steps through the host-buffer C-ABI call, host copies inside the timed region."""
+    torch = ctx.torch
+    from wab_gym_b200 import VecEnv
+    env = VecEnv(n, seed=ctx.args.seed, device=ctx.dev, env_id_base=ctx.rank * n)
+    gen = torch.Generator(device=ctx.dev).manual_seed(1 + ctx.rank)
     hb = env.alloc_host_buffers(pinned=True)
-    host_actions = actions[:min(K, 2048)].cpu().pin_memory()
-    Ke = host_actions.shape[0]
+    host_actions = torch.randint(0, env.n_actions, (256, n), dtype=torch.uint8, device=ctx.dev, generator=gen).cpu().pin_memory()
     env.reset_host(hb)
     acts_np, hnp = host_actions.numpy(), hb["np"]     # numpy views of the pinned buffers: no per-step torch dispatch
-    for t in range(min(W, Ke)):
+    for t in range(max(W, 8)):
+        hnp["actions"][:] = acts_np[t % 256]
+        env.step_host(hb)
+    t0 = time.perf_counter()
+    for t in range(16):
         hnp["actions"][:] = acts_np[t]
         env.step_host(hb)
-    barrier()
+    per = (time.perf_counter() - t0) / 16
+    Ke = int(min(max(K, math.ceil(0.1 / per)), 20000))
+    ctx.barrier()
     t0 = time.perf_counter()
     acc = 0.0
     for t in range(Ke):
-        hnp["actions"][:] = acts_np[t]           # this step's inputs, host memory
+        hnp["actions"][:] = acts_np[t & 255]     # this step's inputs, host memory
         env.step_host(hb)
         acc += float(hnp["reward"][0])           # the step's result is read on the host
-    torch.cuda.synchronize(dev)
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
-    h2d = n
-    d2h = n * (363 + 1 + 1 + 1 + 4 + 1 + 1)
-    e2e = {"value": world * n * Ke / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": d2h, "steps": Ke, "ms_per_step": e2e_ms / Ke,
-           "path": ("wab_vec_step_host_packed, <= 16,384 envs: wab_step_kernel reads the pinned host actions and streams grids/food/"
-                    "role/status/reward/done/info straight into the pinned host block over PCIe -> stream sync" if n <= 16384 else
-                    "wab_vec_step_host_packed: pinned host actions -> H2D -> wab_step_kernel -> one D2H of grids/food/role/status/"
-                    "reward/done/info into a pinned block -> stream sync")}
-
-    return finish(args, env, world, rank, n, K, W, T, fused_ms, kernel_ms, launches, clocks, percall, e2e, stats_all, dist)
-
-
-def finish(args, env, world, rank, n, K, W, T, fused_ms, kernel_ms, launches, clocks, percall, e2e, stats_all, dist):
-    stats = env.stats()
-    env_lpe = env.lanes_per_env
+    torch.cuda.synchronize(ctx.dev)
+    mine_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = ctx.max_over_ranks(mine_ms)
+    per_rank = None
+    if ctx.world > 1:
+        t = torch.zeros(ctx.world, dtype=torch.float64, device=ctx.dev)
+        t[ctx.rank] = n * Ke / (mine_ms * 1e-3)
+        ctx.dist.all_reduce(t)
+        per_rank = [float(x) for x in t.cpu()]
+    mapped = n <= 16384
     env.close()
+    return {"value": ctx.world * n * Ke / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": n,
+            "d2h_bytes_per_step": n * (363 + 1 + 1 + 1 + 4 + 1 + 1), "steps": Ke, "ms_per_step": e2e_ms / Ke,
+            "per_rank": per_rank,
+            "path": ("wab_vec_step_host_packed, <= 16,384 envs: wab_step_kernel reads the pinned host actions and streams grids/food/"
+                     "role/status/reward/done/info straight into the pinned host block over PCIe -> stream sync" if mapped else
+                     "wab_vec_step_host_packed: pinned host actions -> H2D -> wab_step_kernel -> one D2H of grids/food/role/status/"
+                     "reward/done/info into a pinned block -> stream sync")}
 
-    if rank == 0:
-        peak, peak_src = measured_peak()
-        per_launch_s = (kernel_ms * 1e-3) / launches
-        steps_per_launch = K / launches
-        achieved = B_ALG * n * steps_per_launch / per_launch_s / 1e9
+
+def run_ours(args):
+    ctx = Ctx(args)
+    torch = ctx.torch
+    n, K, W, T = args.num_envs, args.steps, max(args.warmup, 3), max(1, min(args.fuse, args.steps))
+    want = ALL_LEGS if args.legs == "all" else tuple(x for x in args.legs.split(",") if x in ALL_LEGS)
+
+    with ClockSampler(ctx.local_rank) as clocks:
+        main = v1_fused_leg(ctx, n, K, W, T, args.min_window_ms, with_collective=True)
+        main_window = ctx.last_window
+    percall = v1_percall_leg(ctx, n, K, W, args.leg_window_ms)
+
+    legs = {}
+    Kl = min(K, 32)        # the big-batch legs bound their output ring: <= 32 steps per launch
+    plan = {
+        "large_batch": lambda: v1_fused_leg(ctx, 131072, Kl, W, Kl, args.leg_window_ms, with_collective=False),
+        "batch_1m": lambda: v1_fused_leg(ctx, 1048576, min(K, 8), W, min(K, 8), args.leg_window_ms, with_collective=False),
+        "v2_config3": lambda: v2_leg(ctx, 65536, (20, 20, 10, 3, 20), args.leg_window_ms, "configs[2]"),
+        "v2_config4": lambda: v2_leg(ctx, 131072, (64, 64, 8, 64, 256), args.leg_window_ms, "configs[3] (8-GPU share of 1,048,576)"),
+        "rollout_fp32": lambda: rollout_leg(ctx, 32768, K, args.leg_window_ms),
+    }
+    for name in want:
+        try:
+            legs[name] = plan[name]()
+            if name in ("large_batch", "batch_1m"):
+                legs[name]["workload"] = workload_name(legs[name]["num_envs_per_gpu"])
+        except Exception as exc:      # a leg must never take the headline down with it
+            legs[name] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+            try:
+                torch.cuda.synchronize(ctx.dev)
+                torch.cuda.empty_cache()
+            except Exception:
+                pass
+
+    e2e = None if args.skip_e2e else e2e_leg(ctx, n, K, W)
+
+    if ctx.rank == 0:
         line = {
-            "metric": METRIC, "value": world * n * K / (fused_ms * 1e-3), "unit": "env-steps/s", "n_gpus": world,
-            "steps": K, "warmup": W, "ms_per_step": fused_ms / K, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": main["value"], "unit": "env-steps/s", "n_gpus": ctx.world,
+            "steps": K, "warmup": W, "repeats": main["repeats"], "window_ms": main["window_ms"],
+            "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8 grids / int32 rules / u32 Philox (int food counter proven == f64)",
-            "data": "synthetic",
-            "config": {"workload": WORKLOAD, "num_envs_per_gpu": n, "global_envs": world * n, "parallelism": "dp%d" % world,
-                       "mode": "wab_vec_step_many, %d steps per launch, every step's obs/reward/done written" % T,
-                       "l2": "each launch writes %d MB of distinct output (> L2); state lives in registers, no reuse between steps"
-                             % int(T * n * 372 / 1e6),
-                       "actions": "uniform 0-4, pre-generated u8[K,N] in HBM"},
-            "clocks": clocks.summary(),
+            "data": "synthetic", "config": config_dict(n, ctx.world),
+            "timing": {"mode": "wab_vec_step_many, %g steps per launch, every step's obs/reward/done written; the K steps "
+                               "replayed %d times for a %.0f ms window" % (main["steps_per_launch"], main["repeats"], main["window_ms"]),
+                       "l2": main["ring"] + "; state lives in registers, no reuse between steps",
+                       "collective": "64-byte statistics all-reduce on a side stream, %d issued inside the window, none awaited "
+                                     "before the stop event" % main["collectives_in_window"]},
+            "clocks": clocks.summary(main_window),
             "e2e": e2e,
             "per_call": percall,
-            "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (337.2e6 if (n == 4096 and T == 256) else None),   # ncu dram read+write per launch, profiles/r1e_ncu_4096_summary.txt
-                         "kernel": "wab_step_kernel<false, LPE=%d>" % env_lpe, "peak_source": peak_src,
-                         "bytes_per_env_step": B_ALG, "env_steps_per_launch": n * steps_per_launch,
-                         "avg_launch_ms": per_launch_s * 1e3},
-            "episode_stats": stats_all or stats,
+            "gpu_launches": main["launches"],
+            "collective_us": main["collective_us"],
+            "roofline": main["roofline"],
+            "legs": legs,
+            "episode_stats": main["episode_stats"],
         }
         try:
             if args.skip_cpu:
@@ -360,9 +603,9 @@ def finish(args, env, world, rank, n, K, W, T, fused_ms, kernel_ms, launches, cl
         except Exception as exc:  # the oracle is test infrastructure; its absence must not hide the GPU numbers
             line["cpu_baseline"] = {"value": None, "unit": "env-steps/s", "cores": 0, "kind": "port", "sample": "failed: %s" % exc}
         emit(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    if ctx.world > 1:
+        ctx.dist.barrier()
+        ctx.dist.destroy_process_group()
 
 
 def main():

@@ -6,7 +6,7 @@ import pytest
 import torch
 import torch.multiprocessing as mp
 
-from wab_gym_b200.sharding import reduce_stats, shard_range
+from wab_gym_b200.sharding import AsyncStatsReducer, reduce_stats, shard_range
 
 
 def test_shard_ranges_tile_the_batch():
@@ -28,6 +28,11 @@ def _worker(rank, world, port, out):
     first, count = shard_range(1000, rank, world)
     local = torch.tensor([count, 10 * count, rank, 1, 2, 3, 0, first], dtype=torch.int64)
     out[rank] = reduce_stats(local)
+    # the asynchronous form used inside timed regions: several submissions in flight, only the last one is read
+    red = AsyncStatsReducer(torch.device("cpu"))
+    for k in range(1, 4):
+        red.submit(lambda k=k: local * k)
+    out[100 + rank] = red.result()
     dist.barrier()
     dist.destroy_process_group()
 
@@ -42,3 +47,11 @@ def test_stats_all_reduce_gloo_world_size_2():
     assert out[0] == out[1]
     assert out[0]["episodes"] == 1000 and out[0]["steps"] == 10000 and out[0]["finished"] == 1
     assert out[0]["overflows"] == 500 and out[0]["starved"] == 2
+    assert out[100] == out[101] and out[100]["episodes"] == 3000 and out[100]["killed"] == 12
+
+
+def test_async_reducer_without_process_group_returns_local_stats():
+    red = AsyncStatsReducer(torch.device("cpu"))
+    assert red.result() is None
+    red.submit(lambda: torch.arange(8, dtype=torch.int64))
+    assert red.result()["steps"] == 1 and red.submitted == 1

@@ -5,6 +5,8 @@ fails loudly. Nothing here (or anywhere in this package) imports ``oracle/``.
 """
 import ctypes
 import os
+import shutil
+import warnings
 
 from . import build as _build
 from .config import WabConfigStruct
@@ -16,7 +18,7 @@ EXPORTS = [
     "wab_vec_reset_host", "wab_vec_stats", "wab_vec_stats_device", "wab_vec_export_state", "wab_vec_num_envs", "wab_vec_lanes_per_env",
     "wab_vec_destroy", "wab_philox_device", "wab_vec_bind_features", "wab_pragmatic_features",
     "wab_vec_flatten_features", "wab_vec_flatten_features_noisy", "wab_sample_categorical", "wab_vec_flat_dim", "wab_vec_host_block_layout", "wab_vec_step_host_packed",
-    "wab2_create", "wab2_reset", "wab2_turn", "wab2_export_state", "wab2_destroy", "wab_last_error", "wab_abi_version",
+    "wab2_create", "wab2_kernel_kind", "wab2_reset", "wab2_turn", "wab2_export_state", "wab2_destroy", "wab_last_error", "wab_abi_version",
 ]
 
 
@@ -43,6 +45,10 @@ def load():
         except Exception as exc:  # no nvcc on this box: only acceptable if a prebuilt library travelled here
             if not os.path.exists(path):
                 raise ImportError("libwab_b200.so is missing and could not be built: %s" % exc) from exc
+            if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
+                raise ImportError("libwab_b200.so is older than its sources and the rebuild failed: %s" % exc) from exc
+            warnings.warn("libwab_b200.so is older than its sources and there is no nvcc here to rebuild it; "
+                          "loading the prebuilt library")
     L = ctypes.CDLL(path)
     vp, i32, i64, u64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64
     L.wab_vec_create.argtypes = [ctypes.POINTER(WabConfigStruct), vp, i32, i64, u64, u64, i32, ctypes.POINTER(vp)]
@@ -74,6 +80,7 @@ def load():
     L.wab2_turn.argtypes = [vp] * 7
     L.wab2_export_state.argtypes = [vp] * 4
     L.wab2_destroy.argtypes = [vp]
+    L.wab2_kernel_kind.argtypes = [vp]
     L.wab2_destroy.restype = None
     L.wab_philox_device.argtypes = [vp, ctypes.c_uint32, ctypes.c_uint32, i64, vp, vp]
     L.wab_last_error.restype = ctypes.c_char_p

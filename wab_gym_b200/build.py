@@ -4,6 +4,7 @@ The library is plain CUDA C++ behind the C ABI of ``include/wab_b200.h``; it lin
 direct ``nvcc -shared`` is the whole build (no torch headers, no JIT cache). ``python -m
 wab_gym_b200.build`` or ``__graft_entry__.build()`` runs it; nvcc cross-compiles without a GPU.
 """
+import glob
 import os
 import shutil
 import subprocess
@@ -13,8 +14,14 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libwab_b200.so")
 SOURCES = [os.path.join(CSRC, "wab_kernels.cu")]
-HEADERS = [os.path.join(CSRC, "wab_core.cuh"), os.path.join(CSRC, "wab_params.h"),
-           os.path.join(os.path.dirname(PKG_DIR), "include", "wab_b200.h")]
+
+
+def headers():
+    """Every header the translation unit can see: an edit to any of them makes the library stale."""
+    inc = os.path.join(os.path.dirname(PKG_DIR), "include")
+    return sorted(glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) +
+                  glob.glob(os.path.join(inc, "*.h")))
+
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -35,7 +42,7 @@ def is_stale():
     if not os.path.exists(LIB_PATH):
         return True
     built = os.path.getmtime(LIB_PATH)
-    return any(os.path.getmtime(p) > built for p in SOURCES + HEADERS)
+    return any(os.path.getmtime(p) > built for p in SOURCES + headers())
 
 
 def build(force=False, verbose=False):

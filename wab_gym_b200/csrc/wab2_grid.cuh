@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(128) wab2_grid_turn_kernel(const __grid_consta
                     __syncwarp();
                     if (at == T_WOLF) {
                         const uint32_t jt = tab[j];
+                        __syncwarp();              // every lane holds the old row of label j before lane 0 rewrites it
                         if (lane == 0) {
                             food[a] += (uint32_t)P.wolf_eat_gain;                                  // :113
                             tab[pick] = (tab[pick] & ~(3u << 18)) | (2u << 18);                    // :114 killed

@@ -215,6 +215,8 @@ void wab2_destroy(Wab2World* h) {
     delete h;
 }
 
+int wab2_kernel_kind(const Wab2World* h) { return h && h->grid ? 1 : 0; }
+
 int wab2_reset(Wab2World* h, void* stream) {
     if (!h) return fail(WAB_E_NULL, "null argument");
     DeviceGuard guard(h->device);

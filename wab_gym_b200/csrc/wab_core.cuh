@@ -124,6 +124,28 @@ WAB_HD uint32_t group_or(const Coop<LPE>& c, uint32_t v) {
 #endif
 }
 
+// The lanes of a group run the scalar rules redundantly on ONE env whose wolf slots (shared memory) and depletion
+// log (global memory) they share. Stores of a value every lane computes identically are benign; read-modify-write
+// updates are not (a lane running ahead would be seen by a lagging one — independent thread scheduling gives no
+// lockstep guarantee), so those are made by the group's first lane only, fenced by group_sync on both sides.
+template <int LPE>
+WAB_HD void group_sync(const Coop<LPE>& c) {
+#if defined(__CUDA_ARCH__)
+    if (LPE > 1) __syncwarp(c.gmask);
+#else
+    (void)c;
+#endif
+}
+template <int LPE>
+WAB_HD bool group_leader(const Coop<LPE>& c) { return LPE == 1 || c.sub == 0u; }
+
+WAB_HD uint32_t popc32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__popc(v);
+#else
+    return (uint32_t)__builtin_popcount(v);
+#endif
+}
 WAB_HD uint32_t pack_xy(int32_t x, int32_t y) { return ((uint32_t)x & 0xFFFFu) | ((uint32_t)y << 16); }
 WAB_HD int32_t unpack_x(uint32_t p) { return (int32_t)(int16_t)(p & 0xFFFFu); }
 WAB_HD int32_t unpack_y(uint32_t p) { return (int32_t)(int16_t)(p >> 16); }
@@ -449,13 +471,17 @@ WAB_HD void env_step(const Params& P, Env& E, const Slots& S, uint32_t action, S
             philox(P, E.env_id, E.episode, ctr2(SITE_DESP, E.turn, rank >> 2), p, w);
             if ((uint64_t)pick4(w, rank & 3u) >= P.thr_keep) keepmask |= 1u << k;
         }
-        WAB_ROLLED
-        for (uint32_t k = 0; k < E.nw; ++k)
-            if ((keepmask >> k) & 1u) {
-                S.wolves[(int32_t)kept * S.wstride] = S.wolves[(int32_t)k * S.wstride];
-                ++kept;
-            }
-        E.nw = kept;
+        group_sync(coop);                       // every lane of the group has read the slots
+        if (group_leader(coop)) {
+            WAB_ROLLED
+            for (uint32_t k = 0; k < E.nw; ++k)
+                if ((keepmask >> k) & 1u) {
+                    S.wolves[(int32_t)kept * S.wstride] = S.wolves[(int32_t)k * S.wstride];
+                    ++kept;
+                }
+        }
+        group_sync(coop);
+        E.nw = popc32(keepmask);
     }
 
     // ---- :266 the frame the rest of the step reads: bushes with food > 0, ostrich status
@@ -474,13 +500,15 @@ WAB_HD void env_step(const Params& P, Env& E, const Slots& S, uint32_t action, S
             const int32_t sx = (ddx > 0) - (ddx < 0), sy = (ddy > 0) - (ddy < 0);
             wx += (ax >= ay) ? sx : 0;                                           // :278-280
             wy += (ax < ay) ? sy : 0;                                            // :281-283
-            S.wolves[(int32_t)k * S.wstride] = pack_xy(wx, wy);                  // :285-286
+            group_sync(coop);                                                    // all lanes hold the old position
+            if (group_leader(coop)) S.wolves[(int32_t)k * S.wstride] = pack_xy(wx, wy);   // :285-286
             ddx = E.x - wx; ddy = E.y - wy;
         }
         if (ddx == 0 && ddy == 0 && !P.god_mode) E.status = 2u;                  // :292-297
         if (ddx >= -HALF && ddx <= HALF && ddy >= -HALF && ddy <= HALF)          // :416-427
             setbit128(O.wm, 11 * (ddx + HALF) + (ddy + HALF), 1u);
     }
+    if (E.nw && P.wolves_can_move) group_sync(coop);                             // moved positions published to the group
 
     // ---- :300-313 eat (bush and status as of the frame above; role is fresh)
     O.ate = 0;
@@ -501,7 +529,9 @@ WAB_HD void env_step(const Params& P, Env& E, const Slots& S, uint32_t action, S
         uint32_t eats;
         if (l >= 0) {
             eats = (uint32_t)S.logcnt[(int64_t)l * S.lstride] + 1u;
-            S.logcnt[(int64_t)l * S.lstride] = (uint8_t)eats;
+            group_sync(coop);                      // every lane of the group has read the old count
+            if (group_leader(coop)) S.logcnt[(int64_t)l * S.lstride] = (uint8_t)eats;
+            group_sync(coop);
         } else if (E.nlog < (uint32_t)P.log_cap) {
             eats = 1u;
             S.logcell[(int64_t)E.nlog * S.lstride] = cell;

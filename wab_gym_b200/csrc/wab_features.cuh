@@ -31,14 +31,6 @@ constexpr uint32_t dirmask_word(int dir, int w) {
 }
 template <int D, int W> struct DirMask { static constexpr uint32_t v = dirmask_word(D, W); };
 
-WAB_HD uint32_t popc32(uint32_t v) {
-#if defined(__CUDA_ARCH__)
-    return (uint32_t)__popc(v);
-#else
-    return (uint32_t)__builtin_popcount(v);
-#endif
-}
-
 WAB_HD uint32_t pack4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return a | (b << 8) | (c << 16) | (d << 24); }
 
 // _get_num_things_each_direction (wab_env.py:812-824), clipped at 10 (:734); bytes [up, right, down, left]

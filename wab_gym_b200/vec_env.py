@@ -118,7 +118,12 @@ class VecEnv:
         if actions.device != self.device:
             actions = actions.to(self.device, non_blocking=True)
         if actions.dtype != torch.uint8:
-            actions = actions.to(torch.uint8)  # values >= n_actions (or negative, wrapped) are counted as bad
+            # the reference raises IndexError for anything outside 0..n_actions-1 (wab_env.py:253); a batch cannot, so
+            # such values become 255 — a bad action: the env does not move and stats()['bad_actions'] counts it —
+            # BEFORE the narrowing cast (which would otherwise wrap 256 to 0, -252 to 4, ...)
+            if actions.dtype.is_floating_point or actions.dtype == torch.bool:
+                raise TypeError("actions must be an integer tensor")
+            actions = torch.where((actions < 0) | (actions >= self.n_actions), 255, actions).to(torch.uint8)
         return actions.contiguous()
 
     # ------------------------------------------------------------------ gym-like surface

@@ -94,6 +94,9 @@ class VecWorld2:
                                       _ptr(self.done), self._stream()))
         return self.planes, self.internal, self.reward, self.done.view(torch.bool)
 
+    def kernel_name(self) -> str:
+        return "wab2_grid_turn_kernel (warp per world)" if self.lib.wab2_kernel_kind(self._h) else "wab2_turn_kernel (thread per world)"
+
     def export_state(self):
         out = np.zeros((self.num_envs, self.n_entities, 9), dtype=np.int32)
         turn = np.zeros(self.num_envs, dtype=np.int32)
