@@ -220,6 +220,10 @@ int wab2_turn(Wab2World *h, const uint8_t *d_actions, uint8_t *d_planes, int32_t
               uint8_t *d_done, void *stream);
 /* Hidden state for tests: out9 i32[N][E][9] = type, x, y, table X, table Y, Visible, food, role, status. Synchronises. */
 int wab2_export_state(Wab2World *h, int32_t *out9, int32_t *turn, void *stream);
+/* The inverse of wab2_export_state (tests: the reference's own known-answer worlds, World_tests.py:5-88, are built
+ * from explicit positions): in9 i32[N][E][9] in the export layout (the type column must match the handle's entity
+ * order: ostriches, wolves, bushes); turn i32[N] or NULL (unchanged). Synchronises. */
+int wab2_import_state(Wab2World *h, const int32_t *in9, const int32_t *turn, void *stream);
 /* Which kernel serves this handle: 0 = wab2_turn_kernel (one thread per world), 1 = wab2_grid_turn_kernel (one
  * warp per world with occupancy planes, for worlds every observation window fits once). Results are identical. */
 int wab2_kernel_kind(const Wab2World *h);

@@ -193,3 +193,70 @@ void wab2_oracle_get_state(const Wab2OracleWorld *w, double *out) {
     }
 }
 int32_t wab2_oracle_turn(const Wab2OracleWorld *w) { return w->turn; }
+
+/* Test hook, the inverse of wab2_oracle_get_state: 9 doubles per entity (the type column is ignored). */
+void wab2_oracle_set_state(Wab2OracleWorld *w, const double *in, int32_t turn) {
+    for (int32_t i = 0; i < w->n; ++i) {
+        Ent *e = &w->e[i];
+        const double *o = in + 9 * i;
+        e->x = (int32_t)o[1]; e->y = (int32_t)o[2]; e->tx = (int32_t)o[3]; e->ty = (int32_t)o[4]; e->visible = (int32_t)o[5];
+        e->food = o[6]; e->role = (int32_t)o[7]; e->status = (int32_t)o[8];
+    }
+    w->turn = turn; w->acted = 0;
+}
+
+/* Batch run for size-independent parity checks (the v2 counterpart of wab_oracle_run): n_envs worlds with ids
+ * env_id_base .. +n_envs-1, `episodes` x (reset_environment + `turns` world turns) driven the way the reference
+ * driver loop drives one world (Env2Tests.py:46-88): for every entity in id order get_obs(i) (acting entities
+ * only: ostriches and wolves; bushes act with 0) then take_action(i, a). actions u8[episodes*turns][A][n_envs]
+ * (entity-major, the layout of wab2_turn). Returns in out2:
+ *   [0] sum over every acting-entity action of (a + 1) * (sum_k planes[k] * (k + 1) + 7 x + 11 y + 13 food + 17 role
+ *       + 19 status + 23 reward + 29 done)        (planes with window radius R, internal obs as integers)
+ *   [1] sum over worlds and entities k of (k + 1) * (x + 3 y + 5 X + 7 Y + 11 Visible + 13 food + 17 role + 19 status)
+ *       of the final entity tables.
+ * The return value is the number of world turns executed. */
+#include <omp.h>
+int64_t wab2_oracle_run(const Wab2OracleConfig *cfg, uint64_t seed, uint64_t env_id_base, int64_t n_envs, int32_t episodes,
+                        int32_t turns, const uint8_t *actions, int32_t R, int32_t n_threads, int64_t *out2) {
+    const int32_t A = cfg->n_ostriches + cfg->n_wolves, n = A + cfg->n_bushes, S = 2 * R + 1;
+    int64_t cs_turns = 0, cs_state = 0, done_turns = 0;
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#pragma omp parallel reduction(+ : cs_turns, cs_state, done_turns)
+    {
+        uint8_t *planes = (uint8_t *)malloc((size_t)(3 * S * S));
+        double *st = (double *)malloc(sizeof(double) * 9 * (size_t)n);
+#pragma omp for schedule(dynamic, 16)
+        for (int64_t e = 0; e < n_envs; ++e) {
+            Wab2OracleWorld *w = wab2_oracle_create(cfg, seed, env_id_base + (uint64_t)e);
+            for (int32_t ep = 0; ep < episodes; ++ep) {
+                wab2_oracle_reset(w);
+                for (int32_t t = 0; t < turns; ++t) {
+                    const uint8_t *act = actions + ((size_t)(ep * turns + t) * (size_t)A) * (size_t)n_envs;
+                    for (int32_t i = 0; i < n; ++i) {
+                        int64_t c = 0;
+                        if (i < A) {
+                            double in5[5];
+                            wab2_oracle_get_obs(w, i, R, planes, in5);
+                            for (int32_t k = 0; k < 3 * S * S; ++k) c += (int64_t)planes[k] * (k + 1);
+                            c += 7 * (int64_t)in5[0] + 11 * (int64_t)in5[1] + 13 * (int64_t)in5[2] + 17 * (int64_t)in5[3] + 19 * (int64_t)in5[4];
+                        }
+                        double reward; int32_t done;
+                        wab2_oracle_take_action(w, i, i < A ? (int32_t)act[(size_t)i * (size_t)n_envs + (size_t)e] : 0, &reward, &done);
+                        if (i < A) cs_turns += (int64_t)(i + 1) * (c + 23 * (int64_t)reward + 29 * (int64_t)done);
+                    }
+                    done_turns += 1;
+                }
+            }
+            wab2_oracle_get_state(w, st);
+            for (int32_t k = 0; k < n; ++k) {
+                const double *o = st + 9 * k;
+                cs_state += (int64_t)(k + 1) * ((int64_t)o[1] + 3 * (int64_t)o[2] + 5 * (int64_t)o[3] + 7 * (int64_t)o[4] + 11 * (int64_t)o[5] +
+                                                13 * (int64_t)o[6] + 17 * (int64_t)o[7] + 19 * (int64_t)o[8]);
+            }
+            wab2_oracle_destroy(w);
+        }
+        free(planes); free(st);
+    }
+    out2[0] = cs_turns; out2[1] = cs_state;
+    return done_turns;
+}

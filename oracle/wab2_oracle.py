@@ -49,6 +49,10 @@ def _lib():
         L.wab2_oracle_get_obs.restype = ctypes.c_int32
         L.wab2_oracle_get_obs.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
         L.wab2_oracle_get_state.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.wab2_oracle_set_state.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32]
+        L.wab2_oracle_run.restype = ctypes.c_int64
+        L.wab2_oracle_run.argtypes = [ctypes.POINTER(Config2), ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int32,
+                                      ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]
         L.wab2_oracle_turn.restype = ctypes.c_int32
         L.wab2_oracle_turn.argtypes = [ctypes.c_void_p]
         _ready = True
@@ -90,6 +94,28 @@ class OracleWorld2:
         _lib().wab2_oracle_get_state(self._h, out.ctypes.data)
         return out
 
+    def set_state(self, state9, turn=0):
+        """Test hook: overwrite every entity (layout of ``state()``); the reference's KAT worlds are built this way."""
+        st = np.ascontiguousarray(state9, dtype=np.float64)
+        assert st.shape == (self.n, 9)
+        _lib().wab2_oracle_set_state(self._h, st.ctypes.data, int(turn))
+
     @property
     def turn(self):
         return _lib().wab2_oracle_turn(self._h)
+
+
+def run(width, height, n_ostriches, n_wolves, n_bushes, game_options, seed, env_id_base, n_envs, episodes, turns, actions,
+        window_radius=None, threads=0):
+    """Batch checksum run (see ``wab2_oracle_run`` in wab2_oracle.c): ``actions`` u8[episodes*turns, A, n_envs].
+    Returns (world turns executed, checksum of every observation/reward/done, checksum of the final entity tables)."""
+    import os
+    cfg = make_config(width, height, n_ostriches, n_wolves, n_bushes, game_options)
+    R = window_radius if window_radius is not None else max(cfg.lookout_view_radius, cfg.gatherer_view_radius, cfg.wolf_view_radius)
+    a = np.ascontiguousarray(actions, dtype=np.uint8)
+    assert a.shape == (episodes * turns, n_ostriches + n_wolves, n_envs), a.shape
+    if threads <= 0:
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    out = np.zeros(2, dtype=np.int64)
+    done = _lib().wab2_oracle_run(ctypes.byref(cfg), seed, env_id_base, n_envs, episodes, turns, a.ctypes.data, R, threads, out.ctypes.data)
+    return int(done), int(out[0]), int(out[1])

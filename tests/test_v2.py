@@ -24,11 +24,17 @@ def actions_for(rng, no, nw, n):
     return [rng.randint(0, 5) if i < no else (rng.randint(0, 4) if i < no + nw else 0) for i in range(n)]
 
 
-def record_reference(world, episodes, turns):
+def window_radius(game_options=None):
+    o = {"lookout_view_radius": 9, "gatherer_view_radius": 5, "wolf_view_radius": 6}
+    o.update({k: v for k, v in (game_options or {}).items() if k in o})
+    return max(o.values())
+
+
+def record_reference(world, episodes, turns, game_options=None):
     """Run the real reference and record everything the other implementations are compared with."""
     W, H, no, nw, nb, seed, env_id = world
-    ref = ref_v2.make_env(W, H, no, nw, nb, seed=seed, env_id=env_id)
-    n, R = no + nw + nb, 9
+    ref = ref_v2.make_env(W, H, no, nw, nb, game_options=game_options, seed=seed, env_id=env_id)
+    n, R = no + nw + nb, window_radius(game_options)
     S = 2 * R + 1
     rng = random.Random(seed)
     rec = {"actions": [], "planes": [], "rows": [], "internal": [], "reward": [], "done": [], "state": []}
@@ -56,11 +62,11 @@ def record_reference(world, episodes, turns):
     return {k: np.asarray(v) for k, v in rec.items()}
 
 
-def replay(world, rec, make, episodes, turns, exact_float=True):
+def replay(world, rec, make, episodes, turns, exact_float=True, game_options=None):
     """Drive an implementation with the recorded actions and compare everything."""
     W, H, no, nw, nb, seed, env_id = world
-    impl = make(W, H, no, nw, nb, seed=seed, env_id=env_id)
-    n, R = no + nw + nb, 9
+    impl = make(W, H, no, nw, nb, game_options=game_options, seed=seed, env_id=env_id)
+    n, R = no + nw + nb, window_radius(game_options)
     S = 2 * R + 1
 
     def state():

@@ -269,4 +269,31 @@ int wab2_export_state(Wab2World* h, int32_t* out9, int32_t* turn, void* stream) 
     return WAB_OK;
 }
 
+int wab2_import_state(Wab2World* h, const int32_t* in9, const int32_t* turn, void* stream) {
+    if (!h || !in9) return fail(WAB_E_NULL, "null argument");
+    DeviceGuard guard(h->device);
+    WAB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    const size_t n = (size_t)h->n;
+    const int E = h->P.n_entities;
+    const size_t sw = (size_t)h->st.stride_word, si = (size_t)h->st.stride_world;
+    uint32_t* ent = new uint32_t[n * 3 * E];
+    int bad = 0;
+    for (size_t i = 0; i < n && !bad; ++i)
+        for (int k = 0; k < E; ++k) {
+            const int32_t* o = in9 + (i * E + k) * 9;
+            if (o[0] != (int32_t)entity_type(h->P, k) || o[3] < 0 || o[3] > 255 || o[4] < 0 || o[4] > 255 || o[6] < 0 ||
+                o[1] < -32768 || o[1] > 32767 || o[2] < -32768 || o[2] > 32767) { bad = 1; break; }
+            ent[(size_t)(3 * k) * sw + i * si] = pack_xy(o[1], o[2]);
+            ent[(size_t)(3 * k + 1) * sw + i * si] = tab_pack((uint32_t)o[3], (uint32_t)o[4], o[5] ? 1u : 0u, (uint32_t)o[7] & 1u, (uint32_t)o[8] & 3u);
+            ent[(size_t)(3 * k + 2) * sw + i * si] = (uint32_t)o[6];
+        }
+    cudaError_t e = cudaSuccess;
+    if (!bad) e = cudaMemcpy(h->st.ent, ent, 4 * n * 3 * E, cudaMemcpyHostToDevice);
+    if (!bad && e == cudaSuccess && turn) e = cudaMemcpy(h->st.turn, turn, 4 * n, cudaMemcpyHostToDevice);
+    delete[] ent;
+    if (bad) return fail(WAB_E_CONFIG, "wab2_import_state: entity type order or value range does not fit the handle");
+    if (e != cudaSuccess) return cuda_fail(e, "wab2_import_state");
+    return WAB_OK;
+}
+
 }  // extern "C"

@@ -103,6 +103,14 @@ class VecWorld2:
         _lib.check(self.lib.wab2_export_state(self._h, out.ctypes.data, turn.ctypes.data, self._stream()))
         return out, turn
 
+    def import_state(self, state9: np.ndarray, turn: Optional[np.ndarray] = None):
+        """Inverse of ``export_state`` (tests): ``state9`` i32[N, E, 9] = type, x, y, table X, table Y, Visible, food, role, status."""
+        st = np.ascontiguousarray(state9, dtype=np.int32)
+        if st.shape != (self.num_envs, self.n_entities, 9):
+            raise ValueError("state9 must have shape (num_envs, n_entities, 9)")
+        tn = None if turn is None else np.ascontiguousarray(turn, dtype=np.int32)
+        _lib.check(self.lib.wab2_import_state(self._h, st.ctypes.data, None if tn is None else tn.ctypes.data, self._stream()))
+
     def close(self):
         if getattr(self, "_h", None):
             self.lib.wab2_destroy(self._h)
