@@ -323,17 +323,22 @@ def v1_fused_leg(ctx, n, K, W, T, min_ms, with_collective):
     from wab_gym_b200 import VecEnv
     from wab_gym_b200.sharding import AsyncStatsReducer
     env = VecEnv(n, seed=ctx.args.seed, device=ctx.dev, env_id_base=ctx.rank * n)
-    chunks = [(s, min(T, K - s)) for s in range(0, K, T)]                 # launches of one pass
-    slots = max(1, int(math.ceil(RING_BYTES / float(T * n * 372))))       # output ring > 2 x L2
-    passes = max(1, int(math.ceil(slots / float(len(chunks)))))           # passes per graph
-    ring = [env._alloc(T) for _ in range(slots)]
+    # Launches of <= T steps. K >= T: a pass of K steps is cut into chunks of T. K < T: a launch carries m = T // K whole
+    # passes (the K steps replayed m times inside ONE launch of the multi-step kernel, actions differing per pass).
+    m = max(1, T // K) if K < T else 1
+    L = m * K if K < T else T                                             # steps per full launch
+    chunks = [(s, min(L, m * K - s)) for s in range(0, m * K, L)]         # launches of one unit of m passes
+    slots = max(1, int(math.ceil(RING_BYTES / float(L * n * 372))))       # output ring > 2 x L2
+    units = max(1, int(math.ceil(slots / float(len(chunks)))))            # units per graph
+    passes = units * m
+    ring = [env._alloc(L) for _ in range(slots)]
     gen = torch.Generator(device=ctx.dev).manual_seed(1 + ctx.rank)
     actions = torch.randint(0, env.n_actions, (passes * K + W, n), dtype=torch.uint8, device=ctx.dev, generator=gen)
     env.reset()
-    for s in range(0, W, T):                                              # W untimed warm-up steps
-        c = min(T, W - s)
+    for s in range(0, W, L):                                              # W untimed warm-up steps
+        c = min(L, W - s)
         env.step_many(actions[passes * K + s:passes * K + s + c], out={k: v[:c] for k, v in ring[0].items()})
-    launches = [(p * K + s, c) for p in range(passes) for (s, c) in chunks]
+    launches = [(u * m * K + s, c) for u in range(units) for (s, c) in chunks]
 
     def enqueue(j):
         s, c = launches[j]
@@ -388,7 +393,7 @@ def v1_fused_leg(ctx, n, K, W, T, min_ms, with_collective):
             "repeats": repeats * passes, "steps_per_pass": K, "steps_per_launch": steps_per_launch, "launches": n_launch,
             "ms_per_step": window_ms / total_steps, "num_envs_per_gpu": n, "global_envs": ctx.world * n,
             "ring": "%d output buffers of %d MB (ring of %d MB > 2 x L2), rotated per launch" % (
-                slots, int(T * n * 372 / 1e6), int(slots * T * n * 372 / 1e6)),
+                slots, int(L * n * 372 / 1e6), int(slots * L * n * 372 / 1e6)),
             "roofline": roof, "collective_us": collective_us,
             "collectives_in_window": (reducer.submitted - 2) if reducer is not None else 0,
             "episode_stats": stats_all or stats}
@@ -535,7 +540,7 @@ def e2e_leg(ctx, n, K, W):
 def run_ours(args):
     ctx = Ctx(args)
     torch = ctx.torch
-    n, K, W, T = args.num_envs, args.steps, max(args.warmup, 3), max(1, min(args.fuse, args.steps))
+    n, K, W, T = args.num_envs, args.steps, max(args.warmup, 3), max(1, args.fuse)
     want = ALL_LEGS if args.legs == "all" else tuple(x for x in args.legs.split(",") if x in ALL_LEGS)
 
     with ClockSampler(ctx.local_rank) as clocks:
@@ -544,10 +549,10 @@ def run_ours(args):
     percall = v1_percall_leg(ctx, n, K, W, args.leg_window_ms)
 
     legs = {}
-    Kl = min(K, 32)        # the big-batch legs bound their output ring: <= 32 steps per launch
+    # the big-batch legs bound their output buffer: <= 64 steps per launch at 131,072 envs (3.1 GB), <= 8 at 1M envs
     plan = {
-        "large_batch": lambda: v1_fused_leg(ctx, 131072, Kl, W, Kl, args.leg_window_ms, with_collective=False),
-        "batch_1m": lambda: v1_fused_leg(ctx, 1048576, min(K, 8), W, min(K, 8), args.leg_window_ms, with_collective=False),
+        "large_batch": lambda: v1_fused_leg(ctx, 131072, min(K, 64), W, 64, args.leg_window_ms, with_collective=False),
+        "batch_1m": lambda: v1_fused_leg(ctx, 1048576, min(K, 8), W, 8, args.leg_window_ms, with_collective=False),
         "v2_config3": lambda: v2_leg(ctx, 65536, (20, 20, 10, 3, 20), args.leg_window_ms, "configs[2]"),
         "v2_config4": lambda: v2_leg(ctx, 131072, (64, 64, 8, 64, 256), args.leg_window_ms, "configs[3] (8-GPU share of 1,048,576)"),
         "rollout_fp32": lambda: rollout_leg(ctx, 32768, K, args.leg_window_ms),
@@ -574,8 +579,9 @@ def run_ours(args):
             "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8 grids / int32 rules / u32 Philox (int food counter proven == f64)",
             "data": "synthetic", "config": config_dict(n, ctx.world),
-            "timing": {"mode": "wab_vec_step_many, %g steps per launch, every step's obs/reward/done written; the K steps "
-                               "replayed %d times for a %.0f ms window" % (main["steps_per_launch"], main["repeats"], main["window_ms"]),
+            "timing": {"mode": "wab_vec_step_many, %g steps per launch (= %g passes of the K steps in one launch of the multi-step "
+                               "kernel), every step's obs/reward/done written; the K steps replayed %d times for a %.0f ms window" % (
+                                   main["steps_per_launch"], main["steps_per_launch"] / K, main["repeats"], main["window_ms"]),
                        "l2": main["ring"] + "; state lives in registers, no reuse between steps",
                        "collective": "64-byte statistics all-reduce on a side stream, %d issued inside the window, none awaited "
                                      "before the stop event" % main["collectives_in_window"]},

@@ -59,7 +59,7 @@ def test_cuda_feature_kernels_match_the_live_wrapper_outputs():
     want = np.zeros((n, 449), dtype=np.float32)
     col = 0
     for k, d in enumerate(dims):
-        want[np.arange(n), col + feats[:, k]] = 1
+        want[np.arange(n), col + feats[:, k].astype(np.int64)] = 1
         col += d
     assert col == 328 and np.array_equal(flat, want)                 # the last 121 columns (view mask) are zero without restrict_view
     env.close()

@@ -65,7 +65,8 @@ struct StatePtrs {
     uint32_t* wolves;    // [wolf_cap][N]
     uint32_t* logcell;   // [log_cap][N]
     uint8_t* logcnt;     // [log_cap][N]
-    unsigned long long* stats;  // [8]
+    unsigned long long* stats;  // [8]  totals, refreshed by wab_stats_reduce_kernel when somebody asks
+    unsigned long long* wstats; // [warps of the grid][8]  every warp accumulates into its own row: no atomics, no barrier
     int64_t n;
 };
 
@@ -181,6 +182,9 @@ __device__ __forceinline__ void stream_put(uint32_t* stream, int bit0, bool last
 
 // gA = 16-byte aligned address of stream bit 0; valid bits are [off, end).
 // `lut` = 256 x uint2 in shared memory: byte value -> its 8 bits as 8 bytes (built once per CTA).
+// USE_LUT = false expands with two multiplies per 8 bytes instead (the lanes-per-env kernels: few chunks per step, and no
+// table means no CTA barrier anywhere in a single-step launch).
+template <bool USE_LUT = true>
 __device__ __forceinline__ void stream_flush(const uint32_t* stream, const uint2* lut, uint8_t* gA, int off, int end,
                                              int lane) {
     const uint16_t* hs = reinterpret_cast<const uint16_t*>(stream);
@@ -188,7 +192,13 @@ __device__ __forceinline__ void stream_flush(const uint32_t* stream, const uint2
 #pragma unroll kFlushUnroll
     for (int c = c_lo + lane; c < c_hi; c += 32) {
         const uint32_t h = hs[c];
-        const uint2 lo = lut[h & 0xFFu], hi = lut[h >> 8];
+        uint2 lo, hi;
+        if (USE_LUT) {
+            lo = lut[h & 0xFFu]; hi = lut[h >> 8];
+        } else {
+            lo = make_uint2(nibble_to_bytes(h & 15u), nibble_to_bytes((h >> 4) & 15u));
+            hi = make_uint2(nibble_to_bytes((h >> 8) & 15u), nibble_to_bytes(h >> 12));
+        }
 #ifndef WAB_EXP_NOSTORE
         __stcs(reinterpret_cast<uint4*>(gA) + c, make_uint4(lo.x, lo.y, hi.x, hi.y));
 #else
@@ -222,18 +232,39 @@ __device__ __forceinline__ void write_features(uint8_t* features, int64_t o, con
     for (int k = 0; k < 7; ++k) dst[k] = f[k];
 }
 
-__device__ __forceinline__ void flush_stats(unsigned long long* stats, const uint32_t c[8], uint32_t* block_s) {
-    // warp redux -> shared atomics -> 8 global atomics per block
-    if (threadIdx.x < 8) block_s[threadIdx.x] = 0u;
-    __syncthreads();
+__device__ __forceinline__ void flush_stats(unsigned long long* wstats, const uint32_t c[8]) {
+    // warp redux, then lane k adds total k to the warp's own row (one 64-byte read-modify-write, exclusive to this warp)
+    const int lane = threadIdx.x & 31;
+    uint32_t mine = 0u;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const uint32_t s = __reduce_add_sync(FULL, c[k]);
-        if ((threadIdx.x & 31) == 0 && s) atomicAdd(&block_s[k], s);
+        mine = lane == k ? s : mine;
     }
-    __syncthreads();
-    if (threadIdx.x < 8 && block_s[threadIdx.x]) atomicAdd(&stats[threadIdx.x], (unsigned long long)block_s[threadIdx.x]);
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (lane < 8 && mine) wstats[warp * 8 + lane] += (unsigned long long)mine;
 }
+
+// totals[k] = sum over warps of wstats[warp][k]; one block per counter
+__global__ void wab_stats_reduce_kernel(const unsigned long long* __restrict__ wstats, int64_t n_warps,
+                                        unsigned long long* __restrict__ totals) {
+    __shared__ unsigned long long part[256];
+    const int k = blockIdx.x;
+    unsigned long long acc = 0ull;
+    for (int64_t w = threadIdx.x; w < n_warps; w += blockDim.x) acc += wstats[w * 8 + k];
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s2 = 128; s2 > 0; s2 >>= 1) {
+        if ((int)threadIdx.x < s2) part[threadIdx.x] += part[threadIdx.x + s2];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) totals[k] = part[0];
+}
+
+// Programmatic dependent launch (sm_90+): consecutive launches of a stream or graph overlap the next launch's
+// scheduling and prologue with this launch's tail. A no-op when the launch carries no programmatic dependency.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ void build_lut(uint2* lut) {
     for (int b = threadIdx.x; b < 256; b += blockDim.x)
@@ -287,7 +318,7 @@ __device__ __forceinline__ void emit_obs(uint32_t* stream, const uint2* lut, con
     if (c.sub == 0)
         stream_put(stream, off + OBS_BYTES * c.slot, c.slot == EPW - 1, total, wm, bm, c.active);
     __syncwarp();
-    stream_flush(stream, lut, grids + (first_byte - off), off, off + OBS_BYTES * c.n_valid, c.lane);
+    stream_flush<LPE == 1>(stream, lut, grids + (first_byte - off), off, off + OBS_BYTES * c.n_valid, c.lane);
     __syncwarp();
 }
 
@@ -304,9 +335,10 @@ wab_step_kernel(const __grid_constant__ Params P, const StatePtrs st, const uint
     const Ctx c = make_ctx<LPE>(n);
     uint32_t* wolves_s = smem + c.env_local;                                  // [wolf_cap][EPB]
     uint32_t* stream = smem + P.wolf_cap * EPB + (threadIdx.x >> 5) * WarpStream<Geo<LPE>::EPW>::WORDS;
-    uint32_t* block_s = smem + P.wolf_cap * EPB + Geo<LPE>::STREAM;            // 8 words
-    uint2* lut = reinterpret_cast<uint2*>(block_s + 8);                        // 256 x 8 bytes
-    build_lut(lut);
+    uint2* lut = reinterpret_cast<uint2*>(smem + P.wolf_cap * EPB + Geo<LPE>::STREAM);   // 256 x 8 bytes (thread-per-env only)
+    pdl_launch_dependents();               // the next launch may be scheduled now; it waits below before touching state
+    if (LPE == 1) build_lut(lut);
+    pdl_wait();                            // everything this launch reads or writes follows the previous launch
     Coop<LPE> coop;
     coop.sub = (uint32_t)c.sub;
     coop.gmask = LPE == 32 ? FULL : (((1u << (LPE & 31)) - 1u) << (c.lane - c.sub));
@@ -368,7 +400,7 @@ wab_step_kernel(const __grid_constant__ Params P, const StatePtrs st, const uint
         cnt[WAB_STAT_BAD_ACTIONS] = (uint32_t)(acc_misc >> 16) & 0xFFFFu;
         cnt[WAB_STAT_OVERFLOWS] = (uint32_t)(acc_misc >> 32) & 0xFFFFu;
     }
-    flush_stats(st.stats, cnt, block_s);
+    flush_stats(st.wstats, cnt);
 }
 
 // reset(mask) + fresh observation of every env
@@ -382,9 +414,10 @@ wab_reset_kernel(const __grid_constant__ Params P, const StatePtrs st, const uin
     const Ctx c = make_ctx<LPE>(n);
     uint32_t* wolves_s = smem + c.env_local;
     uint32_t* stream = smem + P.wolf_cap * EPB + (threadIdx.x >> 5) * WarpStream<Geo<LPE>::EPW>::WORDS;
-    uint32_t* block_s = smem + P.wolf_cap * EPB + Geo<LPE>::STREAM;
-    uint2* lut = reinterpret_cast<uint2*>(block_s + 8);
-    build_lut(lut);
+    uint2* lut = reinterpret_cast<uint2*>(smem + P.wolf_cap * EPB + Geo<LPE>::STREAM);
+    pdl_launch_dependents();
+    if (LPE == 1) build_lut(lut);
+    pdl_wait();
     Env E;
     Slots S;
     S.wolves = wolves_s; S.wstride = EPB;
@@ -411,7 +444,7 @@ wab_reset_kernel(const __grid_constant__ Params P, const StatePtrs st, const uin
         store_env<F64>(st, c.idx, E, wolves_s, EPB);
     }
     emit_obs<LPE>(stream, lut, c, out.grids, c.warp_first * OBS_BYTES, O.wm, O.bm);
-    flush_stats(st.stats, cnt, block_s);
+    flush_stats(st.wstats, cnt);
 }
 
 // PragmaticObsWrapper.observation (wab_env.py:726-761) for an arbitrary observation batch in HBM.
@@ -576,6 +609,7 @@ struct WabVec {
     // device staging for the host-buffer entry points
     uint8_t* stage;
     size_t stage_bytes;
+    int64_t stat_rows; // rows of st.wstats
     int lpe;          // lanes per env chosen at create (see pick_lpe)
     int mb;           // CTAs per SM the thread-per-env kernel is built for (see pick_mb)
     uint8_t* d_features;   // bound feature output, or null
@@ -592,7 +626,7 @@ struct WabVec {
 namespace {
 
 template <int LPE> size_t smem_bytes_for(const Params& P) {
-    return sizeof(uint32_t) * ((size_t)P.wolf_cap * Geo<LPE>::EPB + (size_t)Geo<LPE>::STREAM + 8 + 512);
+    return sizeof(uint32_t) * ((size_t)P.wolf_cap * Geo<LPE>::EPB + (size_t)Geo<LPE>::STREAM + (LPE == 1 ? 512 : 0));
 }
 template <bool F64, int LPE>
 void launch_step_t(const WabVec* h, const uint8_t* a, int T, const OutPtrs& out, cudaStream_t s);
@@ -605,20 +639,38 @@ int check_ptr_align(const void* p, const char* name) {
     return WAB_OK;
 }
 
+// Kernel launch with the programmatic-stream-serialization attribute: back-to-back launches on a stream (or the kernel
+// nodes of a captured graph) overlap the next launch's scheduling and prologue with the tail of the previous one; the
+// kernels order themselves with griddepcontrol.wait. WAB_PDL=0 switches the attribute off (A/B runs).
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("WAB_PDL"); return !(e && atoi(e) == 0); }();
+    return on;
+}
+template <typename... KArgs, typename... Args>
+void launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 template <bool F64, int LPE>
 void launch_step_t(const WabVec* h, const uint8_t* a, int T, const OutPtrs& out, cudaStream_t s) {
     const unsigned grid = (unsigned)((h->n + Geo<LPE>::EPB - 1) / Geo<LPE>::EPB);
     if (LPE == 1 && h->mb == 7)
-        wab_step_kernel<F64, LPE, LPE == 1 ? 7 * kMbScale : Geo<LPE>::MIN_BLOCKS><<<grid, Geo<LPE>::THREADS, smem_bytes_for<LPE>(h->P), s>>>(h->P, h->st, a, T, out);
+        launch_pdl(wab_step_kernel<F64, LPE, LPE == 1 ? 7 * kMbScale : Geo<LPE>::MIN_BLOCKS>, grid, Geo<LPE>::THREADS, smem_bytes_for<LPE>(h->P), s, h->P, h->st, a, T, out);
     else if (LPE == 1 && h->mb == 8)
-        wab_step_kernel<F64, LPE, LPE == 1 ? 8 * kMbScale : Geo<LPE>::MIN_BLOCKS><<<grid, Geo<LPE>::THREADS, smem_bytes_for<LPE>(h->P), s>>>(h->P, h->st, a, T, out);
+        launch_pdl(wab_step_kernel<F64, LPE, LPE == 1 ? 8 * kMbScale : Geo<LPE>::MIN_BLOCKS>, grid, Geo<LPE>::THREADS, smem_bytes_for<LPE>(h->P), s, h->P, h->st, a, T, out);
     else
-        wab_step_kernel<F64, LPE><<<grid, Geo<LPE>::THREADS, smem_bytes_for<LPE>(h->P), s>>>(h->P, h->st, a, T, out);
+        launch_pdl(wab_step_kernel<F64, LPE>, grid, Geo<LPE>::THREADS, smem_bytes_for<LPE>(h->P), s, h->P, h->st, a, T, out);
 }
 template <bool F64, int LPE>
 void launch_reset_t(const WabVec* h, const uint8_t* mask, const OutPtrs& out, cudaStream_t s) {
     const unsigned grid = (unsigned)((h->n + Geo<LPE>::EPB - 1) / Geo<LPE>::EPB);
-    wab_reset_kernel<F64, LPE><<<grid, Geo<LPE>::THREADS, smem_bytes_for<LPE>(h->P), s>>>(h->P, h->st, mask, out);
+    launch_pdl(wab_reset_kernel<F64, LPE>, grid, Geo<LPE>::THREADS, smem_bytes_for<LPE>(h->P), s, h->P, h->st, mask, out);
 }
 // Lanes per env: the largest LPE whose whole grid is co-resident (one wave) on this device, so that a
 // small batch spreads over all SMs and shortens its per-step critical path; large batches use the
@@ -753,6 +805,16 @@ int wab_vec_create(const WabConfig* cfg, const uint32_t* bush_thr, int32_t n_bus
     const size_t o_lcell = o; o = align_up(o + 4 * n * (size_t)cfg->log_cap, 256);
     const size_t o_lcnt = o; o = align_up(o + n * (size_t)cfg->log_cap, 256);
     const size_t o_stats = o; o = align_up(o + 64, 256);
+    // one statistics row per warp of the largest grid this handle launches: its lanes-per-env variant, or thread per
+    // env (which the mapped host path uses whatever the handle's variant is)
+    h->lpe = pick_lpe(h);
+    h->mb = pick_mb(h);
+    auto warps_of = [n](size_t lpe) {
+        const size_t threads = lpe == 1 ? (size_t)WAB_THREADS_LPE1 : (size_t)WAB_THREADS_LPEN, epb = threads / lpe;
+        return (n + epb - 1) / epb * (threads / 32);
+    };
+    const size_t stat_rows = warps_of(1) > warps_of((size_t)h->lpe) ? warps_of(1) : warps_of((size_t)h->lpe);
+    const size_t o_wstats = o; o = align_up(o + 64 * stat_rows, 256);
     cudaError_t e = cudaMalloc(&h->slab, o);
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaMalloc(state)"); }
     uint8_t* base = (uint8_t*)h->slab;
@@ -770,8 +832,7 @@ int wab_vec_create(const WabConfig* cfg, const uint32_t* bush_thr, int32_t n_bus
     st.bush = (uint4*)(base + o_bush); st.nlog = (uint16_t*)(base + o_nlog); st.logsig = (uint32_t*)(base + o_lsig); st.bkey = (uint2*)(base + o_bkey); st.food = (double*)(base + o_food);
     st.wolves = (uint32_t*)(base + o_wolves); st.logcell = (uint32_t*)(base + o_lcell); st.logcnt = base + o_lcnt;
     st.stats = (unsigned long long*)(base + o_stats); st.n = n_envs;
-    h->lpe = pick_lpe(h);
-    h->mb = pick_mb(h);
+    st.wstats = (unsigned long long*)(base + o_wstats); h->stat_rows = (int64_t)stat_rows;
     *out = h;
     return WAB_OK;
 }
@@ -950,8 +1011,10 @@ int wab_vec_stats(WabVec* h, int64_t* h_out8, int32_t clear, void* stream) {
     if (!h || !h_out8) return fail(WAB_E_NULL, "null argument");
     DeviceGuard guard(h->device);
     cudaStream_t s = (cudaStream_t)stream;
+    wab_stats_reduce_kernel<<<8, 256, 0, s>>>(h->st.wstats, h->stat_rows, h->st.stats);
+    WAB_CUDA(cudaGetLastError());
     WAB_CUDA(cudaMemcpyAsync(h_out8, h->st.stats, 64, cudaMemcpyDeviceToHost, s));
-    if (clear) WAB_CUDA(cudaMemsetAsync(h->st.stats, 0, 64, s));
+    if (clear) WAB_CUDA(cudaMemsetAsync(h->st.wstats, 0, 64 * (size_t)h->stat_rows, s));
     WAB_CUDA(cudaStreamSynchronize(s));
     return WAB_OK;
 }
@@ -959,7 +1022,10 @@ int wab_vec_stats(WabVec* h, int64_t* h_out8, int32_t clear, void* stream) {
 int wab_vec_stats_device(WabVec* h, int64_t* d_out8, void* stream) {
     if (!h || !d_out8) return fail(WAB_E_NULL, "null argument");
     DeviceGuard guard(h->device);
-    WAB_CUDA(cudaMemcpyAsync(d_out8, h->st.stats, 64, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    // totals straight into the caller's buffer (the handle's own totals are left alone: this call may run on a side
+    // stream concurrently with wab_vec_stats)
+    wab_stats_reduce_kernel<<<8, 256, 0, (cudaStream_t)stream>>>(h->st.wstats, h->stat_rows, (unsigned long long*)d_out8);
+    WAB_CUDA(cudaGetLastError());
     return WAB_OK;
 }
 
