@@ -62,7 +62,7 @@ typedef struct WabConfig {
     int32_t food_int_start;       /* INT mode: starting_food * turns_to_empty_food                 */
     int32_t food_int_inc;         /* INT mode: turns_to_empty_food / turns_to_fill_food            */
     int32_t food_int_max;         /* INT mode: turns_to_empty_food (clip upper bound)              */
-    int32_t wolf_cap;             /* wolf slots per env (<= 15); overflow is counted, see stats    */
+    int32_t wolf_cap;             /* wolf slots per env (<= 64); overflow is counted, see stats    */
     int32_t log_cap;              /* depletion-log slots per env (<= 255); overflow is counted     */
     double food_start;            /* F64 mode: starting_food; < 0 = random        wab_env.py:596-597 */
     double food_inc;              /* 1 / turns_to_fill_food                       wab_env.py:307-309 */
@@ -191,6 +191,17 @@ int wab_vec_flatten_features_noisy(WabVec *h, const uint8_t *d_features, int64_t
  * uniform per row keyed by (seed, row, *d_counter) — d_counter as in wab_vec_flatten_features_noisy. */
 int wab_sample_categorical(const void *d_probs, int32_t probs_bf16, int64_t n, int32_t n_actions, uint64_t seed,
                            const uint64_t *d_counter, uint8_t *d_actions, void *stream);
+
+/* The tail of the reference's Policy.forward + select_action (actor_critic.py:84-97, :108-125) for n_rows rows in one
+ * pass, fp32: d_z3 f32[n_rows][128] is the PRE-activation output of affine3; x = clamp(leaky_relu(z3), lo, hi);
+ * logits = W[0..A) x + b, value = W[A] x + b[A] (d_w_heads f32[A + 1][128] = action_head.weight stacked on
+ * value_head.weight, d_b_heads f32[A + 1]); probs = softmax(logits); one action per row by inverse CDF on a uniform
+ * keyed by (seed, row, *d_counter). Outputs: d_actions u8[n_rows]; d_value f32[n_rows], d_probs f32[n_rows][A],
+ * d_logp f32[n_rows] (log-probability of the sampled action) — each may be NULL. */
+int wab_policy_tail(const float *d_z3, int32_t hidden, const float *d_w_heads, const float *d_b_heads, int64_t n_rows,
+                    int32_t n_actions, float leaky_slope, float clamp_lo, float clamp_hi, uint64_t seed,
+                    const uint64_t *d_counter, uint8_t *d_actions, float *d_value, float *d_probs, float *d_logp,
+                    void *stream);
 
 /* ---- Environment 2.0 ("/root/reference/Environment 2.0"): a toroidal W x H world of ostriches, wolves and
  * bushes per environment. One call = one world turn: every entity, in id order (ostriches, wolves, bushes),

@@ -90,7 +90,7 @@ class HostSimEnv:
     def hidden_state(self):
         scal = np.zeros(9, dtype=np.int32)
         food = ctypes.c_double()
-        wolves = np.zeros((16, 2), dtype=np.int32)
+        wolves = np.zeros((64, 2), dtype=np.int32)
         mask = np.zeros(4, dtype=np.uint32)
         lib().hostsim_state(self._h, scal.ctypes.data, ctypes.addressof(food), wolves.ctypes.data, mask.ctypes.data)
         nw = int(scal[7])

@@ -94,6 +94,33 @@ def test_wolf_and_log_overflow_are_reported():
     assert seen == 1
 
 
+def test_wolf_packs_beyond_32_stay_exact():
+    """The reference's wolf list is unbounded (wab_env.py:570-575); the kernels hold up to 64 per env. A configuration
+    that keeps ~24 wolves alive (1.2 spawns per turn against 5 % despawn, nobody dies) and peaks above 32 stays equal
+    to the oracle — observation, reward, done and the whole wolf multiset — with no overflow reported."""
+    opts = {"chance_wolf_on_square": 0.05, "god_mode": True, "max_turns": 400, "turns_to_empty_food": 200, "starting_food": 1.0}
+    peak = 0
+    for env_id in range(3):
+        sim = HostSimEnv(opts, seed=11, env_id=env_id, wolf_cap=64)
+        orc = OracleEnv(opts, seed=11, env_id=env_id)
+        a, _ = sim.reset()
+        b = orc.reset()
+        rng = np.random.default_rng(env_id)
+        for t in range(400):
+            assert np.array_equal(a[0], b[0]) and tuple(a[1:]) == tuple(b[1:]), (env_id, t)
+            act = int(rng.integers(0, 5))
+            (a, r1, d1, _, ovf) = sim.step(act)
+            b, r2, d2 = orc.step(act)
+            assert ovf == 0 and np.float32(r2) == r1 and d1 == d2, (env_id, t)
+            if d1:                       # the sim reset itself inside the step (auto_reset): bring the oracle along
+                b = orc.reset()
+                continue
+            hs, ho = sim.hidden_state(), orc.hidden_state()
+            assert sorted(hs["wolves"]) == ho["wolves"], (env_id, t)
+            peak = max(peak, len(ho["wolves"]))
+    assert peak > 32, peak
+
+
 @pytest.mark.parametrize("thr", [0x80008000, 0x12340000, 0xFFFF0001, 0x0000FFFF, 0xE6666667])
 def test_reveal_paths_settle_half_word_ties_on_the_full_draw(thr):
     """slide_window / reset_bush_block compare 16-bit half-words and fall back to the full 32-bit draw on a tie

@@ -1,0 +1,79 @@
+"""configs[4] building blocks on the GPU: the fused policy tail (``wab_policy_tail``: activation, clamp, both heads,
+softmax, Categorical sample) against plain torch fp32, and the rollout loop built from it."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _policy(n_actions=5, seed=0):
+    from wab_gym_b200.policy import Policy
+    torch.manual_seed(seed)
+    return Policy(449, n_actions).cuda()
+
+
+@pytest.mark.parametrize("n_actions", [5, 6])
+def test_policy_tail_matches_torch_fp32(n_actions):
+    from wab_gym_b200.policy import policy_tail, stacked_heads
+    pol = _policy(n_actions)
+    with torch.no_grad():
+        pol.action_head.weight.mul_(6.0)                     # spread the logits so the softmax is not flat
+    n = 4099
+    g = torch.Generator(device="cuda").manual_seed(1)
+    z3 = torch.randn(n, 128, device="cuda", generator=g) * 3.0          # plenty of values beyond the +-4 clamp
+    heads = stacked_heads(pol)
+    actions = torch.empty(n, dtype=torch.uint8, device="cuda")
+    value, logp = torch.empty(n, device="cuda"), torch.empty(n, device="cuda")
+    probs = torch.empty(n, n_actions, device="cuda")
+    ctr = torch.full((1,), 3, dtype=torch.int64, device="cuda")
+    policy_tail(pol, z3, heads, actions, value=value, probs=probs, logp=logp, counter=ctr, seed=11)
+    with torch.no_grad():
+        x = torch.clamp(F.leaky_relu(z3), -4, 4)                          # actor_critic.py:92-93
+        want_p = F.softmax(pol.action_head(x), dim=-1)                    # :96
+        want_v = pol.value_head(x).squeeze(1)                             # :97
+    assert torch.allclose(probs, want_p, rtol=1e-5, atol=1e-6), float((probs - want_p).abs().max())
+    assert torch.allclose(value, want_v, rtol=1e-5, atol=1e-5), float((value - want_v).abs().max())
+    assert int(actions.max()) < n_actions
+    picked = probs.gather(1, actions.long()[:, None]).squeeze(1)
+    assert torch.allclose(logp, picked.log(), rtol=1e-5, atol=1e-5) and float(picked.min()) > 0
+    again = torch.empty_like(actions)
+    policy_tail(pol, z3, heads, again, counter=ctr, seed=11)
+    assert torch.equal(actions, again)                                    # keyed draws: same counter, same actions
+    ctr += 1
+    policy_tail(pol, z3, heads, again, counter=ctr, seed=11)
+    assert not torch.equal(actions, again)
+
+
+def test_policy_tail_samples_follow_the_probabilities():
+    from wab_gym_b200.policy import policy_tail, stacked_heads
+    pol = _policy(5, seed=2)
+    with torch.no_grad():
+        pol.action_head.weight.mul_(4.0)
+    n = 400_000
+    z3 = torch.randn(1, 128, device="cuda").repeat(n, 1).contiguous()
+    heads = stacked_heads(pol)
+    actions = torch.empty(n, dtype=torch.uint8, device="cuda")
+    probs = torch.empty(n, 5, device="cuda")
+    policy_tail(pol, z3, heads, actions, probs=probs, counter=torch.zeros(1, dtype=torch.int64, device="cuda"), seed=5)
+    p = probs[0].double().cpu().numpy()
+    freq = np.bincount(actions.cpu().numpy(), minlength=5) / n
+    assert np.all(np.abs(freq - p) < 5 * np.sqrt(p * (1 - p) / n) + 1e-4), (freq, p)
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_rollout_runs_on_the_fused_tail(use_graph):
+    from wab_gym_b200 import VecEnv
+    from wab_gym_b200.policy import Policy, Rollout
+    torch.manual_seed(0)
+    env = VecEnv(2048, seed=3, features=True)
+    ro = Rollout(env, Policy(env.flat_dim, env.n_actions), use_graph=use_graph)
+    assert ro.fused_tail and "wab_policy_tail_kernel" in ro.describe()
+    before = env.stats()["steps"]
+    ro.run(120)
+    torch.cuda.synchronize()
+    st = env.stats()
+    assert st["steps"] - before == 2048 * 120 and st["bad_actions"] == 0 and st["episodes"] > 2048
+    assert len(torch.unique(ro.actions)) > 1 and torch.isfinite(ro.values).all()
+    env.close()

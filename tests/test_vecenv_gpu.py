@@ -58,7 +58,7 @@ def test_vecenv_matches_oracle_per_env(name, f64):
     """N = 70 (two full warps + a ragged one) lockstep envs vs 70 oracle envs, every step, hidden state too."""
     overrides, greedy = OPTION_SETS[name]
     n, steps, seed, base = 70, 260, 5, 1000
-    env = _vec(n, overrides, seed=seed, env_id_base=base, force_f64_food=f64, wolf_cap=15)
+    env = _vec(n, overrides, seed=seed, env_id_base=base, force_f64_food=f64, wolf_cap=64)
     oracles = [OracleEnv(overrides, seed=seed, env_id=base + i) for i in range(n)]
     rng = np.random.default_rng(11)
     obs = env.reset()
@@ -106,7 +106,7 @@ def test_every_lanes_per_env_variant_matches_oracle(lpe, name, monkeypatch):
     monkeypatch.setenv("WAB_LPE", str(lpe))
     overrides, greedy = OPTION_SETS[name]
     n, steps, seed, base = 41, 160, 77, 5000
-    env = _vec(n, overrides, seed=seed, env_id_base=base, wolf_cap=15)
+    env = _vec(n, overrides, seed=seed, env_id_base=base, wolf_cap=64)
     assert env.lanes_per_env == lpe
     oracles = [OracleEnv(overrides, seed=seed, env_id=base + i) for i in range(n)]
     rng = np.random.default_rng(lpe)
@@ -335,7 +335,7 @@ def _ref_features(grids, food, role, status):
 def test_fused_and_standalone_features(name):
     overrides, greedy = OPTION_SETS[name]
     n, steps = 130, 60
-    env = _vec(n, overrides, seed=21, features=True, wolf_cap=15)
+    env = _vec(n, overrides, seed=21, features=True, wolf_cap=64)
     rng = np.random.default_rng(6)
     obs = env.reset()
     feats = env.last_features
@@ -472,7 +472,7 @@ def test_batch_without_auto_reset_keeps_reporting_done(name):
     fp64 food, masked reset of the finished envs every few steps."""
     overrides, greedy = OPTION_SETS[name]
     n, steps, seed = 48, 220, 13
-    env = _vec(n, overrides, seed=seed, auto_reset=False, wolf_cap=15)
+    env = _vec(n, overrides, seed=seed, auto_reset=False, wolf_cap=64)
     assert env.game.food_mode == 0
     oracles = [OracleEnv(overrides, seed=seed, env_id=i) for i in range(n)]
     rng = np.random.default_rng(3)
@@ -513,7 +513,7 @@ def test_random_option_sets_match_oracle_on_device(case):
     rng = np.random.default_rng(1000 + case)
     opts = random_options(rng)
     n, steps, seed = 96, 160, 40 + case
-    env = _vec(n, opts, seed=seed, wolf_cap=15, force_f64_food=bool(case & 1))
+    env = _vec(n, opts, seed=seed, wolf_cap=64, force_f64_food=bool(case & 1))
     oracles = [OracleEnv(opts, seed=seed, env_id=i) for i in range(n)]
     obs = env.reset()
     cur = [o.reset() for o in oracles]
@@ -533,7 +533,7 @@ def test_random_option_sets_match_oracle_on_device(case):
     env.close()
     # batch checksum at a larger size (thread-per-env and lanes-per-env kernels alike)
     n2, steps2 = 2048, 96
-    big = _vec(n2, opts, seed=seed, wolf_cap=15)
+    big = _vec(n2, opts, seed=seed, wolf_cap=64)
     acts = torch.randint(0, big.n_actions, (steps2, n2), dtype=torch.uint8, device="cuda",
                          generator=torch.Generator("cuda").manual_seed(case))
     big.reset()
@@ -542,6 +542,39 @@ def test_random_option_sets_match_oracle_on_device(case):
     cs = (o.grids.view(steps2, n2, 363).long() * w).sum() + 1000 * o.food.long().sum() + 100000 * o.role.long().sum() \
         + 200000 * o.status.long().sum() + 400000 * d.long().sum()
     n_steps, want = wab_oracle.run(opts, seed, n2, steps2, acts.cpu().numpy())
-    if big.stats()["overflows"] == 0:                    # a full wolf table is counted, not silently wrong
-        assert n_steps == n2 * steps2 and int(cs.item()) == want, (case, opts)
+    assert big.stats()["overflows"] == 0                 # 64 wolf slots: no fuzzed option set gets near
+    assert n_steps == n2 * steps2 and int(cs.item()) == want, (case, opts)
     big.close()
+
+
+@pytest.mark.parametrize("lpe", [1, 8])
+def test_wolf_packs_beyond_32_stay_exact_on_device(lpe, monkeypatch):
+    """The reference's wolf list is unbounded (wab_env.py:570-575). ~24 wolves alive per env with peaks above 32 (64
+    slots): observations, reward, done and the wolf multiset stay equal to the oracle, and nothing overflows."""
+    monkeypatch.setenv("WAB_LPE", str(lpe))
+    opts = {"chance_wolf_on_square": 0.05, "god_mode": True, "max_turns": 400, "turns_to_empty_food": 200, "starting_food": 1.0}
+    n, steps, seed = 24, 300, 11
+    env = _vec(n, opts, seed=seed, wolf_cap=64)
+    oracles = [OracleEnv(opts, seed=seed, env_id=i) for i in range(n)]
+    rng = np.random.default_rng(5)
+    obs = env.reset()
+    cur = [o.reset() for o in oracles]
+    peak = 0
+    for t in range(steps):
+        g, f, r, s = (x.cpu().numpy() for x in obs)
+        for i in range(n):
+            assert np.array_equal(g[i], cur[i][0]) and (int(f[i]), int(r[i]), int(s[i])) == cur[i][1:], (t, i)
+        if t % 25 == 24:
+            st = env.export_state()
+            for i, o in enumerate(oracles):
+                assert _wolves(st, i) == o.hidden_state()["wolves"], (t, i)
+                peak = max(peak, int(st["n_wolves"][i]))
+        acts = rng.integers(0, 5, n).astype(np.uint8)
+        obs, reward, done, _ = env.step(torch.from_numpy(acts).cuda())
+        reward, done = reward.cpu().numpy(), done.cpu().numpy()
+        for i, o in enumerate(oracles):
+            c, rr, d = o.step(int(acts[i]))
+            assert np.float32(rr) == reward[i] and d == bool(done[i]), (t, i)
+            cur[i] = o.reset() if d else c
+    assert peak > 32 and env.stats()["overflows"] == 0
+    env.close()

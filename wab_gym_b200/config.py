@@ -237,7 +237,7 @@ class GameConfig:
     food_int: Tuple[int, int, int]
     reward_table64: np.ndarray = field(repr=False)
     auto_reset: bool = True
-    wolf_cap: int = 8
+    wolf_cap: int = 16
     log_cap: int = 80
 
     @property
@@ -246,7 +246,7 @@ class GameConfig:
 
     @classmethod
     def from_options(cls, game_options: Optional[dict] = None, *, auto_reset: bool = True,
-                     force_f64_food: bool = False, wolf_cap: int = 8, log_cap: Optional[int] = None) -> "GameConfig":
+                     force_f64_food: bool = False, wolf_cap: int = 16, log_cap: Optional[int] = None) -> "GameConfig":
         opts = dict(default_game_options)
         if game_options:
             opts.update(game_options)  # KeyError semantics: missing keys fall back to defaults here
@@ -279,8 +279,8 @@ class GameConfig:
                 rewards[ate * 4 + outcome] = r
         if log_cap is None:
             log_cap = min(max_turns, 255)
-        if not (1 <= wolf_cap <= 15) or not (1 <= log_cap <= 255):
-            raise ValueError("wolf_cap must be in [1, 15] and log_cap in [1, 255]")
+        if not (1 <= wolf_cap <= 64) or not (1 <= log_cap <= 255):
+            raise ValueError("wolf_cap must be in [1, 64] and log_cap in [1, 255]")
         return cls(
             options=opts,
             actions=action_table(opts),

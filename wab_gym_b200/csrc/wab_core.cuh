@@ -460,7 +460,7 @@ WAB_HD void env_step(const Params& P, Env& E, const Slots& S, uint32_t action, S
     // ---- :262-264 despawn (keep iff U > chance). rank = ordinal among earlier wolves on the cell.
     if (E.nw) {
         uint32_t kept = 0;
-        uint32_t keepmask = 0;
+        uint64_t keepmask = 0;                         // wolf_cap <= 64
         WAB_ROLLED
         for (uint32_t k = 0; k < E.nw; ++k) {
             const uint32_t p = S.wolves[(int32_t)k * S.wstride];
@@ -469,19 +469,19 @@ WAB_HD void env_step(const Params& P, Env& E, const Slots& S, uint32_t action, S
             for (uint32_t q = 0; q < k; ++q) rank += (S.wolves[(int32_t)q * S.wstride] == p) ? 1u : 0u;
             uint32_t w[4];
             philox(P, E.env_id, E.episode, ctr2(SITE_DESP, E.turn, rank >> 2), p, w);
-            if ((uint64_t)pick4(w, rank & 3u) >= P.thr_keep) keepmask |= 1u << k;
+            if ((uint64_t)pick4(w, rank & 3u) >= P.thr_keep) keepmask |= 1ull << k;
         }
         group_sync(coop);                       // every lane of the group has read the slots
         if (group_leader(coop)) {
             WAB_ROLLED
             for (uint32_t k = 0; k < E.nw; ++k)
-                if ((keepmask >> k) & 1u) {
+                if ((keepmask >> k) & 1ull) {
                     S.wolves[(int32_t)kept * S.wstride] = S.wolves[(int32_t)k * S.wstride];
                     ++kept;
                 }
         }
         group_sync(coop);
-        E.nw = popc32(keepmask);
+        E.nw = popc32((uint32_t)keepmask) + popc32((uint32_t)(keepmask >> 32));
     }
 
     // ---- :266 the frame the rest of the step reads: bushes with food > 0, ostrich status

@@ -55,10 +55,10 @@ constexpr int kMbScale = 128 / WAB_THREADS_LPE1;
 
 struct StatePtrs {
     uint32_t* pos;       // [N]  x:i16 | y:i16 << 16
-    uint32_t* misc;      // [N]  food_i:8 | role:1 | status:2 | nw:4 | -:1 | turn:16
+    uint32_t* misc;      // [N]  food_i:8 | role:1 | status:2 | nw (low 4 bits):4 | depleted:1 | turn:16
     uint32_t* episode;   // [N]
     uint4* bush;         // [N]  121-bit window occupancy
-    uint16_t* nlog;      // [N]  entries in the depletion log : 8 | stale centre bush : 1
+    uint16_t* nlog;      // [N]  entries in the depletion log : 8 | stale centre bush : 1 | nw (high 3 bits) : 3
     uint32_t* logsig;    // [N]  Bloom signature of the depletion log
     uint2* bkey;         // [N]  the episode's bush key
     double* food;        // [N]  F64 mode only
@@ -87,7 +87,7 @@ __device__ __forceinline__ void load_env(const Params& P, const StatePtrs& st, i
     E.episode = st.episode[idx];
     const uint4 b = st.bush[idx];
     E.m[0] = b.x; E.m[1] = b.y; E.m[2] = b.z; E.m[3] = b.w;
-    { const uint32_t nl = st.nlog[idx]; E.nlog = nl & 0xFFu; E.stale = nl >> 8; }
+    { const uint32_t nl = st.nlog[idx]; E.nlog = nl & 0xFFu; E.stale = (nl >> 8) & 1u; E.nw |= ((nl >> 9) & 7u) << 4; }
     E.logsig = st.logsig[idx];
     { const uint2 bk = st.bkey[idx]; E.bk_a = bk.x; E.bk_b = bk.y; }
     E.food_f = F64 ? st.food[idx] : 0.0;
@@ -100,11 +100,11 @@ template <bool F64>
 __device__ __forceinline__ void store_env(const StatePtrs& st, int64_t idx, const Env& E,
                                           const uint32_t* wolves_s, int wstride) {
     st.pos[idx] = pack_xy(E.x, E.y);
-    st.misc[idx] = ((uint32_t)E.food_i & 0xFFu) | (E.role << 8) | (E.status << 9) | (E.nw << 11) | (E.dep << 15) |
+    st.misc[idx] = ((uint32_t)E.food_i & 0xFFu) | (E.role << 8) | (E.status << 9) | ((E.nw & 15u) << 11) | (E.dep << 15) |
                    (E.turn << 16);
     st.episode[idx] = E.episode;
     st.bush[idx] = make_uint4(E.m[0], E.m[1], E.m[2], E.m[3]);
-    st.nlog[idx] = (uint16_t)(E.nlog | (E.stale << 8));
+    st.nlog[idx] = (uint16_t)(E.nlog | (E.stale << 8) | ((E.nw >> 4) << 9));
     st.logsig[idx] = E.logsig;
     st.bkey[idx] = make_uint2(E.bk_a, E.bk_b);
     if (F64) st.food[idx] = E.food_f;
@@ -493,42 +493,138 @@ __global__ void wab_flatten_kernel(const __grid_constant__ Params P, const uint8
     outp[e] = flat_column(P, features + row * FEAT_BYTES, (int)(e - row * dim), food_dim);
 }
 
-// The policy input of actor_critic.py:188-189 in one pass: flatten + noise_scale * U[0,1) + cast, four elements per
-// thread (one Philox call; the 64-bit draw counter lives in device memory so a captured graph gets fresh noise on
-// every replay). BF16 = 0: f32 output, 1: bf16 output. Replaces five elementwise passes over the f32 matrix.
-template <int BF16>
-__global__ void wab_flatten_noisy_kernel(const __grid_constant__ Params P, const uint8_t* __restrict__ features, int64_t rows,
-                                         int food_dim, void* __restrict__ outp, float noise_scale,
-                                         const unsigned long long* __restrict__ d_counter) {
-    const int dim = flat_dim_of(food_dim);
-    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, total = rows * dim, e0 = q * 4;
-    if (e0 >= total) return;
-    const unsigned long long ctr = d_counter ? *d_counter : 0ull;
-    uint32_t w[4];
-    philox(P, (uint32_t)q, (uint32_t)(q >> 32), (uint32_t)ctr, (uint32_t)(ctr >> 32) ^ 0x464C4154u, w);
-    int64_t row = e0 / dim;
-    int k = (int)(e0 - row * dim);
-    float v[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        v[j] = 0.f;
-        if (e0 + j < total) v[j] = flat_column(P, features + row * FEAT_BYTES, k, food_dim) + noise_scale * ((float)(w[j] >> 8) * (1.0f / 16777216.0f));
-        if (++k == dim) { k = 0; ++row; }
+// The policy input of actor_critic.py:188-189 in one pass: flatten + noise_scale * U[0,1) + cast. One warp per row;
+// lane L owns columns L, L + 32, ... so every store instruction writes 32 consecutive elements of the row (rows are
+// 449 elements long: no 16-byte alignment to exploit), the row's 28 feature bytes sit in a per-warp shared-memory slot,
+// and a column is a table lookup (feature index, value) -> one compare — no division, no per-element branching (the
+// first version spent 64 us on the 32,768 x 449 matrix, 7x its memory time, on 64-bit index arithmetic). One Philox
+// call feeds four columns of a lane; the 64-bit draw counter lives in device memory so a captured graph gets fresh
+// noise on every replay. BF16 = 0: f32 output, 1: bf16 output.
+constexpr int FLAT_MAX_DIM = 2 * (2 * 4 * (MAX_DISTANCE + 1) + 4 * 11) + 2 + 256 + 2 + 3 + CELLS;
+__device__ __forceinline__ uint32_t flat_descriptor(int k, int food_dim) {     // fi : 8 | value : 8 | view-mask column : 1
+    for (int species = 0; species < 2; ++species) {
+        const int base = species * 12;
+        if (k < 96) return (uint32_t)(base + k / 12) | ((uint32_t)(k % 12) << 8);
+        if (k < 140) return (uint32_t)(base + 8 + (k - 96) / 11) | ((uint32_t)((k - 96) % 11) << 8);
+        k -= 140;
     }
-    if (BF16) {
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(outp) + e0;
-        if (e0 + 3 < total) {
-            __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b2 = __floats2bfloat162_rn(v[2], v[3]);
-            uint2 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b2);
-            *reinterpret_cast<uint2*>(o) = pk;
-        } else {
-            for (int j = 0; e0 + j < total; ++j) o[j] = __float2bfloat16_rn(v[j]);
+    if (k < 2) return 24u | ((uint32_t)k << 8);
+    if (k < 2 + food_dim) return 25u | ((uint32_t)(k - 2) << 8);
+    if (k < 4 + food_dim) return 26u | ((uint32_t)(k - 2 - food_dim) << 8);
+    if (k < 7 + food_dim) return 27u | ((uint32_t)(k - 4 - food_dim) << 8);
+    return 26u | ((uint32_t)(k - 7 - food_dim) << 8) | (1u << 16);              // view mask cell, selected by the role
+}
+template <int BF16>
+__global__ void __launch_bounds__(256) wab_flatten_noisy_kernel(const __grid_constant__ Params P, const uint8_t* __restrict__ features,
+                                                                int64_t rows, int food_dim, void* __restrict__ outp, float noise_scale,
+                                                                const unsigned long long* __restrict__ d_counter) {
+    __shared__ uint32_t desc[FLAT_MAX_DIM];
+    __shared__ uint32_t frow[8][8];                   // the 28 feature bytes of the row each warp is working on
+    const int dim = flat_dim_of(food_dim);
+    for (int k = threadIdx.x; k < dim; k += blockDim.x) desc[k] = flat_descriptor(k, food_dim);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned long long ctr = d_counter ? *d_counter : 0ull;
+    const bool noisy = noise_scale != 0.f;
+    const float scale = noise_scale * (1.0f / 16777216.0f);
+    for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < rows; row += (int64_t)gridDim.x * 8) {
+        __syncwarp();
+        if (lane < 7) frow[warp][lane] = reinterpret_cast<const uint32_t*>(features + row * FEAT_BYTES)[lane];
+        __syncwarp();
+        const uint8_t* f = reinterpret_cast<const uint8_t*>(frow[warp]);
+        const uint32_t* vm = P.restrict_view ? (f[26] == 1 ? P.mask_gath : P.mask_look) : nullptr;
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        int it = 0;
+        for (int k = lane; k < dim; k += 32, ++it) {
+            if (noisy && (it & 3) == 0)
+                philox(P, (uint32_t)row, (uint32_t)(row >> 32) ^ ((uint32_t)(it >> 2) << 24) ^ ((uint32_t)lane << 16), (uint32_t)ctr,
+                       (uint32_t)(ctr >> 32) ^ 0x464C4154u, w);
+            const uint32_t d = desc[k];
+            float v;
+            if (d >> 16) {
+                const uint32_t c = (d >> 8) & 0xFFu;
+                v = vm ? (float)((vm[c >> 5] >> (c & 31)) & 1u) : 0.f;
+            } else {
+                v = f[d & 0xFFu] == ((d >> 8) & 0xFFu) ? 1.f : 0.f;
+            }
+            if (noisy) v += scale * (float)(pick4(w, (uint32_t)it & 3u) >> 8);
+            if (BF16) reinterpret_cast<__nv_bfloat16*>(outp)[row * dim + k] = __float2bfloat16_rn(v);
+            else reinterpret_cast<float*>(outp)[row * dim + k] = v;
         }
-    } else {
-        float* o = reinterpret_cast<float*>(outp) + e0;
-        if (e0 + 3 < total) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-        else for (int j = 0; e0 + j < total; ++j) o[j] = v[j];
+    }
+}
+
+// The tail of the reference's Policy.forward and select_action in one pass (actor_critic.py:84-97, :108-125): from the
+// pre-activation output z3 of affine3, x = clamp(leaky_relu(z3), -4, 4); logits = action_head(x); value = value_head(x);
+// probs = softmax(logits); action = Categorical(probs).sample() (inverse CDF on one keyed uniform per row) and its
+// log-probability. One warp per row: each lane holds HID / 32 activations, the n_actions + 1 dot products are warp
+// sums. fp32 throughout. Replaces eleven library launches (clamp, two skinny GEMMs that cuBLAS runs as 17 us gemv-style
+// kernels at 32,768 rows, their bias adds, softmax, sampling, copies) with one pass over the 16 MB activation matrix.
+template <int HID>
+__global__ void __launch_bounds__(256) wab_policy_tail_kernel(const __grid_constant__ Params P, const float* __restrict__ z3,
+                                                              const float* __restrict__ w_heads, const float* __restrict__ b_heads,
+                                                              int64_t rows, int n_actions, float slope, float clamp_lo, float clamp_hi,
+                                                              const unsigned long long* __restrict__ d_counter,
+                                                              uint8_t* __restrict__ actions, float* __restrict__ value,
+                                                              float* __restrict__ probs, float* __restrict__ logp) {
+    constexpr int PER = HID / 32;
+    __shared__ float wsm[9 * HID];
+    const int n_out = n_actions + 1;
+    for (int k = threadIdx.x; k < n_out * HID; k += blockDim.x) wsm[k] = w_heads[k];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned long long ctr = d_counter ? *d_counter : 0ull;
+    for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < rows; row += (int64_t)gridDim.x * 8) {
+        float x[PER];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            float v = z3[row * HID + j * 32 + lane];
+            v = v > 0.f ? v : v * slope;                                  // F.leaky_relu, :92
+            x[j] = fminf(fmaxf(v, clamp_lo), clamp_hi);                   // torch.clamp(x, -4, 4), :93
+        }
+        float acc[9];
+#pragma unroll
+        for (int o = 0; o < 9; ++o) {
+            acc[o] = 0.f;
+            if (o < n_out) {
+#pragma unroll
+                for (int j = 0; j < PER; ++j) acc[o] = fmaf(x[j], wsm[o * HID + j * 32 + lane], acc[o]);
+#pragma unroll
+                for (int sft = 16; sft > 0; sft >>= 1) acc[o] += __shfl_xor_sync(FULL, acc[o], sft);
+                acc[o] += b_heads[o];
+            }
+        }
+        float mx = -3.4e38f;
+#pragma unroll
+        for (int o = 0; o < 8; ++o) if (o < n_actions) mx = fmaxf(mx, acc[o]);
+        float e[8], tot = 0.f;
+#pragma unroll
+        for (int o = 0; o < 8; ++o) { e[o] = o < n_actions ? expf(acc[o] - mx) : 0.f; tot += e[o]; }   // F.softmax, :96
+        uint32_t w[4];
+        philox(P, (uint32_t)(row >> 2), (uint32_t)(row >> 34), (uint32_t)ctr, (uint32_t)(ctr >> 32) ^ 0x53414D50u, w);
+        const float u = (float)(pick4(w, (uint32_t)row & 3u) >> 8) * (1.0f / 16777216.0f);
+        const float target = u * tot;
+        float cum = 0.f, p_pick = 0.f;
+        int pick = n_actions - 1;
+        bool found = false;
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {                                     // smallest a with target < e[0] + ... + e[a]
+            cum += e[o];
+            if (!found && o < n_actions && target < cum) { pick = o; found = true; }
+        }
+#pragma unroll
+        for (int o = 0; o < 8; ++o) if (o == pick) p_pick = e[o];
+        if (lane == 0) {
+            actions[row] = (uint8_t)pick;
+            if (value) value[row] = acc[n_actions < 8 ? n_actions : 8];
+            if (logp) logp[row] = logf(p_pick / tot);
+        }
+        if (probs && lane < n_actions) {
+            float mine = 0.f;
+#pragma unroll
+            for (int o = 0; o < 8; ++o) if (o == lane) mine = e[o];
+            probs[row * n_actions + lane] = mine / tot;
+        }
     }
 }
 
@@ -1052,7 +1148,7 @@ int wab_vec_export_state(WabVec* h, int32_t* x, int32_t* y, double* food, int32_
     if (e == cudaSuccess) {
         for (size_t i = 0; i < n; ++i) {
             const uint32_t m = misc[i];
-            const int nw = (int)((m >> 11) & 15u);
+            const int nw = (int)(((m >> 11) & 15u) | (((nl[i] >> 9) & 7u) << 4));
             if (x) x[i] = unpack_x(pos[i]);
             if (y) y[i] = unpack_y(pos[i]);
             if (food) food[i] = h->cfg.food_mode == WAB_FOOD_F64 ? fd[i] : (double)(m & 0xFFu) / h->cfg.food_obs_scale;
@@ -1123,14 +1219,38 @@ int wab_vec_flatten_features_noisy(WabVec* h, const uint8_t* d_features, int64_t
     if (n_rows <= 0) return WAB_OK;
     if (((uintptr_t)d_out & 15u) != 0) return fail(WAB_E_CONFIG, "d_out must be 16-byte aligned");
     DeviceGuard guard(h->device);
-    const int64_t quads = (n_rows * wab_vec_flat_dim(h) + 3) / 4;
-    const unsigned grid = (unsigned)((quads + 255) / 256);
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device);
+    const int64_t want = (n_rows + 7) / 8;
+    const unsigned grid = (unsigned)(want < (int64_t)n_sm * 8 ? want : (int64_t)n_sm * 8);
     const int food_dim = (int)h->cfg.food_obs_scale + 1;
     const unsigned long long* ctr = reinterpret_cast<const unsigned long long*>(d_counter);
     if (out_bf16)
         wab_flatten_noisy_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(h->P, d_features, n_rows, food_dim, d_out, noise_scale, ctr);
     else
         wab_flatten_noisy_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(h->P, d_features, n_rows, food_dim, d_out, noise_scale, ctr);
+    WAB_CUDA(cudaGetLastError());
+    return WAB_OK;
+}
+
+int wab_policy_tail(const float* d_z3, int32_t hidden, const float* d_w_heads, const float* d_b_heads, int64_t n_rows,
+                    int32_t n_actions, float leaky_slope, float clamp_lo, float clamp_hi, uint64_t seed,
+                    const uint64_t* d_counter, uint8_t* d_actions, float* d_value, float* d_probs, float* d_logp, void* stream) {
+    if (!d_z3 || !d_w_heads || !d_b_heads || !d_actions) return fail(WAB_E_NULL, "null argument");
+    if (n_actions < 1 || n_actions > 8) return fail(WAB_E_CONFIG, "n_actions must be in [1, 8]");
+    if (hidden != 128) return fail(WAB_E_UNSUPPORTED, "wab_policy_tail is built for the reference's 128-wide trunk (actor_critic.py:65-70)");
+    if (n_rows <= 0) return WAB_OK;
+    Params P;
+    memset(&P, 0, sizeof(P));
+    fill_round_keys(P, (uint32_t)seed, (uint32_t)(seed >> 32));
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t want = (n_rows + 7) / 8;
+    const unsigned grid = (unsigned)(want < (int64_t)n_sm * 8 ? want : (int64_t)n_sm * 8);
+    wab_policy_tail_kernel<128><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        P, d_z3, d_w_heads, d_b_heads, n_rows, n_actions, leaky_slope, clamp_lo, clamp_hi,
+        reinterpret_cast<const unsigned long long*>(d_counter), d_actions, d_value, d_probs, d_logp);
     WAB_CUDA(cudaGetLastError());
     return WAB_OK;
 }

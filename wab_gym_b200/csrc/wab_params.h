@@ -28,7 +28,7 @@ inline int validate_config(const WabConfig* cfg, int32_t n_bush_thr, int64_t n_e
             return fail(WAB_E_CONFIG, "binomial-first tables must be non-decreasing");
     if (cfg->n_actions < 1 || cfg->n_actions > WAB_MAX_ACTIONS) return fail(WAB_E_CONFIG, "n_actions out of range");
     if (cfg->max_turns < 1 || cfg->max_turns > 30000) return fail(WAB_E_CONFIG, "max_turns must be in [1, 30000]");
-    if (cfg->wolf_cap < 1 || cfg->wolf_cap > 15) return fail(WAB_E_CONFIG, "wolf_cap must be in [1, 15]");
+    if (cfg->wolf_cap < 1 || cfg->wolf_cap > 64) return fail(WAB_E_CONFIG, "wolf_cap must be in [1, 64]");
     if (cfg->log_cap < 1 || cfg->log_cap > 255) return fail(WAB_E_CONFIG, "log_cap must be in [1, 255]");
     if (n_bush_thr < 0 || n_bush_thr > 255) return fail(WAB_E_UNSUPPORTED, "max_berries_per_bush above 255");
     if (cfg->food_mode != WAB_FOOD_F64 && cfg->food_mode != WAB_FOOD_INT) return fail(WAB_E_CONFIG, "food_mode");

@@ -88,7 +88,7 @@ class WolvesAndBushesEnv:
         self.game_options = game_options  # held by reference, like wab_env.py:107
         for key in ("width", "height", "max_turns", "gatherer_only", "lookout_only"):
             game_options[key]  # KeyError on missing options, as the reference's dict lookups
-        self._game = GameConfig.from_options(game_options, auto_reset=False, force_f64_food=True, wolf_cap=15)
+        self._game = GameConfig.from_options(game_options, auto_reset=False, force_f64_food=True, wolf_cap=64)
         self.lookout_tile_mask = LOOKOUT_TILE_MASK.astype(np.int64)    # wab_env.py:109-123
         self.gatherer_tile_mask = GATHERER_TILE_MASK.astype(np.int64)  # wab_env.py:125-139
         self.spec = EnvSpec(id="WolvesAndBushes-v0", max_episode_steps=game_options["max_turns"],

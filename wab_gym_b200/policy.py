@@ -11,13 +11,15 @@ the host inside the loop.
 """
 from __future__ import annotations
 
+import ctypes
 from typing import Dict, Optional
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .vec_env import VecEnv
+from . import _lib
+from .vec_env import VecEnv, _ptr, _raw_stream
 
 
 class Policy(nn.Module):
@@ -39,6 +41,33 @@ class Policy(nn.Module):
         return F.softmax(self.action_head(x), dim=-1), self.value_head(x)
 
 
+def policy_tail(policy: "Policy", z3: torch.Tensor, heads: tuple, actions: torch.Tensor, value: Optional[torch.Tensor] = None,
+                probs: Optional[torch.Tensor] = None, logp: Optional[torch.Tensor] = None,
+                counter: Optional[torch.Tensor] = None, seed: int = 0) -> torch.Tensor:
+    """``clamp(leaky_relu(z3)) -> action_head / value_head -> softmax -> Categorical.sample()`` (``actor_critic.py:92-97``,
+    ``:114-120``) as ONE kernel of the library (``wab_policy_tail``): ``z3`` f32[N, 128] is ``policy.affine3``'s output
+    before its activation, ``heads`` = ``stacked_heads(policy)``. Fills ``actions`` u8[N] (and ``value``, ``probs``,
+    ``logp`` when given)."""
+    w, b = heads
+    if z3.dtype != torch.float32 or not z3.is_contiguous() or z3.shape[1] != 128:
+        raise ValueError("z3 must be a contiguous float32 [N, 128] tensor")
+    dev = z3.device.index if z3.device.index is not None else torch.cuda.current_device()
+    stream = ctypes.c_void_p(_raw_stream(dev)) if _raw_stream is not None else ctypes.c_void_p(torch.cuda.current_stream(z3.device).cuda_stream)
+    _lib.check(_lib.load().wab_policy_tail(_ptr(z3), 128, _ptr(w), _ptr(b), z3.shape[0], w.shape[0] - 1, 0.01, -4.0, 4.0,
+                                           int(seed) & (2 ** 64 - 1), _ptr(counter), _ptr(actions), _ptr(value), _ptr(probs),
+                                           _ptr(logp), stream))
+    return actions
+
+
+def stacked_heads(policy: "Policy") -> tuple:
+    """(action_head.weight stacked on value_head.weight f32[A + 1, 128], the two biases f32[A + 1]) — refresh after an
+    optimiser step."""
+    with torch.no_grad():
+        w = torch.cat([policy.action_head.weight, policy.value_head.weight], 0).float().contiguous()
+        b = torch.cat([policy.action_head.bias, policy.value_head.bias], 0).float().contiguous()
+    return w, b
+
+
 class Rollout:
     """N-environment rollout with every tensor resident on the device.
 
@@ -47,7 +76,7 @@ class Rollout:
     for small batches)."""
 
     def __init__(self, env: VecEnv, policy: Optional[Policy] = None, noise: bool = True, use_graph: bool = False,
-                 dtype: torch.dtype = torch.float32):
+                 dtype: torch.dtype = torch.float32, fused_tail: Optional[bool] = None, track_reward: bool = False):
         if not env.with_features:
             raise ValueError("Rollout needs VecEnv(features=True)")
         self.env, self.noise, self.dtype = env, noise, dtype
@@ -58,6 +87,12 @@ class Rollout:
         self.actions = torch.zeros(env.num_envs, dtype=torch.uint8, device=env.device)
         self.values = torch.zeros(env.num_envs, dtype=torch.float32, device=env.device)
         self.reward_sum = torch.zeros((), dtype=torch.float64, device=env.device)
+        self.track_reward = track_reward         # episode statistics live in env.stats(); summing rewards here is optional
+        # fp32: the trunk's three GEMMs stay library calls (cuBLAS), everything after affine3 is one kernel of this library
+        self.fused_tail = (dtype == torch.float32) if fused_tail is None else bool(fused_tail)
+        if self.fused_tail and dtype != torch.float32:
+            raise ValueError("the fused policy tail is an fp32 kernel")
+        self.heads = stacked_heads(self.policy) if self.fused_tail else None
         env.reset()
         self.graph = None
         if use_graph:
@@ -78,11 +113,24 @@ class Rollout:
         # gym.spaces.flatten (actor_critic.py:188) + U[0,1)/100 input noise (:189) + cast, one kernel
         env.flatten_features_noisy(env.last_features, self.flat, 0.01 if self.noise else 0.0, self.noise_ctr)
         self.noise_ctr += 1
-        probs, value = self.policy(self.flat)
-        env.sample_actions(probs, self.actions, self.noise_ctr, seed=self.sample_seed)   # Categorical(probs).sample(), :117-120
-        self.values.copy_(value.squeeze(1))
+        if self.fused_tail:
+            p = self.policy
+            h = F.leaky_relu(p.affine1(self.flat))                                       # :88-90 (cuBLAS)
+            z3 = p.affine3(F.leaky_relu(p.affine2(h)))
+            policy_tail(p, z3, self.heads, self.actions, value=self.values, counter=self.noise_ctr, seed=self.sample_seed)
+        else:
+            probs, value = self.policy(self.flat)
+            env.sample_actions(probs, self.actions, self.noise_ctr, seed=self.sample_seed)   # Categorical(probs).sample(), :117-120
+            self.values.copy_(value.squeeze(1))
         _, reward, _, _ = env.step(self.actions)
-        self.reward_sum += reward.sum(dtype=torch.float64)
+        if self.track_reward:
+            self.reward_sum += reward.sum(dtype=torch.float64)
+
+    def describe(self) -> str:
+        if self.fused_tail:
+            return ("wab_flatten_noisy_kernel (flatten + noise) -> affine1..3 fp32 (cuBLAS) + leaky_relu -> wab_policy_tail_kernel "
+                    "(activation, clamp, both heads, softmax, Categorical sample) -> wab_step_kernel; one CUDA graph per step")
+        return "wab_flatten_noisy_kernel -> torch MLP (cuBLAS) -> wab_sample_kernel -> wab_step_kernel; one CUDA graph per step"
 
     def step(self):
         if self.graph is not None:

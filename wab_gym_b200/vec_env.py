@@ -44,7 +44,7 @@ def _ptr(t: Optional[torch.Tensor]):
 
 class VecEnv:
     def __init__(self, num_envs: int, game_options: Optional[dict] = None, device="cuda", seed: int = 0,
-                 env_id_base: int = 0, auto_reset: bool = True, wolf_cap: int = 8, log_cap: Optional[int] = None,
+                 env_id_base: int = 0, auto_reset: bool = True, wolf_cap: int = 16, log_cap: Optional[int] = None,
                  force_f64_food: bool = False, features: bool = False):
         self._h = None
         self._bound = None     # feature buffer currently bound in the handle
