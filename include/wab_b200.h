@@ -192,6 +192,16 @@ int wab_vec_flatten_features_noisy(WabVec *h, const uint8_t *d_features, int64_t
 int wab_sample_categorical(const void *d_probs, int32_t probs_bf16, int64_t n, int32_t n_actions, uint64_t seed,
                            const uint64_t *d_counter, uint8_t *d_actions, void *stream);
 
+/* ---- the reference's egocentric observation family (wab_env.py:637-667, WolvesAndBushesEnvEgoCentric :930-958):
+ * for the five squares the ostrich can reach next (up, right, down, left, stay) the proximity
+ * clip(max_distance - taxicab distance, 0, max_distance), max_distance = 11, of the nearest wolf and of the nearest
+ * bush with food among every cell seen this episode. wab_vec_enable_ego (before the first reset) makes the step
+ * kernels keep each episode's position history (4 bytes per env-step); wab_vec_ego_proximities writes
+ * d_out10 u8[N][10] = wolves[5], bushes[5] for the state left by the last reset/step. Envs stepped past max_turns
+ * without a reset keep only their first max_turns positions. */
+int wab_vec_enable_ego(WabVec *h);
+int wab_vec_ego_proximities(WabVec *h, uint8_t *d_out10, void *stream);
+
 /* The tail of the reference's Policy.forward + select_action (actor_critic.py:84-97, :108-125) for n_rows rows in one
  * pass, fp32: d_z3 f32[n_rows][128] is the PRE-activation output of affine3; x = clamp(leaky_relu(z3), lo, hi);
  * logits = W[0..A) x + b, value = W[A] x + b[A] (d_w_heads f32[A + 1][128] = action_head.weight stacked on

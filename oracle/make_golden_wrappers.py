@@ -90,6 +90,48 @@ def render():
     np.savez_compressed(os.path.join(GOLDEN_DIR, "render.npz"), meta=json.dumps(meta), **out)
 
 
+
+
+EGO_CASES = [("defaults", {}, False), ("dense", None, False), ("tiny_bushes", None, True)]
+
+
+def ego():
+    """``tests/golden/ego.npz`` — the reference's egocentric observation family (wab_env.py:637-667): after the reset and
+    after every step of keyed reference runs, ``_get_wolf_proximities()`` and ``_get_bush_proximities()`` (the latter is
+    element 0 of ``WolvesAndBushesEnvEgoCentric._get_obs``, :951-958), plus the actions (-1 = reset after done)."""
+    from oracle import ref_shim
+    from tests.util import OPTION_SETS, pick_action
+    out, meta = {}, []
+    for name, opts, _ in EGO_CASES:
+        if opts is None:
+            opts = OPTION_SETS[name][0]
+        greedy = OPTION_SETS[name][1] if name in OPTION_SETS else False
+        for env_id in (40, 41):
+            env = ref_shim.make_env(opts, seed=17, env_id=env_id)
+            env.max_distance = env.game_options["width"] // 2 + env.game_options["height"] // 2 + 1   # :932-934
+            rng = np.random.default_rng(env_id)
+            obs = env._get_obs()
+            actions, prox = [], []
+            prox.append([int(v) for v in env._get_wolf_proximities()] + [int(v) for v in env._get_bush_proximities()])
+            for t in range(260):
+                a = pick_action(rng, [np.asarray(obs[0]), np.asarray(obs[1])], env.action_space.n, greedy)
+                obs, r, done, _ = env.step(a)
+                actions.append(a)
+                prox.append([int(v) for v in env._get_wolf_proximities()] + [int(v) for v in env._get_bush_proximities()])
+                if done:
+                    obs = env.reset()
+                    actions.append(-1)
+                    prox.append([int(v) for v in env._get_wolf_proximities()] + [int(v) for v in env._get_bush_proximities()])
+            key = "%s_%d" % (name, env_id)
+            out[key + "_actions"] = np.asarray(actions, dtype=np.int8)
+            out[key + "_prox"] = np.asarray(prox, dtype=np.uint8)
+            meta.append({"name": name, "options": opts, "seed": 17, "env_id": env_id, "key": key})
+            print("ego golden:", key, len(actions), "events; bush proximities seen:", sorted(set(np.asarray(prox)[:, 5:].ravel().tolist())))
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "ego.npz"), meta=json.dumps(meta), **out)
+
+
 if __name__ == "__main__":
-    features()
-    render()
+    import sys
+    which = sys.argv[1:] or ["features", "render", "ego"]
+    for w in which:
+        {"features": features, "render": render, "ego": ego}[w]()

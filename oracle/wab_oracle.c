@@ -429,3 +429,32 @@ int64_t wab_oracle_run(const WabOracleConfig *cfg, uint64_t seed, int64_t n_envs
     if (checksum_out) *checksum_out = total;
     return n_envs * n_steps;
 }
+
+/* Egocentric proximity observations, wab_env.py:637-667 (+ generate_potential_actions :71-84, the EgoCentric
+ * _get_obs :951-958): for the five squares the ostrich can reach next (up, right, down, left, stay) the taxicab
+ * distance to the nearest wolf (ALL wolves, fresh spawns included) and to the nearest bush record with food > 0 (EVERY
+ * cell ever seen this episode, not just the window), as proximity = clip(max_distance - distance, 0, max_distance),
+ * max_distance = width // 2 + height // 2 + 1 (:932-934). Without any wolf (bush) the reference takes the distances
+ * to be pd.Series([0] * 5) (:648, :664), i.e. proximity max_distance. out10 = wolves[5], bushes[5]. */
+void wab_oracle_ego_proximities(const WabOracleEnv *e, int32_t *out10) {
+    const int32_t maxd = e->cfg.width / 2 + e->cfg.height / 2 + 1;
+    const int32_t cx[5] = { e->ox, e->ox + 1, e->ox, e->ox - 1, e->ox };
+    const int32_t cy[5] = { e->oy + 1, e->oy, e->oy - 1, e->oy, e->oy };
+    for (int a = 0; a < 5; ++a) {
+        int32_t dw = -1, db = -1;
+        for (int32_t k = 0; k < e->nw; ++k) {
+            const int32_t d = abs(cx[a] - e->wx[k]) + abs(cy[a] - e->wy[k]);
+            if (dw < 0 || d < dw) dw = d;
+        }
+        for (int32_t k = 0; k < e->nrec; ++k) {
+            if (e->recs[k].food <= 0) continue;
+            const int32_t d = abs(cx[a] - e->recs[k].x) + abs(cy[a] - e->recs[k].y);
+            if (db < 0 || d < db) db = d;
+        }
+        if (dw < 0) dw = 0;
+        if (db < 0) db = 0;
+        int32_t pw = maxd - dw, pb = maxd - db;
+        out10[a] = pw < 0 ? 0 : (pw > maxd ? maxd : pw);
+        out10[5 + a] = pb < 0 ? 0 : (pb > maxd ? maxd : pb);
+    }
+}

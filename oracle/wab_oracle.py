@@ -73,6 +73,7 @@ def lib():
         L.wab_oracle_get_bushes.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.wab_oracle_philox.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.wab_oracle_philox2.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]
+        L.wab_oracle_ego_proximities.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.wab_oracle_run.restype = ctypes.c_int64
         L.wab_oracle_run.argtypes = [ctypes.POINTER(OracleConfig), ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64,
                                      ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_uint64)]
@@ -155,6 +156,12 @@ class OracleEnv:
         if lib().wab_oracle_step(self._h, int(action), ctypes.byref(self._obs), ctypes.byref(r), ctypes.byref(d)):
             raise IndexError("single positional indexer is out-of-bounds")
         return self._obs_tuple(), r.value, bool(d.value)
+
+    def ego_proximities(self):
+        """(wolf proximities[5], bush proximities[5]) of wab_env.py:637-667 for up, right, down, left, stay."""
+        out = np.zeros(10, dtype=np.int32)
+        lib().wab_oracle_ego_proximities(self._h, out.ctypes.data)
+        return [int(v) for v in out[:5]], [int(v) for v in out[5:]]
 
     def hidden_state(self):
         x, y, role, status, turn = (ctypes.c_int32() for _ in range(5))

@@ -17,7 +17,7 @@ EXPORTS = [
     "wab_vec_create", "wab_vec_reset", "wab_vec_step", "wab_vec_step_many", "wab_vec_step_host",
     "wab_vec_reset_host", "wab_vec_stats", "wab_vec_stats_device", "wab_vec_export_state", "wab_vec_num_envs", "wab_vec_lanes_per_env",
     "wab_vec_destroy", "wab_philox_device", "wab_vec_bind_features", "wab_pragmatic_features",
-    "wab_vec_flatten_features", "wab_vec_flatten_features_noisy", "wab_sample_categorical", "wab_policy_tail", "wab_vec_flat_dim", "wab_vec_host_block_layout", "wab_vec_step_host_packed",
+    "wab_vec_flatten_features", "wab_vec_flatten_features_noisy", "wab_sample_categorical", "wab_policy_tail", "wab_vec_enable_ego", "wab_vec_ego_proximities", "wab_vec_flat_dim", "wab_vec_host_block_layout", "wab_vec_step_host_packed",
     "wab2_create", "wab2_kernel_kind", "wab2_reset", "wab2_turn", "wab2_export_state", "wab2_import_state", "wab2_destroy", "wab_last_error", "wab_abi_version",
 ]
 
@@ -74,6 +74,8 @@ def load():
     L.wab_vec_flatten_features_noisy.argtypes = [vp, vp, i64, vp, ctypes.c_int32, ctypes.c_float, vp, vp]
     L.wab_sample_categorical.argtypes = [vp, ctypes.c_int32, i64, ctypes.c_int32, ctypes.c_uint64, vp, vp, vp]
     L.wab_policy_tail.argtypes = [vp, i32, vp, vp, i64, i32, ctypes.c_float, ctypes.c_float, ctypes.c_float, u64, vp, vp, vp, vp, vp, vp]
+    L.wab_vec_enable_ego.argtypes = [vp]
+    L.wab_vec_ego_proximities.argtypes = [vp, vp, vp]
     L.wab_vec_flat_dim.argtypes = [vp]
     L.wab_vec_flat_dim.restype = i32
     L.wab2_create.argtypes = [vp, i64, u64, u64, i32, ctypes.POINTER(vp)]

@@ -67,6 +67,8 @@ struct StatePtrs {
     uint8_t* logcnt;     // [log_cap][N]
     unsigned long long* stats;  // [8]  totals, refreshed by wab_stats_reduce_kernel when somebody asks
     unsigned long long* wstats; // [warps of the grid][8]  every warp accumulates into its own row: no atomics, no barrier
+    uint32_t* hist;      // [hist_len][N] ostrich position after turn t of the current episode, or null (egocentric observations only)
+    int32_t hist_len;
     int64_t n;
 };
 
@@ -365,6 +367,7 @@ wab_step_kernel(const __grid_constant__ Params P, const StatePtrs st, const uint
         if (c.active && t + 1 < n_steps) a_next = *ap;   // prefetch: off the critical path
         if (c.active) {
             env_step<F64, LPE>(P, E, S, a, O, coop);
+            if (st.hist && c.writer && E.turn < (uint32_t)st.hist_len) st.hist[(int64_t)E.turn * n + c.idx] = pack_xy(E.x, E.y);
             need_reset = O.done && P.auto_reset;
             acc_outcome += 1ull << (16u * O.outcome);    // auto_reset = 0: every step that reports done counts
             acc_misc += (unsigned long long)O.ate | ((unsigned long long)O.bad_action << 16);
@@ -660,6 +663,84 @@ __global__ void wab_sample_kernel(const __grid_constant__ Params P, const void* 
     actions[i] = (uint8_t)pick;
 }
 
+// Egocentric proximity observations (wab_env.py:637-667, :951-958): for the five squares the ostrich can reach next
+// (up, right, down, left, stay) the proximity max_distance - taxicab distance (clipped to [0, max_distance]) of the
+// nearest wolf and of the nearest bush with food among EVERY cell seen this episode. One warp per env, on the state
+// as stored after the last step: wolves go over the lanes; the cells of the taxicab-11 diamond around the ostrich go
+// over the lanes too — inside the window the occupancy mask answers, outside it a cell counts iff some earlier
+// position of this episode had it in view (position history, st.hist), its procedural draw makes it a bush and the
+// depletion log has not emptied it. No wolf (no bush) at all: the reference substitutes distance 0 (:648, :664).
+__global__ void __launch_bounds__(128) wab_ego_kernel(const __grid_constant__ Params P, const StatePtrs st, uint8_t* __restrict__ out10) {
+    __shared__ uint32_t hs[4][1025];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t idx = (int64_t)blockIdx.x * 4 + warp, n = st.n;
+    if (idx >= n) return;
+    constexpr int MAXD = VIEW / 2 + VIEW / 2 + 1;
+    const uint32_t pos = st.pos[idx], misc = st.misc[idx], nl = st.nlog[idx];
+    const int32_t x = unpack_x(pos), y = unpack_y(pos);
+    const uint32_t nw = ((misc >> 11) & 15u) | (((nl >> 9) & 7u) << 4), dep = (misc >> 15) & 1u, nlog = nl & 0xFFu;
+    int32_t turn = (int32_t)(misc >> 16);
+    if (turn > st.hist_len - 1) turn = st.hist_len - 1;
+    const uint4 mb = st.bush[idx];
+    const uint32_t m[4] = {mb.x, mb.y, mb.z, mb.w};
+    const uint2 bk = st.bkey[idx];
+    const uint32_t logsig = st.logsig[idx];
+    for (int t = lane; t <= turn; t += 32) hs[warp][t] = t == 0 ? 0u : st.hist[(int64_t)t * n + idx];   // turn 0 is (0, 0)
+    __syncwarp();
+    const int32_t cx[5] = {x, x + 1, x, x - 1, x}, cy[5] = {y + 1, y, y - 1, y, y};       // generate_potential_actions :76-82
+    int32_t dw[5], db[5];
+#pragma unroll
+    for (int a = 0; a < 5; ++a) { dw[a] = 1 << 20; db[a] = 1 << 20; }
+    for (uint32_t k = (uint32_t)lane; k < nw; k += 32) {
+        const uint32_t p = st.wolves[(int64_t)k * n + idx];
+        const int32_t wx = unpack_x(p), wy = unpack_y(p);
+#pragma unroll
+        for (int a = 0; a < 5; ++a) dw[a] = min(dw[a], abs(cx[a] - wx) + abs(cy[a] - wy));
+    }
+    constexpr int SPAN = 2 * MAXD + 1;                       // 23 x 23 box around the ostrich, diamond inside
+    for (int c = lane; c < SPAN * SPAN; c += 32) {
+        const int32_t ddx = c / SPAN - MAXD, ddy = c % SPAN - MAXD;
+        if (abs(ddx) + abs(ddy) > MAXD) continue;            // farther than 10 from all five squares: proximity 0 anyway
+        const int32_t px = x + ddx, py = y + ddy;
+        bool has;
+        if (abs(ddx) <= HALF && abs(ddy) <= HALF) {
+            const int bit = 11 * (HALF - ddx) + (HALF - ddy);     // [5 - (objx - x)][5 - (objy - y)]
+            has = (m[bit >> 5] >> (bit & 31)) & 1u;
+        } else {
+            bool seen = false;
+            for (int t = 0; t <= turn && !seen; ++t) {
+                const uint32_t h = hs[warp][t];
+                seen = abs(px - unpack_x(h)) <= HALF && abs(py - unpack_y(h)) <= HALF;
+            }
+            has = false;
+            if (seen && P.n_bush_thr > 0) {
+                const uint32_t word = bush_word_rare(pack_xy(px >> 1, py >> 1) ^ bk.x, bk.y, P.rk2[0], bush_lane(px, py));
+                has = word >= P.thr_bush1;
+                if (has && dep && (logsig & cell_sig(pack_xy(px, py)))) {
+                    const uint32_t cell = pack_xy(px, py);
+                    for (uint32_t l = 0; l < nlog; ++l)
+                        if (st.logcell[(int64_t)l * n + idx] == cell) { has = alive_after(P, word, (uint32_t)st.logcnt[(int64_t)l * n + idx]); break; }
+                }
+            }
+        }
+        if (has) {
+#pragma unroll
+            for (int a = 0; a < 5; ++a) db[a] = min(db[a], abs(cx[a] - px) + abs(cy[a] - py));
+        }
+    }
+    uint32_t res = 0;
+#pragma unroll
+    for (int a = 0; a < 5; ++a) {
+        int32_t w = __reduce_min_sync(FULL, dw[a]), b = __reduce_min_sync(FULL, db[a]);
+        if (w >= (1 << 20)) w = 0;                            // pd.Series([0] * 5), :648
+        if (b >= (1 << 20)) b = 0;                            // :664
+        const int32_t pw = max(0, min(MAXD, MAXD - w)), pb = max(0, min(MAXD, MAXD - b));
+        if (lane == a) res = (uint32_t)pw;
+        if (lane == 5 + a) res = (uint32_t)pb;
+    }
+    if (lane < 10) out10[idx * 10 + lane] = (uint8_t)res;
+}
+
 __global__ void wab_philox_kernel(const __grid_constant__ Params P, const uint32_t* __restrict__ ctr, int64_t n,
                                   uint32_t* __restrict__ outw) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -706,6 +787,7 @@ struct WabVec {
     uint8_t* stage;
     size_t stage_bytes;
     int64_t stat_rows; // rows of st.wstats
+    uint32_t* d_hist; // position history of every env's current episode (egocentric observations), or null
     int lpe;          // lanes per env chosen at create (see pick_lpe)
     int mb;           // CTAs per SM the thread-per-env kernel is built for (see pick_mb)
     uint8_t* d_features;   // bound feature output, or null
@@ -937,6 +1019,7 @@ void wab_vec_destroy(WabVec* h) {
     if (!h) return;
     DeviceGuard guard(h->device);
     if (h->slab) cudaFree(h->slab);
+    if (h->d_hist) cudaFree(h->d_hist);
     if (h->d_thr) cudaFree(h->d_thr);
     if (h->stage) cudaFree(h->stage);
     if (h->host_graph) cudaGraphExecDestroy(h->host_graph);
@@ -1178,6 +1261,28 @@ int wab_vec_export_state(WabVec* h, int32_t* x, int32_t* y, double* food, int32_
     delete[] pos; delete[] misc; delete[] ep; delete[] bush; delete[] nl; delete[] fd;
     delete[] wv; delete[] lcell; delete[] lcnt;
     if (e != cudaSuccess) return cuda_fail(e, "export_state");
+    return WAB_OK;
+}
+
+int wab_vec_enable_ego(WabVec* h) {
+    if (!h) return fail(WAB_E_NULL, "null argument");
+    if (h->d_hist) return WAB_OK;
+    if (h->cfg.max_turns > 1023) return fail(WAB_E_UNSUPPORTED, "egocentric observations keep a position history of at most 1,023 turns");
+    DeviceGuard guard(h->device);
+    const size_t len = (size_t)h->cfg.max_turns + 1;
+    WAB_CUDA(cudaMalloc(&h->d_hist, 4 * len * (size_t)h->n));
+    WAB_CUDA(cudaMemset(h->d_hist, 0, 4 * len * (size_t)h->n));
+    h->st.hist = h->d_hist; h->st.hist_len = (int32_t)len;
+    if (h->host_graph) { cudaGraphExecDestroy(h->host_graph); h->host_graph = nullptr; }   // captured with the old StatePtrs
+    return WAB_OK;
+}
+
+int wab_vec_ego_proximities(WabVec* h, uint8_t* d_out10, void* stream) {
+    if (!h || !d_out10) return fail(WAB_E_NULL, "null argument");
+    if (!h->d_hist) return fail(WAB_E_CONFIG, "call wab_vec_enable_ego before the first reset");
+    DeviceGuard guard(h->device);
+    wab_ego_kernel<<<(unsigned)((h->n + 3) / 4), 128, 0, (cudaStream_t)stream>>>(h->P, h->st, d_out10);
+    WAB_CUDA(cudaGetLastError());
     return WAB_OK;
 }
 

@@ -45,7 +45,7 @@ def _ptr(t: Optional[torch.Tensor]):
 class VecEnv:
     def __init__(self, num_envs: int, game_options: Optional[dict] = None, device="cuda", seed: int = 0,
                  env_id_base: int = 0, auto_reset: bool = True, wolf_cap: int = 16, log_cap: Optional[int] = None,
-                 force_f64_food: bool = False, features: bool = False):
+                 force_f64_food: bool = False, features: bool = False, ego: bool = False):
         self._h = None
         self._bound = None     # feature buffer currently bound in the handle
         self.lib = _lib.load()  # raises if the CUDA library is unavailable — no fallback
@@ -69,6 +69,9 @@ class VecEnv:
                                            ctypes.byref(handle)))
         self._h = handle
         self.lanes_per_env = int(self.lib.wab_vec_lanes_per_env(self._h))
+        self.with_ego = bool(ego)
+        if ego:      # egocentric observation family: the kernels keep every episode's position history
+            _lib.check(self.lib.wab_vec_enable_ego(self._h))
         self.with_features = bool(features)
         self.flat_dim = int(self.lib.wab_vec_flat_dim(self._h))
         self._out = self._alloc(None)
@@ -214,6 +217,18 @@ class VecEnv:
         _lib.check(self.lib.wab_sample_categorical(_ptr(probs), int(probs.dtype == torch.bfloat16), probs.shape[0],
                                                    probs.shape[1], int(seed) & (2 ** 64 - 1), _ptr(counter), _ptr(out),
                                                    self._stream()))
+        return out
+
+    def ego_proximities(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The reference's egocentric observations (``_get_wolf_proximities`` / ``_get_bush_proximities``,
+        wab_env.py:637-667) of the state left by the last reset()/step(): u8[N, 10] = wolves[5], bushes[5] for the
+        squares up, right, down, left, stay; ``WolvesAndBushesEnvEgoCentric._get_obs`` (:951-958) is
+        ``(out[:, 5:], food, role, status)``. Needs ``VecEnv(ego=True)``."""
+        if not self.with_ego:
+            raise ValueError("ego_proximities needs VecEnv(ego=True)")
+        if out is None:
+            out = torch.empty((self.num_envs, 10), dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.wab_vec_ego_proximities(self._h, _ptr(out), self._stream()))
         return out
 
     # ------------------------------------------------------------------ host-buffer entry points
