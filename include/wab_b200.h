@@ -161,6 +161,10 @@ int64_t wab_vec_num_envs(const WabVec *h);
 /* Lanes cooperating on one env (1, 4, 8, 16 or 32), chosen at create from the batch size so that a
  * small batch still covers every SM; results do not depend on it. */
 int wab_vec_lanes_per_env(const WabVec *h);
+/* Which kernels serve this handle: 0 = the specialised 11 x 11 / spawn-margin-1 kernels (a 121-bit window sliding in
+ * registers), 1 = the warp-per-env kernels for every other odd viewport up to 31 x 31 and margins 1, 2 (wab_generic.cuh;
+ * WAB_GENERIC=1 in the environment forces them onto the default geometry, for tests). Results are identical. */
+int wab_vec_kernel_kind(const WabVec *h);
 void wab_vec_destroy(WabVec *h);
 
 /* ---- next row of the path: the reference's PragmaticObsWrapper (wab_env.py:670-824), the observation

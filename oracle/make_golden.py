@@ -3,6 +3,7 @@
 
     python -m oracle.make_golden            # all option sets, in parallel
     python -m oracle.make_golden defaults   # one set
+    python -m oracle.make_golden --sized    # viewports other than 11x11 / spawn margins other than 1
 
 Each trace is produced by the unmodified ``/root/reference/wab_env.py`` under ``oracle/ref_shim``
 (keyed draws, pandas-3 compatibility) driven by a seeded action trace, and records after every
@@ -39,6 +40,17 @@ OPTION_SETS = {
 }
 
 
+#: viewports other than 11x11 and spawn margins other than 1 (the reference is generic in both: wab_env.py:25-26, :34,
+#: :147-148, :510-576) -> tests/golden/sized_<name>.npz, same record layout
+SIZED_SETS = {
+    "5x5_m1": ({"width": 5, "height": 5, "chance_wolf_on_square": 0.01, "bush_power": 20}, 31, 3, 400, "greedy"),
+    "7x9_m1": ({"width": 7, "height": 9, "chance_wolf_on_square": 0.004, "lookout_only": False, "starting_role": None}, 32, 8, 400, "greedy"),
+    "11x11_m2": ({"wolf_spawn_margin": 2, "chance_wolf_on_square": 0.002}, 33, 1, 400, "random"),
+    "15x13_m2": ({"width": 15, "height": 13, "wolf_spawn_margin": 2, "chance_wolf_on_square": 0.002, "bush_power": 40}, 34, 21, 350, "greedy"),
+    "31x31_m2": ({"width": 31, "height": 31, "wolf_spawn_margin": 2, "chance_wolf_on_square": 0.0005, "max_turns": 60}, 35, 6, 170, "greedy"),
+}
+
+
 def bush_digest(bushes):
     """Order-free 64-bit digest of the bush record map {(x, y): food}."""
     h = 0
@@ -52,8 +64,10 @@ def bush_digest(bushes):
 def trace(name):
     from . import ref_shim
 
-    overrides, seed, env_id, n_events, policy = OPTION_SETS[name]
+    sized = name in SIZED_SETS
+    overrides, seed, env_id, n_events, policy = (SIZED_SETS if sized else OPTION_SETS)[name]
     env = ref_shim.make_env(overrides, seed=seed, env_id=env_id)
+    ci, cj = env.game_options["width"] // 2, env.game_options["height"] // 2
     n_act = env.action_space.n
     rng = np.random.default_rng(seed * 7919 + env_id)
     rec = {k: [] for k in ("action", "grids", "food", "role", "status", "reward", "done", "x", "y", "food_f64",
@@ -84,7 +98,7 @@ def trace(name):
             push(-1, o, 0.0, False)
             obs, done = rec["grids"][-1], False
             continue
-        if policy == "greedy" and obs[1][5, 5] == 1 and rng.random() < 0.75:
+        if policy == "greedy" and obs[1][ci, cj] == 1 and rng.random() < 0.75:
             a = 4  # stay on the bush (and, with 6 actions, become gatherer)
         else:
             a = int(rng.integers(0, n_act))
@@ -101,12 +115,12 @@ def trace(name):
     out["meta"] = np.array(json.dumps({"name": name, "overrides": overrides, "seed": seed, "env_id": env_id,
                                        "n_actions": n_act, "policy": policy}))
     os.makedirs(GOLDEN_DIR, exist_ok=True)
-    np.savez_compressed(os.path.join(GOLDEN_DIR, "trace_%s.npz" % name), **out)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, ("sized_%s.npz" if sized else "trace_%s.npz") % name), **out)
     return name, len(rec["action"]), int(np.sum(out["done"])), int(np.max(out["n_wolves"]))
 
 
 def main(argv):
-    names = argv or list(OPTION_SETS)
+    names = list(SIZED_SETS) if argv == ["--sized"] else (argv or list(OPTION_SETS))
     with mp.get_context("spawn").Pool(min(len(names), os.cpu_count() or 1)) as pool:
         for res in pool.imap_unordered(trace, names):
             print("golden trace %-28s events=%d dones=%d max_wolves=%d" % res, flush=True)

@@ -69,8 +69,11 @@ def test_config_errors_map_to_reference_exceptions():
     h = ctypes.c_void_p()
     rc = L.wab_vec_create(ctypes.byref(cs), thr.ctypes.data, len(thr), 16, 0, 0, 0, ctypes.byref(h))
     assert rc == 2 and b"odd" in L.wab_last_error()           # ValueError at wab_env.py:147-148
-    cs.width = 13
+    cs.width = 33
     cs.height = 13
     rc = L.wab_vec_create(ctypes.byref(cs), thr.ctypes.data, len(thr), 16, 0, 0, 0, ctypes.byref(h))
-    assert rc == 3                                             # valid for the reference, not implemented here
+    assert rc == 3 and b"31 x 31" in L.wab_last_error()       # valid for the reference, not implemented here
+    cs.width, cs.wolf_spawn_margin = 13, 3
+    rc = L.wab_vec_create(ctypes.byref(cs), thr.ctypes.data, len(thr), 16, 0, 0, 0, ctypes.byref(h))
+    assert rc == 3 and b"margin" in L.wab_last_error()
     assert L.wab_vec_create(None, None, 0, 1, 0, 0, 0, ctypes.byref(h)) == 1

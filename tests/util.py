@@ -12,8 +12,13 @@ def golden_names():
     return sorted(os.path.basename(p)[len("trace_"):-len(".npz")] for p in glob.glob(os.path.join(GOLDEN_DIR, "trace_*.npz")))
 
 
-def load_golden(name):
-    z = np.load(os.path.join(GOLDEN_DIR, "trace_%s.npz" % name))
+def sized_names():
+    """Traces of viewports other than 11x11 / spawn margins other than 1 (oracle/make_golden.py --sized)."""
+    return sorted(os.path.basename(p)[len("sized_"):-len(".npz")] for p in glob.glob(os.path.join(GOLDEN_DIR, "sized_*.npz")))
+
+
+def load_golden(name, sized=False):
+    z = np.load(os.path.join(GOLDEN_DIR, ("sized_%s.npz" if sized else "trace_%s.npz") % name))
     meta = json.loads(str(z["meta"]))
     return meta, {k: z[k] for k in z.files if k != "meta"}
 

@@ -15,7 +15,7 @@ _lib = None
 
 EXPORTS = [
     "wab_vec_create", "wab_vec_reset", "wab_vec_step", "wab_vec_step_many", "wab_vec_step_host",
-    "wab_vec_reset_host", "wab_vec_stats", "wab_vec_stats_device", "wab_vec_export_state", "wab_vec_num_envs", "wab_vec_lanes_per_env",
+    "wab_vec_reset_host", "wab_vec_stats", "wab_vec_stats_device", "wab_vec_export_state", "wab_vec_num_envs", "wab_vec_lanes_per_env", "wab_vec_kernel_kind",
     "wab_vec_destroy", "wab_philox_device", "wab_vec_bind_features", "wab_pragmatic_features",
     "wab_vec_flatten_features", "wab_vec_flatten_features_noisy", "wab_sample_categorical", "wab_policy_tail", "wab_vec_enable_ego", "wab_vec_ego_proximities", "wab_vec_flat_dim", "wab_vec_host_block_layout", "wab_vec_step_host_packed",
     "wab2_create", "wab2_kernel_kind", "wab2_reset", "wab2_turn", "wab2_export_state", "wab2_import_state", "wab2_destroy", "wab_last_error", "wab_abi_version",
@@ -64,6 +64,7 @@ def load():
     L.wab_vec_export_state.argtypes = [vp] * 14
     L.wab_vec_num_envs.argtypes = [vp]
     L.wab_vec_num_envs.restype = i64
+    L.wab_vec_kernel_kind.argtypes = [vp]
     L.wab_vec_lanes_per_env.argtypes = [vp]
     L.wab_vec_lanes_per_env.restype = i32
     L.wab_vec_destroy.argtypes = [vp]
@@ -90,7 +91,7 @@ def load():
     L.wab_last_error.restype = ctypes.c_char_p
     L.wab_abi_version.restype = i32
     for name in EXPORTS:
-        if name not in ("wab_vec_num_envs", "wab_vec_lanes_per_env", "wab_vec_flat_dim", "wab_vec_destroy", "wab2_destroy",
+        if name not in ("wab_vec_num_envs", "wab_vec_lanes_per_env", "wab_vec_kernel_kind", "wab_vec_flat_dim", "wab_vec_destroy", "wab2_destroy",
                         "wab_last_error", "wab_abi_version"):
             getattr(L, name).restype = ctypes.c_int
     _lib = L

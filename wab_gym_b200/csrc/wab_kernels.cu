@@ -750,6 +750,12 @@ __global__ void wab_philox_kernel(const __grid_constant__ Params P, const uint32
     outw[4 * i] = w[0]; outw[4 * i + 1] = w[1]; outw[4 * i + 2] = w[2]; outw[4 * i + 3] = w[3];
 }
 
+}  // namespace
+
+#include "wab_generic.cuh"
+
+namespace {
+
 // ---------------------------------------------------------------------------------------- host
 thread_local std::string g_err;
 
@@ -788,6 +794,9 @@ struct WabVec {
     size_t stage_bytes;
     int64_t stat_rows; // rows of st.wstats
     uint32_t* d_hist; // position history of every env's current episode (egocentric observations), or null
+    bool generic;     // viewport other than 11 x 11 or spawn margin other than 1: warp-per-env kernels of wab_generic.cuh
+    GenGeo geo;
+    int64_t obs_bytes; // 3 * width * height
     int lpe;          // lanes per env chosen at create (see pick_lpe)
     int mb;           // CTAs per SM the thread-per-env kernel is built for (see pick_mb)
     uint8_t* d_features;   // bound feature output, or null
@@ -911,6 +920,16 @@ int pick_mb(const WabVec* h) {
 int launch_step(WabVec* h, int n_steps, const uint8_t* d_actions, const WabObs& obs, float* d_reward,
                 uint8_t* d_done, uint8_t* d_info, cudaStream_t s, int lpe = 0) {
     OutPtrs out{obs.d_grids, obs.d_food, obs.d_role, obs.d_status, d_reward, d_done, d_info, h->d_features};
+    if (h->generic) {
+        const unsigned grid = (unsigned)((h->n + GEN_WARPS - 1) / GEN_WARPS);
+        const size_t smem = sizeof(uint32_t) * (size_t)GEN_WARPS * (size_t)h->geo.warp_words;
+        if (h->cfg.food_mode == WAB_FOOD_F64)
+            launch_pdl(wab_generic_step_kernel<true>, grid, GEN_WARPS * 32, smem, s, h->P, h->st, h->geo, d_actions, n_steps, out);
+        else
+            launch_pdl(wab_generic_step_kernel<false>, grid, GEN_WARPS * 32, smem, s, h->P, h->st, h->geo, d_actions, n_steps, out);
+        WAB_CUDA(cudaGetLastError());
+        return WAB_OK;
+    }
     WAB_DISPATCH_LPE(lpe ? lpe : h->lpe, launch_step_t, h, d_actions, n_steps, out, s);
     WAB_CUDA(cudaGetLastError());
     return WAB_OK;
@@ -927,11 +946,11 @@ int ensure_stage(WabVec* h, size_t bytes) {
 }
 
 struct StageLayout { size_t actions, grids, food, role, status, reward, done, info, total; };
-StageLayout stage_layout(int64_t n) {
+StageLayout stage_layout(int64_t n, int64_t obs_bytes = OBS_BYTES) {
     StageLayout L;
     size_t o = 0;
     L.actions = o; o = align_up(o + (size_t)n, 256);
-    L.grids = o; o = align_up(o + (size_t)n * OBS_BYTES, 256);
+    L.grids = o; o = align_up(o + (size_t)n * (size_t)obs_bytes, 256);
     L.food = o; o = align_up(o + (size_t)n, 256);
     L.role = o; o = align_up(o + (size_t)n, 256);
     L.status = o; o = align_up(o + (size_t)n, 256);
@@ -964,6 +983,9 @@ int wab_vec_create(const WabConfig* cfg, const uint32_t* bush_thr, int32_t n_bus
     if (!h) return fail(WAB_E_CUDA, "out of host memory");
     memset(h, 0, sizeof(*h));
     h->cfg = *cfg; h->device = device; h->n = n_envs; h->host_mapped = -1;
+    h->generic = cfg->width != VIEW || cfg->height != VIEW || cfg->wolf_spawn_margin != 1 || getenv("WAB_GENERIC") != nullptr;
+    h->geo = make_gen_geo(cfg->width, cfg->height, cfg->wolf_spawn_margin, cfg->wolf_cap);
+    h->obs_bytes = 3 * (int64_t)cfg->width * cfg->height;
 
     Params& P = h->P;
     params_from_config(*cfg, bush_thr, n_bush_thr, seed, env_id_base, P);
@@ -991,7 +1013,8 @@ int wab_vec_create(const WabConfig* cfg, const uint32_t* bush_thr, int32_t n_bus
         const size_t threads = lpe == 1 ? (size_t)WAB_THREADS_LPE1 : (size_t)WAB_THREADS_LPEN, epb = threads / lpe;
         return (n + epb - 1) / epb * (threads / 32);
     };
-    const size_t stat_rows = warps_of(1) > warps_of((size_t)h->lpe) ? warps_of(1) : warps_of((size_t)h->lpe);
+    const size_t stat_rows = h->generic ? (n + GEN_WARPS - 1) / GEN_WARPS * GEN_WARPS
+                                        : (warps_of(1) > warps_of((size_t)h->lpe) ? warps_of(1) : warps_of((size_t)h->lpe));
     const size_t o_wstats = o; o = align_up(o + 64 * stat_rows, 256);
     cudaError_t e = cudaMalloc(&h->slab, o);
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaMalloc(state)"); }
@@ -1028,7 +1051,8 @@ void wab_vec_destroy(WabVec* h) {
 }
 
 int64_t wab_vec_num_envs(const WabVec* h) { return h ? h->n : 0; }
-int wab_vec_lanes_per_env(const WabVec* h) { return h ? h->lpe : 0; }
+int wab_vec_kernel_kind(const WabVec* h) { return h && h->generic ? 1 : 0; }
+int wab_vec_lanes_per_env(const WabVec* h) { return h ? (h->generic ? 32 : h->lpe) : 0; }
 
 int wab_vec_reset(WabVec* h, const uint8_t* d_mask, WabObs obs, void* stream) {
     if (!h || !obs.d_grids || !obs.d_food || !obs.d_role || !obs.d_status) return fail(WAB_E_NULL, "null argument");
@@ -1036,6 +1060,16 @@ int wab_vec_reset(WabVec* h, const uint8_t* d_mask, WabObs obs, void* stream) {
     DeviceGuard guard(h->device);
     OutPtrs out{obs.d_grids, obs.d_food, obs.d_role, obs.d_status, nullptr, nullptr, nullptr, h->d_features};
     cudaStream_t s = (cudaStream_t)stream;
+    if (h->generic) {
+        const unsigned grid = (unsigned)((h->n + GEN_WARPS - 1) / GEN_WARPS);
+        const size_t smem = sizeof(uint32_t) * (size_t)GEN_WARPS * (size_t)h->geo.warp_words;
+        if (h->cfg.food_mode == WAB_FOOD_F64)
+            launch_pdl(wab_generic_reset_kernel<true>, grid, GEN_WARPS * 32, smem, s, h->P, h->st, h->geo, d_mask, out);
+        else
+            launch_pdl(wab_generic_reset_kernel<false>, grid, GEN_WARPS * 32, smem, s, h->P, h->st, h->geo, d_mask, out);
+        WAB_CUDA(cudaGetLastError());
+        return WAB_OK;
+    }
     WAB_DISPATCH(launch_reset_t, h, d_mask, out, s);
     WAB_CUDA(cudaGetLastError());
     return WAB_OK;
@@ -1066,14 +1100,14 @@ int wab_vec_step_host(WabVec* h, const uint8_t* h_actions, uint8_t* h_grids, uin
         return fail(WAB_E_NULL, "null argument");
     DeviceGuard guard(h->device);
     cudaStream_t s = (cudaStream_t)stream;
-    const StageLayout L = stage_layout(h->n);
+    const StageLayout L = stage_layout(h->n, h->obs_bytes);
     if (int rc = ensure_stage(h, L.total)) return rc;
     uint8_t* b = h->stage;
     const size_t n = (size_t)h->n;
     WAB_CUDA(cudaMemcpyAsync(b + L.actions, h_actions, n, cudaMemcpyHostToDevice, s));
     WabObs obs{b + L.grids, b + L.food, b + L.role, b + L.status};
     if (int rc = launch_step(h, 1, b + L.actions, obs, (float*)(b + L.reward), b + L.done, b + L.info, s)) return rc;
-    WAB_CUDA(cudaMemcpyAsync(h_grids, b + L.grids, n * OBS_BYTES, cudaMemcpyDeviceToHost, s));
+    WAB_CUDA(cudaMemcpyAsync(h_grids, b + L.grids, n * (size_t)h->obs_bytes, cudaMemcpyDeviceToHost, s));
     WAB_CUDA(cudaMemcpyAsync(h_food, b + L.food, n, cudaMemcpyDeviceToHost, s));
     WAB_CUDA(cudaMemcpyAsync(h_role, b + L.role, n, cudaMemcpyDeviceToHost, s));
     WAB_CUDA(cudaMemcpyAsync(h_status, b + L.status, n, cudaMemcpyDeviceToHost, s));
@@ -1086,7 +1120,7 @@ int wab_vec_step_host(WabVec* h, const uint8_t* h_actions, uint8_t* h_grids, uin
 
 int wab_vec_host_block_layout(const WabVec* h, int64_t* offsets7, int64_t* total_bytes) {
     if (!h || !offsets7 || !total_bytes) return fail(WAB_E_NULL, "null argument");
-    const StageLayout L = stage_layout(h->n);
+    const StageLayout L = stage_layout(h->n, h->obs_bytes);
     const size_t v[7] = {L.grids, L.food, L.role, L.status, L.reward, L.done, L.info};
     for (int k = 0; k < 7; ++k) offsets7[k] = (int64_t)(v[k] - L.grids);
     *total_bytes = (int64_t)(L.total - L.grids);
@@ -1097,7 +1131,7 @@ int wab_vec_step_host_packed(WabVec* h, const uint8_t* h_actions, uint8_t* h_blo
     if (!h || !h_actions || !h_block) return fail(WAB_E_NULL, "null argument");
     DeviceGuard guard(h->device);
     cudaStream_t s = (cudaStream_t)stream;
-    const StageLayout L = stage_layout(h->n);
+    const StageLayout L = stage_layout(h->n, h->obs_bytes);
     if (int rc = ensure_stage(h, L.total)) return rc;
     uint8_t* b = h->stage;
     WabObs obs{b + L.grids, b + L.food, b + L.role, b + L.status};
@@ -1172,13 +1206,13 @@ int wab_vec_reset_host(WabVec* h, uint8_t* h_grids, uint8_t* h_food, uint8_t* h_
     if (!h || !h_grids || !h_food || !h_role || !h_status) return fail(WAB_E_NULL, "null argument");
     DeviceGuard guard(h->device);
     cudaStream_t s = (cudaStream_t)stream;
-    const StageLayout L = stage_layout(h->n);
+    const StageLayout L = stage_layout(h->n, h->obs_bytes);
     if (int rc = ensure_stage(h, L.total)) return rc;
     uint8_t* b = h->stage;
     const size_t n = (size_t)h->n;
     WabObs obs{b + L.grids, b + L.food, b + L.role, b + L.status};
     if (int rc = wab_vec_reset(h, nullptr, obs, stream)) return rc;
-    WAB_CUDA(cudaMemcpyAsync(h_grids, b + L.grids, n * OBS_BYTES, cudaMemcpyDeviceToHost, s));
+    WAB_CUDA(cudaMemcpyAsync(h_grids, b + L.grids, n * (size_t)h->obs_bytes, cudaMemcpyDeviceToHost, s));
     WAB_CUDA(cudaMemcpyAsync(h_food, b + L.food, n, cudaMemcpyDeviceToHost, s));
     WAB_CUDA(cudaMemcpyAsync(h_role, b + L.role, n, cudaMemcpyDeviceToHost, s));
     WAB_CUDA(cudaMemcpyAsync(h_status, b + L.status, n, cudaMemcpyDeviceToHost, s));
@@ -1268,6 +1302,7 @@ int wab_vec_enable_ego(WabVec* h) {
     if (!h) return fail(WAB_E_NULL, "null argument");
     if (h->d_hist) return WAB_OK;
     if (h->cfg.max_turns > 1023) return fail(WAB_E_UNSUPPORTED, "egocentric observations keep a position history of at most 1,023 turns");
+    if (h->generic) return fail(WAB_E_UNSUPPORTED, "egocentric observations are implemented for the 11 x 11 viewport with spawn margin 1");
     DeviceGuard guard(h->device);
     const size_t len = (size_t)h->cfg.max_turns + 1;
     WAB_CUDA(cudaMalloc(&h->d_hist, 4 * len * (size_t)h->n));
@@ -1288,6 +1323,8 @@ int wab_vec_ego_proximities(WabVec* h, uint8_t* d_out10, void* stream) {
 
 int wab_vec_bind_features(WabVec* h, uint8_t* d_features) {
     if (!h) return fail(WAB_E_NULL, "null argument");
+    if (d_features && (h->cfg.width != VIEW || h->cfg.height != VIEW))
+        return fail(WAB_E_UNSUPPORTED, "PragmaticObsWrapper features are implemented for the 11 x 11 viewport");
     if (((uintptr_t)d_features & 3u) != 0) return fail(WAB_E_CONFIG, "d_features must be 4-byte aligned");
     h->d_features = d_features;
     return WAB_OK;

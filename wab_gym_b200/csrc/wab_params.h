@@ -19,9 +19,12 @@ inline int validate_config(const WabConfig* cfg, int32_t n_bush_thr, int64_t n_e
     if (cfg->abi_version != WAB_ABI_VERSION) return fail(WAB_E_CONFIG, "WabConfig.abi_version mismatch");
     if (cfg->width % 2 == 0 || cfg->height % 2 == 0)
         return fail(WAB_E_CONFIG, "width and height must be odd numbers");       // wab_env.py:147-148
-    if (cfg->width != VIEW || cfg->height != VIEW)
-        return fail(WAB_E_UNSUPPORTED, "the sm_100a kernels implement the 11x11 viewport only");
-    if (cfg->wolf_spawn_margin != 1) return fail(WAB_E_UNSUPPORTED, "the sm_100a kernels implement wolf_spawn_margin = 1 only");
+    if (cfg->width < 1 || cfg->height < 1 || cfg->width > 31 || cfg->height > 31)
+        return fail(WAB_E_UNSUPPORTED, "viewports up to 31 x 31 are implemented");
+    if (cfg->wolf_spawn_margin < 1 || cfg->wolf_spawn_margin > 2)
+        return fail(WAB_E_UNSUPPORTED, "wolf_spawn_margin 1 and 2 are implemented");
+    if (cfg->restrict_view && (cfg->width != VIEW || cfg->height != VIEW))
+        return fail(WAB_E_UNSUPPORTED, "restrict_view exists for the 11 x 11 viewport only (the reference's tile masks are 11 x 11 literals)");
     if (n_envs < 1) return fail(WAB_E_CONFIG, "n_envs must be >= 1");
     for (int k = 1; k < 32; ++k)
         if (cfg->spawn_cdf[k] < cfg->spawn_cdf[k - 1] || cfg->init_cdf[k] < cfg->init_cdf[k - 1])

@@ -106,7 +106,7 @@ class WolvesAndBushesEnv:
                                             int(seed) & 0xFFFFFFFFFFFFFFFF, int(env_id), int(device),
                                             ctypes.byref(handle)))
         self._h = handle
-        self._grids = np.zeros((3, 11, 11), dtype=np.uint8)
+        self._grids = np.zeros((3, w, h), dtype=np.uint8)
         self._b = {k: np.zeros(1, dtype=np.uint8) for k in ("action", "food", "role", "status", "done", "info")}
         self._reward = np.zeros(1, dtype=np.float32)
         self.current_turn = 0
@@ -152,7 +152,7 @@ class WolvesAndBushesEnv:
         """RGB frame in the reference's colours (wab_env.py:468-502): wolves red, bushes green, ostriches blue."""
         wolves, bushes, ostriches = (self._grids[p].astype(np.uint8) for p in range(3))
         status = int(self._b["status"][0])
-        image = np.zeros((11, 11, 3), dtype=np.uint8)
+        image = np.zeros(self._grids.shape[1:] + (3,), dtype=np.uint8)
         image[:, :, 0], image[:, :, 1], image[:, :, 2] = 255 * wolves, 255 * bushes, 255 * ostriches
         empty = (image[:, :, 0] == 0) & (image[:, :, 1] == 0) & (image[:, :, 2] == 0)
         image[empty] = 127 if status == 2 else 255

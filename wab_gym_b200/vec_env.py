@@ -60,6 +60,9 @@ class VecEnv:
             game_options, auto_reset=auto_reset, force_f64_food=force_f64_food, wolf_cap=wolf_cap, log_cap=log_cap)
         self.game_options = self.game.options
         self.n_actions = self.game.n_actions
+        #: viewport (wab_env.py:25-26): grids are u8[N, 3, width, height]; 11 x 11 with spawn margin 1 runs on the
+        #: specialised kernels, every other odd size up to 31 x 31 (margins 1, 2) on the warp-per-env generic ones
+        self.view = (int(self.game_options["width"]), int(self.game_options["height"]))
         self.seed, self.env_id_base = int(seed), int(env_id_base)
         cs = self.game.to_struct()
         thr = np.ascontiguousarray(self.game.bush_thr, dtype=np.uint32)
@@ -69,6 +72,7 @@ class VecEnv:
                                            ctypes.byref(handle)))
         self._h = handle
         self.lanes_per_env = int(self.lib.wab_vec_lanes_per_env(self._h))
+        self.generic_kernels = bool(self.lib.wab_vec_kernel_kind(self._h))
         self.with_ego = bool(ego)
         if ego:      # egocentric observation family: the kernels keep every episode's position history
             _lib.check(self.lib.wab_vec_enable_ego(self._h))
@@ -85,7 +89,7 @@ class VecEnv:
         extra = {"features": torch.empty(lead + (28,), **u8)} if self.with_features else {}
         return {
             **extra,
-            "grids": torch.empty(lead + (3, 11, 11), **u8), "food": torch.empty(lead, **u8),
+            "grids": torch.empty(lead + (3,) + self.view, **u8), "food": torch.empty(lead, **u8),
             "role": torch.empty(lead, **u8), "status": torch.empty(lead, **u8),
             "reward": torch.empty(lead, dtype=torch.float32, device=dev), "done": torch.empty(lead, **u8),
             "info": torch.empty(lead, **u8),
@@ -242,7 +246,8 @@ class VecEnv:
         block = torch.empty(total.value, dtype=torch.uint8, pin_memory=pinned)
         view = lambda k, nbytes: block[int(offs[k]):int(offs[k]) + nbytes]
         hb = {"actions": torch.empty(n, dtype=torch.uint8, pin_memory=pinned), "block": block,
-              "grids": view(0, n * 363).view(n, 3, 11, 11), "food": view(1, n), "role": view(2, n), "status": view(3, n),
+              "grids": view(0, n * 3 * self.view[0] * self.view[1]).view(n, 3, *self.view), "food": view(1, n), "role": view(2, n),
+              "status": view(3, n),
               "reward": view(4, 4 * n).view(torch.float32), "done": view(5, n), "info": view(6, n)}
         # numpy views of the same memory (cheap per-step access from Python) and the two pointers a step passes
         hb["np"] = {k: v.numpy() for k, v in hb.items() if k != "block"}
