@@ -578,3 +578,37 @@ def test_wolf_packs_beyond_32_stay_exact_on_device(lpe, monkeypatch):
             cur[i] = o.reset() if d else c
     assert peak > 32 and env.stats()["overflows"] == 0
     env.close()
+
+
+@pytest.mark.parametrize("lpe", [8, 16])
+@pytest.mark.parametrize("name", ["defaults", "dense", "six_actions_random_start", "restrict_view", "tiny_bushes"])
+def test_time_chunked_kernel_equals_single_steps(lpe, name, monkeypatch):
+    """The multi-step launch of the lanes-per-env geometries runs ahead of the rules inside chunks of LPE steps (bush and
+    spawn draws made in parallel from the known actions, falling back after an episode end). Every output of launches of
+    1, 5, LPE, LPE + 1, 23 and 64 steps — observations, features, reward, done, info, the position history, the hidden
+    state and the statistics — equals what single-step launches (the step-by-step kernel) give."""
+    monkeypatch.setenv("WAB_LPE", str(lpe))
+    monkeypatch.setenv("WAB_CHUNK", "1")            # opt-in: measured no faster than the step-by-step kernel (DESIGN.md §4)
+    overrides, _ = OPTION_SETS[name]
+    n, seed = 45, 123
+    a = _vec(n, overrides, seed=seed, features=True, wolf_cap=64, ego=True)
+    b = _vec(n, overrides, seed=seed, features=True, wolf_cap=64, ego=True)
+    assert a.lanes_per_env == lpe
+    gen = torch.Generator(device="cuda").manual_seed(lpe)
+    a.reset(); b.reset()
+    for T in (1, 5, lpe, lpe + 1, 23, 64, 2 * lpe):
+        acts = torch.randint(0, a.n_actions, (T, n), dtype=torch.uint8, device="cuda", generator=gen)
+        acts[T // 2, 3] = 77                                   # a bad action inside a chunk
+        oa, ra, da, ia = a.step_many(acts)
+        for t in range(T):
+            ob, rb, db, ib = b.step(acts[t])
+            for x, y in zip(oa, ob):
+                assert torch.equal(x[t], y), (lpe, name, T, t)
+            assert torch.equal(ra[t], rb) and torch.equal(da[t], db) and torch.equal(ia["info"][t], ib["info"]), (lpe, name, T, t)
+            assert torch.equal(ia["features"][t], ib["features"]), (lpe, name, T, t)
+        assert torch.equal(a.ego_proximities(), b.ego_proximities()), (lpe, name, T)
+        sa, sb = a.export_state(), b.export_state()
+        for k in sa:
+            assert np.array_equal(sa[k], sb[k]), (lpe, name, T, k)
+    assert a.stats() == b.stats() and a.stats()["bad_actions"] == 7 * 1
+    a.close(); b.close()

@@ -188,14 +188,14 @@ __device__ __forceinline__ void stream_put(uint32_t* stream, int bit0, bool last
 // table means no CTA barrier anywhere in a single-step launch).
 template <bool USE_LUT = true>
 __device__ __forceinline__ void stream_flush(const uint32_t* stream, const uint2* lut, uint8_t* gA, int off, int end,
-                                             int lane) {
+                                             int lane, bool lut_built = true) {
     const uint16_t* hs = reinterpret_cast<const uint16_t*>(stream);
     const int c_lo = (off + 15) >> 4, c_hi = end >> 4;            // chunks entirely inside [off, end)
 #pragma unroll kFlushUnroll
     for (int c = c_lo + lane; c < c_hi; c += 32) {
         const uint32_t h = hs[c];
         uint2 lo, hi;
-        if (USE_LUT) {
+        if (USE_LUT && lut_built) {
             lo = lut[h & 0xFFu]; hi = lut[h >> 8];
         } else {
             lo = make_uint2(nibble_to_bytes(h & 15u), nibble_to_bytes((h >> 4) & 15u));
@@ -313,14 +313,14 @@ __device__ __forceinline__ Ctx make_ctx(int64_t n) {
 // in the grids tensor (any alignment).
 template <int LPE>
 __device__ __forceinline__ void emit_obs(uint32_t* stream, const uint2* lut, const Ctx& c, uint8_t* grids,
-                                         int64_t first_byte, const uint32_t wm[4], const uint32_t bm[4]) {
+                                         int64_t first_byte, const uint32_t wm[4], const uint32_t bm[4], bool lut_built = true) {
     constexpr int EPW = Geo<LPE>::EPW;
     const int off = (int)(first_byte & 15);
     const int total = off + EPW * OBS_BYTES;
     if (c.sub == 0)
         stream_put(stream, off + OBS_BYTES * c.slot, c.slot == EPW - 1, total, wm, bm, c.active);
     __syncwarp();
-    stream_flush<LPE == 1>(stream, lut, grids + (first_byte - off), off, off + OBS_BYTES * c.n_valid, c.lane);
+    stream_flush<true>(stream, lut, grids + (first_byte - off), off, off + OBS_BYTES * c.n_valid, c.lane, lut_built);
     __syncwarp();
 }
 
@@ -338,8 +338,12 @@ wab_step_kernel(const __grid_constant__ Params P, const StatePtrs st, const uint
     uint32_t* wolves_s = smem + c.env_local;                                  // [wolf_cap][EPB]
     uint32_t* stream = smem + P.wolf_cap * EPB + (threadIdx.x >> 5) * WarpStream<Geo<LPE>::EPW>::WORDS;
     uint2* lut = reinterpret_cast<uint2*>(smem + P.wolf_cap * EPB + Geo<LPE>::STREAM);   // 256 x 8 bytes (thread-per-env only)
+    // The 256-entry byte-expansion table (and the CTA barrier that publishes it) serves the thread-per-env kernel, whose
+    // ALU pipes are the bottleneck; the lanes-per-env kernels expand with multiplies: measured on one box at 4,096 envs,
+    // 240 steps per launch, 1.757e9 env-steps/s without the table against 1.703e9 with it (profiles/r2_ab_small_batch.txt).
+    const bool lut_built = LPE == 1;
     pdl_launch_dependents();               // the next launch may be scheduled now; it waits below before touching state
-    if (LPE == 1) build_lut(lut);
+    if (lut_built) build_lut(lut);
     pdl_wait();                            // everything this launch reads or writes follows the previous launch
     Coop<LPE> coop;
     coop.sub = (uint32_t)c.sub;
@@ -388,8 +392,176 @@ wab_step_kernel(const __grid_constant__ Params P, const StatePtrs st, const uint
             if (out.features) write_features(out.features, o, O);
         }
 #ifndef WAB_EXP_NOEMIT
-        emit_obs<LPE>(stream, lut, c, out.grids, first_byte, O.wm, O.bm);
+        emit_obs<LPE>(stream, lut, c, out.grids, first_byte, O.wm, O.bm, lut_built);
 #endif
+    }
+    if (c.writer) store_env<F64>(st, c.idx, E, wolves_s, EPB);
+    uint32_t cnt[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    if (c.writer) {
+        const uint32_t fin = (uint32_t)(acc_outcome >> 16) & 0xFFFFu, sta = (uint32_t)(acc_outcome >> 32) & 0xFFFFu,
+                       kil = (uint32_t)(acc_outcome >> 48) & 0xFFFFu;
+        cnt[WAB_STAT_EPISODES] = fin + sta + kil;
+        cnt[WAB_STAT_STEPS] = (uint32_t)n_steps;
+        cnt[WAB_STAT_FINISHED] = fin; cnt[WAB_STAT_STARVED] = sta; cnt[WAB_STAT_KILLED] = kil;
+        cnt[WAB_STAT_EATS] = (uint32_t)acc_misc & 0xFFFFu;
+        cnt[WAB_STAT_BAD_ACTIONS] = (uint32_t)(acc_misc >> 16) & 0xFFFFu;
+        cnt[WAB_STAT_OVERFLOWS] = (uint32_t)(acc_misc >> 32) & 0xFFFFu;
+    }
+    flush_stats(st.wstats, cnt);
+}
+
+// ---- the multi-step kernel of the lanes-per-env geometries, chunked over time -------------------------------------
+// A group of LPE lanes owns one env. Run step by step (wab_step_kernel above), a small batch is bound by the length
+// of one step's dependent instruction chain: ~770 instructions per warp-step at < 2 warps per scheduler. But only a
+// small part of a step depends on the previous one. For a chunk of LPE consecutive steps:
+//   phase 1 (parallel over the lanes of a group, one step each): the actions of the chunk are known, so the ostrich's
+//     path is a prefix sum; the cells each move reveals are keyed by position only and the spawn draw by (episode, turn)
+//     only — the 6 x LPE bush-block draws of the chunk are spread over the group's lanes and every lane makes the spawn
+//     draw of "its" step. All of it assumes that the episode does not end inside the chunk.
+//   phase 2 (sequential, the group's lanes in lock step): the rules of wab_core.cuh with the draws handed in; after an
+//     episode end the rest of the chunk falls back to drawing in place (pre_ok = false). Each step's planes and
+//     scalars are parked in shared memory.
+//   phase 3 (parallel again): lane (env, s) puts step s of its env into the bit stream of that step and writes its
+//     scalars; the warp then flushes the LPE streams.
+// Results are identical to wab_step_kernel's (same functions, same draws); WAB_CHUNK=0 selects the step-by-step kernel.
+template <int LPE> struct ChunkGeo {
+    static constexpr int EPW = 32 / LPE;
+    static constexpr int SW = WarpStream<EPW>::WORDS;      // stream words of one step of the warp's envs
+    static constexpr int RES = 12;                         // words parked per (env, step)
+    static constexpr int WARP_WORDS = LPE * SW + 32 * RES + 3 * 32;   // streams, results, line / position / move per (env, step)
+};
+
+template <bool F64, int LPE>
+__global__ void __launch_bounds__(Geo<LPE>::THREADS, 1)
+wab_step_chunk_kernel(const __grid_constant__ Params P, const StatePtrs st, const uint8_t* __restrict__ actions,
+                      const int n_steps, const OutPtrs out) {
+    extern __shared__ uint32_t smem[];
+    constexpr int EPB = Geo<LPE>::EPB, EPW = Geo<LPE>::EPW, SW = ChunkGeo<LPE>::SW, RES = ChunkGeo<LPE>::RES;
+    const int64_t n = st.n;
+    const Ctx c = make_ctx<LPE>(n);
+    uint32_t* wolves_s = smem + c.env_local;                                   // [wolf_cap][EPB]
+    uint32_t* wbase = smem + P.wolf_cap * EPB + (threadIdx.x >> 5) * ChunkGeo<LPE>::WARP_WORDS;
+    uint32_t* streams = wbase;                         // [LPE][SW]
+    uint32_t* res = streams + LPE * SW;                // [EPW][LPE][RES]
+    uint32_t* lines = res + 32 * RES;                  // [EPW][LPE]  OR of the step's six reveal_block words
+    uint32_t* spos = lines + 32;                       // [EPW][LPE]  position after the step, if no episode ends before it
+    uint32_t* smove = spos + 32;                       // [EPW][LPE]  the step's move code
+    pdl_launch_dependents();
+    pdl_wait();
+    Coop<LPE> coop;
+    coop.sub = (uint32_t)c.sub;
+    coop.gmask = LPE == 32 ? FULL : (((1u << (LPE & 31)) - 1u) << (c.lane - c.sub));
+    const int gfirst = c.lane - c.sub, me = c.slot * LPE + c.sub;
+    Env E;
+    Slots S;
+    S.wolves = wolves_s; S.wstride = EPB;
+    S.logcell = st.logcell + (c.active ? c.idx : 0); S.logcnt = st.logcnt + (c.active ? c.idx : 0); S.lstride = n;
+    if (c.active) load_env<F64>(P, st, c.idx, E, wolves_s, EPB);
+    else { E = Env(); }
+    unsigned long long acc_outcome = 0ull, acc_misc = 0ull;
+    for (int t0 = 0; t0 < n_steps; t0 += LPE) {
+        const int Sn = min(LPE, n_steps - t0);
+        // ---------------- phase 1: lane `sub` prepares step t0 + sub of its env
+        uint32_t a_mine = 0xFFu;
+        if (c.active && c.sub < Sn) a_mine = actions[(int64_t)(t0 + c.sub) * n + c.idx];
+        const uint32_t code = a_mine >= (uint32_t)P.n_actions ? 0x05u : (uint32_t)(P.act_tbl >> (8 * a_mine)) & 0xFFu;
+        int32_t px = (int32_t)(code & 3u) - 1, py = (int32_t)((code >> 2) & 3u) - 1;
+#pragma unroll
+        for (int d = 1; d < LPE; d <<= 1) {             // inclusive prefix sum of the moves over the group
+            const int32_t ux = __shfl_up_sync(FULL, px, d, LPE), uy = __shfl_up_sync(FULL, py, d, LPE);
+            if (c.sub >= d) { px += ux; py += uy; }
+        }
+        lines[me] = 0u;
+        spos[me] = pack_xy(E.x + px, E.y + py);
+        smove[me] = code;
+        uint64_t v_mine = 0ull;
+        if (c.active && c.sub < Sn && P.wolves) v_mine = binomial_draw(P, E.env_id, E.episode, SITE_SPAWN, E.turn + (uint32_t)c.sub + 1u);
+        __syncwarp();
+        if (c.active && P.n_bush_thr > 0) {
+            for (int j = c.sub; j < 6 * Sn; j += LPE) {  // bush-block draw j = (step, block) of the chunk
+                const int sj = j / 6, b = j - 6 * sj, at = c.slot * LPE + sj;
+                const uint32_t mj = smove[at];
+                const int32_t jdx = (int32_t)(mj & 3u) - 1, jdy = (int32_t)((mj >> 2) & 3u) - 1;
+                if (jdx != 0 || jdy != 0) {
+                    const uint32_t pj = spos[at];
+                    const RevealGeo g = reveal_geo(unpack_x(pj), unpack_y(pj), jdx, jdy);
+                    atomicOr(lines + at, reveal_block(P, g, E.bk_a, E.bk_b, b));
+                }
+            }
+        }
+        __syncwarp();
+        // ---------------- phase 2: the rules, step by step
+        bool spec_ok = true;
+        for (int s2 = 0; s2 < Sn; ++s2) {
+            StepOut O;
+            bool need_reset = false;
+            const uint32_t a = __shfl_sync(FULL, a_mine, gfirst + s2);
+            const uint64_t v = ((uint64_t)__shfl_sync(FULL, (uint32_t)(v_mine >> 32), gfirst + s2) << 32) |
+                               (uint64_t)__shfl_sync(FULL, (uint32_t)v_mine, gfirst + s2);
+            const uint32_t line = lines[c.slot * LPE + s2];
+            if (c.active) {
+                env_step_impl<F64, LPE, true>(P, E, S, a, O, coop, spec_ok, line, v);
+                if (st.hist && c.writer && E.turn < (uint32_t)st.hist_len) st.hist[(int64_t)E.turn * n + c.idx] = pack_xy(E.x, E.y);
+                need_reset = O.done && P.auto_reset;
+                acc_outcome += 1ull << (16u * O.outcome);
+                acc_misc += (unsigned long long)O.ate | ((unsigned long long)O.bad_action << 16);
+            } else {
+                O = StepOut();
+            }
+            if (__any_sync(FULL, need_reset)) {
+                warp_reset<F64, LPE>(P, E, S, need_reset, c.lane, O.wm, O.bm, O.overflow);
+                if (need_reset) {
+                    O.food_obs = food_observation(P, E, F64);
+                    O.role = E.role; O.status = E.status;
+                    spec_ok = false;               // the draws made ahead belonged to the episode that just ended
+                }
+            }
+            apply_view_mask(P, O.role, O.wm, O.bm);
+            if (c.writer) {
+                acc_misc += (unsigned long long)O.overflow << 32;
+                uint4* r = reinterpret_cast<uint4*>(res + (c.slot * LPE + s2) * RES);
+                r[0] = make_uint4(O.wm[0], O.wm[1], O.wm[2], O.wm[3]);
+                r[1] = make_uint4(O.bm[0], O.bm[1], O.bm[2], O.bm[3]);
+                r[2] = make_uint4(O.food_obs | (O.role << 8) | (O.status << 16) | (O.done << 24), O.info, __float_as_uint(O.reward), 0u);
+            }
+        }
+        __syncwarp();
+        // ---------------- phase 3: lane (env, s) publishes step t0 + s of its env
+        {
+            const int s3 = c.sub;
+            if (s3 < Sn) {
+                const int64_t fb3 = ((int64_t)(t0 + s3) * n + c.warp_first) * OBS_BYTES;
+                const int off3 = (int)(fb3 & 15);
+                const uint4* r = reinterpret_cast<const uint4*>(res + me * RES);
+                const uint4 w4 = r[0], b4 = r[1], sc = r[2];
+                const uint32_t wm[4] = {w4.x, w4.y, w4.z, w4.w}, bm[4] = {b4.x, b4.y, b4.z, b4.w};
+                stream_put(streams + s3 * SW, off3 + OBS_BYTES * c.slot, c.slot == EPW - 1, off3 + EPW * OBS_BYTES, wm, bm, c.active);
+                if (c.active) {
+                    const int64_t o3 = (int64_t)(t0 + s3) * n + c.idx;
+                    out.food[o3] = (uint8_t)(sc.x & 0xFFu);
+                    out.role[o3] = (uint8_t)((sc.x >> 8) & 0xFFu);
+                    out.status[o3] = (uint8_t)((sc.x >> 16) & 0xFFu);
+                    if (out.reward) out.reward[o3] = __uint_as_float(sc.z);
+                    if (out.done) out.done[o3] = (uint8_t)(sc.x >> 24);
+                    if (out.info) out.info[o3] = (uint8_t)sc.y;
+                    if (out.features) {
+                        StepOut O3;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) { O3.wm[k] = wm[k]; O3.bm[k] = bm[k]; }
+                        O3.food_obs = sc.x & 0xFFu; O3.role = (sc.x >> 8) & 0xFFu; O3.status = (sc.x >> 16) & 0xFFu;
+                        write_features(out.features, o3, O3);
+                    }
+                }
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int sf = 0; sf < Sn; ++sf) {
+                const int64_t fbs = ((int64_t)(t0 + sf) * n + c.warp_first) * OBS_BYTES;
+                const int offs = (int)(fbs & 15);
+                stream_flush<false>(streams + sf * SW, nullptr, out.grids + (fbs - offs), offs, offs + OBS_BYTES * c.n_valid, c.lane);
+            }
+            __syncwarp();
+        }
     }
     if (c.writer) store_env<F64>(st, c.idx, E, wolves_s, EPB);
     uint32_t cnt[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
@@ -421,6 +593,7 @@ wab_reset_kernel(const __grid_constant__ Params P, const StatePtrs st, const uin
     pdl_launch_dependents();
     if (LPE == 1) build_lut(lut);
     pdl_wait();
+    const bool lut_built = LPE == 1;
     Env E;
     Slots S;
     S.wolves = wolves_s; S.wstride = EPB;
@@ -446,7 +619,7 @@ wab_reset_kernel(const __grid_constant__ Params P, const StatePtrs st, const uin
         cnt[WAB_STAT_OVERFLOWS] += O.overflow;
         store_env<F64>(st, c.idx, E, wolves_s, EPB);
     }
-    emit_obs<LPE>(stream, lut, c, out.grids, c.warp_first * OBS_BYTES, O.wm, O.bm);
+    emit_obs<LPE>(stream, lut, c, out.grids, c.warp_first * OBS_BYTES, O.wm, O.bm, lut_built);
     flush_stats(st.wstats, cnt);
 }
 
@@ -813,7 +986,7 @@ struct WabVec {
 namespace {
 
 template <int LPE> size_t smem_bytes_for(const Params& P) {
-    return sizeof(uint32_t) * ((size_t)P.wolf_cap * Geo<LPE>::EPB + (size_t)Geo<LPE>::STREAM + (LPE == 1 ? 512 : 0));
+    return sizeof(uint32_t) * ((size_t)P.wolf_cap * Geo<LPE>::EPB + (size_t)Geo<LPE>::STREAM + 512);
 }
 template <bool F64, int LPE>
 void launch_step_t(const WabVec* h, const uint8_t* a, int T, const OutPtrs& out, cudaStream_t s);
@@ -844,9 +1017,21 @@ void launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t sm
     cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+// The time-chunked kernel is opt-in (WAB_CHUNK=1): bit-identical, but measured no faster than the step-by-step kernel at
+// 4,096 envs (1.77e9 vs 1.79e9 env-steps/s; profiles/r2e_*): the draws it makes ahead are ~15 % of a step's instructions,
+// and parking / re-reading every step's planes costs about as much.
+bool chunk_enabled() { const char* e = getenv("WAB_CHUNK"); return e && atoi(e) != 0; }
 template <bool F64, int LPE>
 void launch_step_t(const WabVec* h, const uint8_t* a, int T, const OutPtrs& out, cudaStream_t s) {
     const unsigned grid = (unsigned)((h->n + Geo<LPE>::EPB - 1) / Geo<LPE>::EPB);
+    if constexpr (LPE == 8 || LPE == 16) {
+        if (chunk_enabled() && T > 1) {          // the time-chunked kernel (a single step has nothing to run ahead of)
+            const size_t smem = sizeof(uint32_t) * ((size_t)h->P.wolf_cap * Geo<LPE>::EPB +
+                                                    (size_t)(Geo<LPE>::THREADS / 32) * ChunkGeo<LPE>::WARP_WORDS);
+            launch_pdl(wab_step_chunk_kernel<F64, LPE>, grid, Geo<LPE>::THREADS, smem, s, h->P, h->st, a, T, out);
+            return;
+        }
+    }
     if (LPE == 1 && h->mb == 7)
         launch_pdl(wab_step_kernel<F64, LPE, LPE == 1 ? 7 * kMbScale : Geo<LPE>::MIN_BLOCKS>, grid, Geo<LPE>::THREADS, smem_bytes_for<LPE>(h->P), s, h->P, h->st, a, T, out);
     else if (LPE == 1 && h->mb == 8)
