@@ -231,8 +231,9 @@ HostSim2* hostsim2_create(const Wab2Config* c, uint64_t seed, uint64_t env_id) {
     P.window_r = c->window_radius; P.starting_role = c->starting_role; P.ostrich_food = c->ostrich_starting_food;
     P.wolf_food = c->wolf_starting_food; P.wolf_eat_gain = c->wolf_food_for_eating_ostrich;
     P.bush_food = c->food_per_bush; P.bush_given = c->food_given_per_turn; P.env_id_base = 0;
-    h->words.assign((size_t)3 * P.n_entities, 0u);
+    h->words.assign((size_t)3 * P.n_entities, 0u);                       // [2E] table rows and food, then [E] object coords
     h->W.base = h->words.data(); h->W.stride = 1; h->W.env_id = (uint32_t)env_id;
+    h->W.obj = h->words.data() + 2 * P.n_entities; h->W.ostride = 1;
     world2_create(P, h->W);
     return h;
 }
@@ -252,7 +253,7 @@ void hostsim2_act(HostSim2* h, int32_t a, int32_t action, float* reward, int32_t
 }
 void hostsim2_state(const HostSim2* h, int32_t* out9, int32_t* turn) {
     for (int k = 0; k < h->P.n_entities; ++k) {
-        const uint32_t obj = h->words[3 * k], tab = h->words[3 * k + 1], food = h->words[3 * k + 2];
+        const uint32_t obj = h->words[2 * h->P.n_entities + k], tab = h->words[2 * k], food = h->words[2 * k + 1];
         int32_t* o = out9 + 9 * k;
         o[0] = (int32_t)entity_type(h->P, k); o[1] = unpack_x(obj); o[2] = unpack_y(obj); o[3] = (int32_t)(tab & 0xFFu);
         o[4] = (int32_t)((tab >> 8) & 0xFFu); o[5] = (int32_t)((tab >> 16) & 1u); o[6] = (int32_t)food;

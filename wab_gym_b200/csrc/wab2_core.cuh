@@ -28,15 +28,19 @@ struct Params2 {
     uint64_t env_id_base;
 };
 
-// entity k of this world: words at base[(3*k + f) * stride], f = 0 object coords (x:i16 | y:i16<<16, never
-// wrapped, World.py:331-332), 1 table row (X:8 | Y:8 | Visible:1 | role:1 | status:2), 2 food (integer-valued).
+// entity k of this world: three words — object coords (x:i16 | y:i16<<16, never wrapped, World.py:331-332), table row
+// (X:8 | Y:8 | Visible:1 | role:1 | status:2), food (integer-valued). Table row and food are what every observation and
+// co-location test scans: base[(2*k + f) * stride], f = 0 table row, 1 food (shared memory in the kernel). The object
+// coords are touched once per action only and stay where the state lives: obj[k * ostride] (global memory in the
+// kernel — a third less shared memory per world, which is what bounds the worlds resident per SM).
 struct World2 {
     uint32_t* base; int32_t stride;
+    uint32_t* obj; int64_t ostride;
     uint32_t env_id, episode, turn;
 };
-WAB_HD uint32_t& w2_obj(const World2& W, int k) { return W.base[(3 * k + 0) * W.stride]; }
-WAB_HD uint32_t& w2_tab(const World2& W, int k) { return W.base[(3 * k + 1) * W.stride]; }
-WAB_HD uint32_t& w2_food(const World2& W, int k) { return W.base[(3 * k + 2) * W.stride]; }
+WAB_HD uint32_t& w2_obj(const World2& W, int k) { return W.obj[(int64_t)k * W.ostride]; }
+WAB_HD uint32_t& w2_tab(const World2& W, int k) { return W.base[(2 * k + 0) * W.stride]; }
+WAB_HD uint32_t& w2_food(const World2& W, int k) { return W.base[(2 * k + 1) * W.stride]; }
 WAB_HD uint32_t tab_pack(uint32_t tx, uint32_t ty, uint32_t vis, uint32_t role, uint32_t status) {
     return tx | (ty << 8) | (vis << 16) | (role << 17) | (status << 18);
 }

@@ -23,13 +23,24 @@ struct Out2Ptrs {
     uint8_t* done;      // [A][N]
 };
 
+// thread-per-world kernels: table rows and food are staged in shared memory, object coords are used in place
+__device__ __forceinline__ void bind_world(const State2Ptrs& st, int64_t idx, World2& W) {
+    W.obj = st.ent + idx * st.stride_world; W.ostride = 3 * st.stride_word;
+}
 __device__ __forceinline__ void load_world(const Params2& P, const State2Ptrs& st, int64_t idx, World2& W) {
-    for (int k = 0; k < 3 * P.n_entities; ++k) W.base[k * W.stride] = st.ent[k * st.stride_word + idx * st.stride_world];
+    bind_world(st, idx, W);
+    for (int k = 0; k < P.n_entities; ++k) {
+        W.base[(2 * k) * W.stride] = st.ent[(3 * k + 1) * st.stride_word + idx * st.stride_world];
+        W.base[(2 * k + 1) * W.stride] = st.ent[(3 * k + 2) * st.stride_word + idx * st.stride_world];
+    }
     W.episode = st.episode[idx]; W.turn = st.turn[idx];
     W.env_id = (uint32_t)(P.env_id_base + (uint64_t)idx);
 }
 __device__ __forceinline__ void store_world(const Params2& P, const State2Ptrs& st, int64_t idx, const World2& W) {
-    for (int k = 0; k < 3 * P.n_entities; ++k) st.ent[k * st.stride_word + idx * st.stride_world] = W.base[k * W.stride];
+    for (int k = 0; k < P.n_entities; ++k) {
+        st.ent[(3 * k + 1) * st.stride_word + idx * st.stride_world] = W.base[(2 * k) * W.stride];
+        st.ent[(3 * k + 2) * st.stride_word + idx * st.stride_world] = W.base[(2 * k + 1) * W.stride];
+    }
     st.episode[idx] = W.episode; st.turn[idx] = W.turn;
 }
 
@@ -41,6 +52,7 @@ __global__ void wab2_init_kernel(const __grid_constant__ Params2 P, const State2
     World2 W;
     W.base = smem2 + threadIdx.x; W.stride = blockDim.x;
     if (mode == 0) {
+        bind_world(st, idx, W);
         W.env_id = (uint32_t)(P.env_id_base + (uint64_t)idx);
         world2_create(P, W);
     } else {
@@ -60,8 +72,8 @@ __global__ void wab2_turn_kernel(const __grid_constant__ Params2 P, const State2
     const bool active = idx < n;
     const int64_t warp_first = idx - lane;
     const int n_valid = (int)((n - warp_first) < 32 ? (n - warp_first > 0 ? n - warp_first : 0) : 32);
-    uint32_t* ents = smem2;                                          // [3E][bs]
-    uint32_t* streams = ents + 3 * P.n_entities * bs;                // [warps][stream_words]: one stream per warp
+    uint32_t* ents = smem2;                                          // [2E][bs] table rows and food
+    uint32_t* streams = ents + 2 * P.n_entities * bs;                // [warps][stream_words]: one stream per warp
     uint2* lut = reinterpret_cast<uint2*>(streams + (((bs >> 5) * stream_words + 1) & ~1));
     build_lut(lut);
     World2 W;
@@ -176,10 +188,10 @@ int wab2_create(const Wab2Config* cfg, int64_t n_envs, uint64_t seed, uint64_t e
     int max_smem = 48 * 1024;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     int bs = 128;
-    auto need = [&](int b) { return sizeof(uint32_t) * ((size_t)3 * E * b + (size_t)(((b >> 5) * h->stream_words + 1) & ~1) + 512); };
+    auto need = [&](int b) { return sizeof(uint32_t) * ((size_t)2 * E * b + (size_t)(((b >> 5) * h->stream_words + 1) & ~1) + 512); };
     while (bs > 32 && need(bs) > (size_t)max_smem / 2) bs >>= 1;
     if (need(bs) > (size_t)max_smem) { delete h; return fail(WAB_E_UNSUPPORTED, "too many entities for the shared-memory staging"); }
-    h->bs = bs; h->smem_turn = need(bs); h->smem_init = sizeof(uint32_t) * (size_t)3 * E * bs;
+    h->bs = bs; h->smem_turn = need(bs); h->smem_init = sizeof(uint32_t) * (size_t)2 * E * bs;
     cudaError_t e = cudaSuccess;
     if (h->grid) {
         h->smem_turn = sizeof(uint32_t) * ((size_t)4 * grid_geom(E, cfg->width, h->stream_words).total + 512);
