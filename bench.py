@@ -442,6 +442,14 @@ def v2_leg(ctx, n, dims, min_ms, name):
     S = 2 * env.R + 1
     bytes_per_turn = A * (3 * S * S + 9) + 2 * E * 8
     kernel = env.kernel_name() if hasattr(env, "kernel_name") else "wab2 turn kernel"
+    traffic, traffic_src = None, None
+    try:                      # DRAM bytes of one launch (= one turn of all worlds) as ncu measured them, scaled to this batch
+        with open(os.path.join(REPO, "profiles", "dram_traffic_table.json")) as fh:
+            hit = json.load(fh).get("v2_config3" if name.startswith("configs[2]") else "v2_config4")
+        if hit:
+            traffic, traffic_src = float(hit["bytes_per_world_turn"]) * n, "ncu (%s)" % hit["source"]
+    except Exception:
+        pass
     env.close()
     del env
     torch.cuda.empty_cache()
@@ -455,7 +463,8 @@ def v2_leg(ctx, n, dims, min_ms, name):
             "outputs": "per acting entity a %dx%dx3 u8 window + 5 int32 + reward + done, rewritten per turn (%d MB > L2)" % (
                 S, S, int(A * n * 3 * S * S / 1e6)),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": ctx.peak, "unit": "GB/s", "frac": achieved / ctx.peak,
-                         "bytes_per_world_turn": bytes_per_turn, "kernel": kernel, "traffic": None}}
+                         "bytes_per_world_turn": bytes_per_turn, "kernel": kernel, "traffic": traffic, "traffic_source": traffic_src,
+                         "frac_dram": (tps * traffic / n / 1e9 / ctx.peak) if traffic else None}}
 
 
 def rollout_leg(ctx, n, K, min_ms):
