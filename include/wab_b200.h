@@ -236,11 +236,13 @@ typedef struct Wab2World Wab2World;
 int wab2_create(const Wab2Config *cfg, int64_t n_envs, uint64_t seed, uint64_t env_id_base, int32_t device, Wab2World **out);
 /* reset_environment (WAB_Environment2.py:113-118) of every world. */
 int wab2_reset(Wab2World *h, void *stream);
-/* One world turn. Every array is ENTITY-MAJOR so that the worlds of a warp are contiguous: d_actions u8[A][N],
- * A = n_ostriches + n_wolves (bushes act with 0). Outputs per acting entity: d_planes u8[A][N][3][2R+1][2R+1]
+/* One world turn. d_actions u8[A][N] is ENTITY-MAJOR, A = n_ostriches + n_wolves (bushes act with 0). Outputs per
+ * acting entity, in the handle's output layout (wab2_output_layout): 0 = entity-major, d_planes u8[A][N][3][2R+1][2R+1]
  * (ostriches, wolves, bushes listed by get_observations at [dx+R][dy+R]; may be NULL), d_internal i32[A][N][5]
- * (x, y, food, role | is_running, status; may be NULL), d_reward f32[A][N], d_done u8[A][N]. The observation of
- * entity i is taken right before it acts. */
+ * (x, y, food, role | is_running, status; may be NULL), d_reward f32[A][N], d_done u8[A][N] — the worlds of a warp
+ * are contiguous; 1 = world-major, the same arrays with the first two dimensions exchanged ([N][A]...) — the A
+ * windows of a world are one contiguous run for the warp that owns it. The observation of entity i is taken right
+ * before it acts. */
 int wab2_turn(Wab2World *h, const uint8_t *d_actions, uint8_t *d_planes, int32_t *d_internal, float *d_reward,
               uint8_t *d_done, void *stream);
 /* Hidden state for tests: out9 i32[N][E][9] = type, x, y, table X, table Y, Visible, food, role, status. Synchronises. */
@@ -252,6 +254,9 @@ int wab2_import_state(Wab2World *h, const int32_t *in9, const int32_t *turn, voi
 /* Which kernel serves this handle: 0 = wab2_turn_kernel (one thread per world), 1 = wab2_grid_turn_kernel (one
  * warp per world with occupancy planes, for worlds every observation window fits once). Results are identical. */
 int wab2_kernel_kind(const Wab2World *h);
+/* Layout of wab2_turn's outputs for this handle: 0 = entity-major [A][N]..., 1 = world-major [N][A]... (the
+ * warp-per-world kernel). */
+int wab2_output_layout(const Wab2World *h);
 void wab2_destroy(Wab2World *h);
 
 /* Raw Philox4x32-10 on the device for n counters (cross-checks the RNG contract). d_ctr u32[n][4],

@@ -207,10 +207,10 @@ def test_vecworld2_outputs_never_touch_guard_bytes():
     n, G = 45, 256
     env = VecWorld2(n, 7, 9, 6, 4, 5, seed=2)
     env.reset_environment()
-    raw = torch.full((env.planes.numel() + 2 * G,), 0xAB, dtype=torch.uint8, device="cuda")
+    raw = torch.full((env.planes_store.numel() + 2 * G,), 0xAB, dtype=torch.uint8, device="cuda")
     # 16-byte aligned interior: G is a multiple of 16
-    inner = raw[G:G + env.planes.numel()].view(env.planes.shape)
-    env.planes = inner
+    inner = raw[G:G + env.planes_store.numel()].view(env.planes_store.shape)
+    env.planes_store = inner
     acts = torch.randint(0, 5, (env.n_acting, n), dtype=torch.uint8, device="cuda")
     for _ in range(4):
         env.turn(acts)

@@ -222,7 +222,7 @@ def gpu_checksums(env, actions, episodes, turns):
             planes, internal, reward, done = env.turn(actions[ep * turns + t])
             per = torch.empty((A, n), dtype=torch.int64, device="cuda")
             for a in range(A):    # float32 dot products are exact here: at most K (K + 1) / 2 < 2^24
-                per[a] = (planes[a].view(n, K).to(torch.float32) @ w).to(torch.int64)
+                per[a] = (planes[a].reshape(n, K).to(torch.float32) @ w).to(torch.int64)
             per += (internal.to(torch.int64) * iw).sum(-1) + 23 * reward.to(torch.int64) + 29 * done.to(torch.int64)
             total += int((per.sum(1) * ent_w).sum().item())
     st, _ = env.export_state()

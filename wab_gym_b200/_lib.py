@@ -18,7 +18,7 @@ EXPORTS = [
     "wab_vec_reset_host", "wab_vec_stats", "wab_vec_stats_device", "wab_vec_export_state", "wab_vec_num_envs", "wab_vec_lanes_per_env", "wab_vec_kernel_kind",
     "wab_vec_destroy", "wab_philox_device", "wab_vec_bind_features", "wab_pragmatic_features",
     "wab_vec_flatten_features", "wab_vec_flatten_features_noisy", "wab_sample_categorical", "wab_policy_tail", "wab_vec_enable_ego", "wab_vec_ego_proximities", "wab_vec_flat_dim", "wab_vec_host_block_layout", "wab_vec_step_host_packed",
-    "wab2_create", "wab2_kernel_kind", "wab2_reset", "wab2_turn", "wab2_export_state", "wab2_import_state", "wab2_destroy", "wab_last_error", "wab_abi_version",
+    "wab2_create", "wab2_kernel_kind", "wab2_output_layout", "wab2_reset", "wab2_turn", "wab2_export_state", "wab2_import_state", "wab2_destroy", "wab_last_error", "wab_abi_version",
 ]
 
 
@@ -85,6 +85,7 @@ def load():
     L.wab2_export_state.argtypes = [vp] * 4
     L.wab2_destroy.argtypes = [vp]
     L.wab2_kernel_kind.argtypes = [vp]
+    L.wab2_output_layout.argtypes = [vp]
     L.wab2_import_state.argtypes = [vp] * 4
     L.wab2_destroy.restype = None
     L.wab_philox_device.argtypes = [vp, ctypes.c_uint32, ctypes.c_uint32, i64, vp, vp]

@@ -1,11 +1,28 @@
 // wab2_grid.cuh — Environment 2.0 world turn, one WARP per world (for worlds with 2R+1 <= W, H <= 64).
 //
 // The thread-per-world kernel (wab2_kernels.cuh) walks every entity for every observation: fine for 33
-// entities, hopeless for the 64x64 world of BASELINE config 4 (328 entities, 72 observers per turn). Here the
+// entities, hopeless for the 64x64 world of BASELINE config 4 (328 entities, 72 observations per turn). Here the
 // world keeps, in shared memory, one occupancy bit plane per entity type (column x = 64 bits over y; a bit is
 // set iff a VISIBLE entity of that type has that table position), so an observation is 3 x (2R+1) rotated and
 // circle-masked column reads instead of an entity scan, a co-location test is one bit test (plus a ballot
 // over the candidates when it hits), and a move is two bit updates (with a ballot recount of the vacated cell).
+//
+// A turn has three parts:
+//   1. PRE-PASS, one lane per entity: everything an entity's action does to ITSELF depends on nothing any other
+//      entity does in the same turn (decode, move, role; World.py:25-43, :61-73, :331-332), and neither do its
+//      internal observation (World.py:50-51, :80-81) nor an ostrich's reward / done (ostriches act before any
+//      wolf can kill them in the turn: ids are ostriches, wolves, bushes). So they are computed 32 entities at a
+//      time; the new table row waits in `newtab` until the entity's place in the order.
+//   2. ORDERED LOOP over the entities (the only sequential part): entity a's window columns are read from the
+//      planes as they are right before it acts (get_obs(a) then take_action(a), Env2Tests.py:46-88) into a
+//      staging slot; then its pending row is committed, the planes follow, and default_game_update
+//      (World.py:93-132) runs when the plane says somebody is there.
+//   3. FLUSH, every kGridGroup observations: the staged column words of the group are turned into the u8 windows
+//      by all 32 lanes at once — lane -> (observation, 16-byte chunk), 16 bits from two neighbouring column
+//      words, byte expansion through the table, one streaming 16-byte store — and the < 16 ragged bytes at
+//      either end of a window as single bytes. A wolf's reward (its own food after its own action) is written
+//      by a post-pass, one lane per wolf.
+//
 // Semantics are those of wab2_core.cuh / the reference (World.py:93-132, :243-316, :325-377), including the
 // one visible difference between the reference's wrap rule and a true torus when every window fits the world:
 // the strict test `size < entity + radius` (World.py:264, :285) makes the single cell at delta = +radius
@@ -14,172 +31,268 @@
 
 namespace {
 
+constexpr int kGridGroup = 8;   // observations staged between two flushes
+
 struct GridGeom {        // shared-memory layout of one warp's world, in 32-bit words
-    int ent;             // [3][E]   obj, tab, food
-    int cols;            // [3][W]   u64 occupancy columns (2 words each)
-    int stream;          // observation bit stream
+    int tab;             // [E] table rows, then [E] food (contiguous, like the state in global memory)
+    int newtab;          // [A] pending rows of the pre-pass
+    int cols;            // [3][W] u64 occupancy columns (2 words each), then [2][W] u64 "more than one" columns (ostriches, wolves)
+    int stage;           // [kGridGroup][stage_words] window columns of the observations waiting for the flush
     int total;
 };
-__host__ __device__ inline GridGeom grid_geom(int E, int W, int stream_words) {
+__host__ __device__ inline int grid_stage_words(int S) { return 3 * S + 16 / S + 2; }   // zero words behind the last column
+__host__ __device__ inline GridGeom grid_geom(int E, int A, int W, int S) {
     GridGeom g;
-    g.ent = 0;
-    g.cols = (3 * E + 1) & ~1;
-    g.stream = g.cols + 3 * W * 2;
-    g.total = (g.stream + stream_words + 1) & ~1;
+    g.tab = 0;
+    g.newtab = 2 * E;
+    g.cols = (2 * E + A + 1) & ~1;
+    g.stage = g.cols + 5 * W * 2;
+    g.total = (g.stage + kGridGroup * grid_stage_words(S) + 2 + 1) & ~1;   // + 2: the flush reads one column pair past the last slot
     return g;
 }
 
 __device__ __forceinline__ uint64_t rot_window(uint64_t col, int s, int H) {   // bits (s + k) mod H of col at position k
-    if (H == 64) return s ? (col >> s) | (col << (64 - s)) : col;
     const uint64_t m = (1ull << H) - 1ull;
     return s ? ((col >> s) | (col << (H - s))) & m : col;
 }
-__device__ __forceinline__ void col_set(uint32_t* cols, int W, uint32_t type, uint32_t x, uint32_t y) {
-    atomicOr(cols + ((type * W + x) << 1) + (y >> 5), 1u << (y & 31));
-}
-__device__ __forceinline__ void col_clear(uint32_t* cols, int W, uint32_t type, uint32_t x, uint32_t y) {
-    atomicAnd(cols + ((type * W + x) << 1) + (y >> 5), ~(1u << (y & 31)));
-}
-__device__ __forceinline__ bool col_test(const uint32_t* cols, int W, uint32_t type, uint32_t x, uint32_t y) {
-    return (cols[((type * W + x) << 1) + (y >> 5)] >> (y & 31)) & 1u;
-}
+__device__ __forceinline__ int col_word(int W, uint32_t plane, uint32_t x, uint32_t y) { return (int)(((plane * W + x) << 1) + (y >> 5)); }
 // id range of an entity type
 __device__ __forceinline__ void type_range(const Params2& P, uint32_t type, int& lo, int& hi) {
     lo = type == T_OSTRICH ? 0 : (type == T_WOLF ? P.n_ostriches : P.n_ostriches + P.n_wolves);
     hi = type == T_OSTRICH ? P.n_ostriches : (type == T_WOLF ? P.n_ostriches + P.n_wolves : P.n_entities);
 }
-// After an entity of `type` left (or became invisible at) cell `cell` = X | Y << 8: clear the plane bit unless
-// another visible entity of that type is still there. All lanes call; tab[] must be up to date and synced.
-__device__ __forceinline__ void recount_cell(const Params2& P, const uint32_t* tab, uint32_t* cols, uint32_t type,
-                                             uint32_t cell, int lane) {
-    int lo, hi;
-    type_range(P, type, lo, hi);
-    const uint32_t want = cell | (1u << 16);
-    bool any = false;
-    for (int base = lo; base < hi; base += 32) {
-        const int k = base + lane;
-        any |= __any_sync(FULL, k < hi && (tab[k] & 0x1FFFFu) == want);
+// A visible entity of `type` arrived at (x, y). Planes 3, 4 say "possibly more than one here" for ostriches and wolves
+// (sticky until a recount): leaving a cell whose bit is clear needs no scan of the others. Every lane calls with the
+// same arguments; lane 0 is the only writer; ends with a warp barrier.
+__device__ __forceinline__ void plane_arrive(uint32_t* cols, int W, uint32_t type, uint32_t x, uint32_t y, int lane) {
+    const int w = col_word(W, type, x, y);
+    const uint32_t bit = 1u << (y & 31), old = cols[w];
+    __syncwarp();
+    if (lane == 0) {
+        cols[w] = old | bit;
+        if ((old & bit) && type != T_BUSH) cols[col_word(W, 3u + type, x, y)] |= bit;
     }
-    if (!any && lane == 0) col_clear(cols, P.width, type, cell & 0xFFu, (cell >> 8) & 0xFFu);
+    __syncwarp();
+}
+// A visible entity of `type` left `cell` = X | Y << 8 (or became invisible there); tab[] is already up to date.
+__device__ __forceinline__ void plane_leave(const Params2& P, const uint32_t* tab, uint32_t* cols, uint32_t type, uint32_t cell,
+                                            int lane) {
+    const int W = P.width;
+    const uint32_t x = cell & 0xFFu, y = (cell >> 8) & 0xFFu, bit = 1u << (y & 31);
+    const int w = col_word(W, type, x, y), wm = col_word(W, type == T_BUSH ? 0u : 3u + type, x, y);
+    const bool shared_cell = type == T_BUSH || (cols[wm] & bit);       // bushes only ever "move" in the first turn: always count
+    int left = 0;
+    if (shared_cell) {
+        int lo, hi;
+        type_range(P, type, lo, hi);
+        const uint32_t want = cell | (1u << 16);
+        for (int base = lo; base < hi; base += 32) {
+            const int k = base + lane;
+            left += __popc(__ballot_sync(FULL, k < hi && (tab[k] & 0x1FFFFu) == want));
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        if (left == 0) cols[w] &= ~bit;
+        if (shared_cell && type != T_BUSH && left < 2) cols[wm] &= ~bit;
+    }
     __syncwarp();
 }
 
-// One world turn, one warp per world.
+// Windows of the `g` observations staged in `stage` (slot e = entity a0 + e) -> `dst`, the first byte of entity a0's
+// window. The outputs of this kernel are WORLD-major, so the g windows are one run of g * obs_bytes bytes: bit p =
+// (type*S + dxi)*S + dyi of window e is byte e * obs_bytes + p of the run, which starts at ANY byte address — whole
+// 16-byte chunks go out as one streaming store per lane, the < 16 bytes at either end of the run byte by byte.
+__device__ __forceinline__ uint32_t window_bits16(const uint32_t* stage, int S, int SW, uint32_t inv_s, uint32_t e, uint32_t p) {
+    const uint32_t q = (p * inv_s) >> 20, r = p - q * (uint32_t)S;       // column word, bit in it; 16 bits from there on
+    const uint32_t* col = stage + e * SW + q;
+    uint32_t h = (col[0] >> r) | (col[1] << (S - r));
+    if (S < 15)                                                          // narrow windows: more than two columns in 16 bits
+        for (int filled = 2 * S - (int)r, k = 2; filled < 16; filled += S, ++k) h |= col[k] << filled;
+    return h;
+}
+__device__ __forceinline__ void grid_flush_group(const uint32_t* stage, const uint2* lut, uint8_t* dst, int g, int S, int SW,
+                                                 uint32_t inv_s, uint32_t inv_ob, int obs_bytes, int lane) {
+    // inv_s = ceil(2^20 / S): (p * inv_s) >> 20 == p / S for p < 3 S^2 (p * S < 2^20); inv_ob = ceil(2^32 / obs_bytes):
+    // __umulhi(b, inv_ob) == b / obs_bytes for b < kGridGroup * obs_bytes (b * obs_bytes < 2^32)
+    const int total = g * obs_bytes;
+    const int off = (int)(reinterpret_cast<uintptr_t>(dst) & 15);
+    const int head = off ? min(16 - off, total) : 0;             // bytes before the first whole chunk
+    const int n_chunks = (total - head) >> 4;
+    uint4* out16 = reinterpret_cast<uint4*>(dst + head);
+    for (int c = lane; c < n_chunks; c += 32) {
+        const uint32_t pg = (uint32_t)(head + (c << 4));             // byte of the run = window e, bit p
+        const uint32_t e = __umulhi(pg, inv_ob), p = pg - e * (uint32_t)obs_bytes;
+        uint32_t h = window_bits16(stage, S, SW, inv_s, e, p);
+        const int have = obs_bytes - (int)p;                         // the zero words behind a slot's last column end its bits
+        if (have < 16) h |= window_bits16(stage, S, SW, inv_s, e + 1u, 0u) << have;
+        h &= 0xFFFFu;
+        const uint2 lo = lut[h & 0xFFu], hi = lut[h >> 8];
+        __stcs(out16 + c, make_uint4(lo.x, lo.y, hi.x, hi.y));
+    }
+    const int tail0 = head + (n_chunks << 4);
+    const int pb = lane < 16 ? lane : tail0 + lane - 16;             // ragged head (lanes 0-15) and tail (lanes 16-31)
+    if (lane < 16 ? pb < head : pb < total) {
+        const uint32_t e = __umulhi((uint32_t)pb, inv_ob), p = (uint32_t)pb - e * (uint32_t)obs_bytes;
+        const uint32_t q = (p * inv_s) >> 20, r = p - q * (uint32_t)S;
+        dst[pb] = (uint8_t)((stage[e * SW + q] >> r) & 1u);
+    }
+}
+
+// One world turn, one warp per world. H64: the world is 64 high (a window column is one funnel shift of the plane column).
+template <bool H64>
 __global__ void __launch_bounds__(128) wab2_grid_turn_kernel(const __grid_constant__ Params2 P, const State2Ptrs st,
-                                                             const uint8_t* __restrict__ actions, const Out2Ptrs out,
-                                                             const int stream_words) {
+                                                             const uint8_t* __restrict__ actions, const Out2Ptrs out) {
     extern __shared__ uint32_t smem2[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const int E = P.n_entities, A = P.n_acting, W = P.width, H = P.height;
-    const GridGeom g = grid_geom(E, W, stream_words);
+    const int E = P.n_entities, A = P.n_acting, nO = P.n_ostriches, W = P.width, H = H64 ? 64 : P.height;
+    const int R = P.window_r, S = 2 * R + 1, obs_bytes = 3 * S * S, SW = grid_stage_words(S);
+    const GridGeom g = grid_geom(E, A, W, S);
     uint2* lut = reinterpret_cast<uint2*>(smem2 + wpb * g.total);
     build_lut(lut);
     const int64_t idx = (int64_t)blockIdx.x * wpb + warp, n = st.n;
     if (idx >= n) return;                                   // whole warp
-    uint32_t* obj = smem2 + warp * g.total + g.ent;
-    uint32_t* tab = obj + E;
+    uint32_t* tab = smem2 + warp * g.total + g.tab;
     uint32_t* food = tab + E;
+    uint32_t* newtab = smem2 + warp * g.total + g.newtab;
     uint32_t* cols = smem2 + warp * g.total + g.cols;
-    uint32_t* stream = smem2 + warp * g.total + g.stream;
-    const uint32_t* src = st.ent + idx * st.stride_world;
-    for (int k = lane; k < 3 * E; k += 32) obj[(k % 3) * E + k / 3] = src[k];   // world-major [entity][obj, tab, food]: coalesced read, planar in smem
-    for (int k = lane; k < 3 * W * 2; k += 32) cols[k] = 0u;
+    uint32_t* stage = smem2 + warp * g.total + g.stage;
+    uint32_t* gent = st.ent + idx * st.stride_world;        // this world: [obj | table row | food][E], planar
+    for (int k = lane; k < 2 * E; k += 32) tab[k] = gent[E + k];
+    for (int k = lane; k < 5 * W * 2; k += 32) cols[k] = 0u;
+    for (int k = lane; k < kGridGroup * SW + 2; k += 32) stage[k] = 0u;   // the words behind the last column stay zero
     const uint32_t env_id = (uint32_t)(P.env_id_base + (uint64_t)idx), episode = st.episode[idx];
-    uint32_t turn = st.turn[idx];
+    const uint32_t turn = st.turn[idx];
+    // this lane's column of the window: circle mask per radius kind (lookout, gatherer, wolf).
+    // |dy| <= m  <=>  dx^2 + dy^2 <= r^2 (World.py:295-297): bits R-m .. R+m of the 2R+1 window column; 0 beyond the radius
+    const int rad[3] = {P.lookout_r, P.gatherer_r, P.wolf_r};
+    uint32_t cmask[3];
+#pragma unroll
+    for (int rs = 0; rs < 3; ++rs) {
+        const int adx = lane - R < 0 ? R - lane : lane - R;
+        cmask[rs] = 0u;
+        if (lane < S && adx <= rad[rs]) { const int m = (int)P.halfwidth[rs][adx]; cmask[rs] = ((2u << (2 * m)) - 1u) << (R - m); }
+    }
     __syncwarp();
     for (int k = lane; k < E; k += 32) {
         const uint32_t t = tab[k];
-        if ((t >> 16) & 1u) col_set(cols, W, entity_type(P, k), t & 0xFFu, (t >> 8) & 0xFFu);
+        if ((t >> 16) & 1u) {
+            const uint32_t ty = entity_type(P, k), x = t & 0xFFu, y = (t >> 8) & 0xFFu, bit = 1u << (y & 31);
+            const uint32_t old = atomicOr(cols + col_word(W, ty, x, y), bit);
+            if ((old & bit) && ty != T_BUSH) atomicOr(cols + col_word(W, 3u + ty, x, y), bit);
+        }
     }
-    __syncwarp();
-    const int R = P.window_r, S = 2 * R + 1, obs_bytes = 3 * S * S;
     // bushes never move: their "action" only refreshes a table position left stale by reset_world (World.py:353-356),
     // i.e. it is a no-op except in the first turn of an episode
     const int last = turn == 0u ? E : A;
-    for (int a = 0; a < last; ++a) {
-        const bool acting = a < A;
-        const uint32_t at = entity_type(P, a);
-        const int64_t o = (int64_t)a * n + idx;
-        uint32_t atab = tab[a];
-        if (acting && out.planes) {                                  // get_observations(a), World.py:360-377
-            const int64_t first_byte = o * obs_bytes;
-            const int off = (int)(first_byte & 15);
-#pragma unroll 1
-            for (int k = lane; k < stream_words; k += 32) stream[k] = 0u;     // rolled: the unrolled form cost ~70 instructions
-            __syncwarp();
-            const int ax = (int)(atab & 0xFFu), ay = (int)((atab >> 8) & 0xFFu);
-            const int rsel = at == T_WOLF ? 2 : (((atab >> 17) & 1u) ? 1 : 0);
-            const int r = rsel == 2 ? P.wolf_r : (rsel == 1 ? P.gatherer_r : P.lookout_r);
-            // no division anywhere below: 0 <= ax < W, 0 <= ay < H and R < W, H, so one conditional add wraps
-            const int sy = ay - R + (ay < R ? H : 0);
-            const uint64_t smask = (1ull << S) - 1ull;
-#pragma unroll 1
-            for (int dxi = lane; dxi < S; dxi += 32) {               // one lane per column offset: the three type
-                const int dx = dxi - R, adx = dx < 0 ? -dx : dx;     // planes share x, rotation, circle mask and quirks
-                if (adx > r) continue;
-                int x = ax + dx;
-                x += x < 0 ? W : 0;
-                x -= x >= W ? W : 0;
-                const int m = (int)P.halfwidth[rsel][adx];           // |dy| <= m  <=>  dx^2 + dy^2 <= r^2
-                uint64_t mask = (((2ull << (2 * m)) - 1ull) << (R - m)) & smask;
-                if (dx == r && ax + r == W) mask = 0;                // World.py:264 strict test: this image is missed
-                if (dx == 0 && ay + r == H) mask &= ~(1ull << (R + r));   // World.py:285, same on the y axis
-#pragma unroll
-                for (int type_p = 0; type_p < 3; ++type_p) {
-                    const uint2 cw = *reinterpret_cast<const uint2*>(cols + ((type_p * W + x) << 1));
-                    const uint64_t bits = rot_window((uint64_t)cw.x | ((uint64_t)cw.y << 32), sy, H) & mask;
-                    if (bits) {
-                        const int pos = off + (type_p * S + dxi) * S;
-                        const uint64_t sh = bits << (pos & 31);
-                        atomicOr(stream + (pos >> 5), (uint32_t)sh);
-                        if (sh >> 32) atomicOr(stream + (pos >> 5) + 1, (uint32_t)(sh >> 32));
-                    }
-                }
-            }
-            __syncwarp();
-            stream_flush(stream, lut, out.planes + (first_byte - off), off, off + obs_bytes, lane);
-            __syncwarp();
+    // world-major outputs: entity e of this world
+    int32_t* o_internal = out.internal ? out.internal + idx * A * 5 : nullptr;
+    float* o_reward = out.reward + idx * A;
+    uint8_t* o_done = out.done + idx * A;
+
+    // ---- 1. pre-pass: one lane per acting entity
+    for (int e = lane; e < A; e += 32) {
+        const bool ostrich = e < nO;
+        const uint32_t ob = gent[e], t = tab[e];
+        int32_t x = unpack_x(ob), y = unpack_y(ob);
+        uint32_t role = (t >> 17) & 1u;
+        if (o_internal) {                                             // internal_obs, World.py:50-51, :80-81
+            int32_t* dst = o_internal + e * 5;
+            dst[0] = x; dst[1] = y; dst[2] = (int32_t)food[e]; dst[3] = (int32_t)role; dst[4] = (int32_t)((t >> 18) & 3u);
         }
-        if (acting && out.internal && lane == 0) {                   // internal_obs, World.py:50-51, :80-81
-            int32_t* dst = out.internal + o * 5;
-            const uint32_t ob = obj[a];
-            dst[0] = unpack_x(ob); dst[1] = unpack_y(ob); dst[2] = (int32_t)food[a];
-            dst[3] = (int32_t)((atab >> 17) & 1u); dst[4] = (int32_t)((atab >> 18) & 3u);
+        if (ostrich) {                                                // compute_reward / is_done: status cannot change before it acts
+            const uint32_t s2 = (t >> 18) & 3u;
+            o_reward[e] = s2 == 0u ? 1.f : 0.f;
+            o_done[e] = (uint8_t)(s2 != 0u);
         }
-        // ---- take_action(a): act, table update (World.py:325-334)
-        const uint32_t action = acting ? (uint32_t)actions[o] : 0u;
-        int32_t x = unpack_x(obj[a]), y = unpack_y(obj[a]);
-        uint32_t role = (atab >> 17) & 1u;
-        if (at != T_BUSH) {
-            if (action == 0u) y += 1; else if (action == 1u) x += 1; else if (action == 2u) y -= 1; else if (action == 3u) x -= 1;
-            else if (at == T_OSTRICH && action == 4u) role = 0u; else if (at == T_OSTRICH && action == 5u) role = 1u;
-        }
+        const uint32_t action = (uint32_t)actions[(int64_t)e * n + idx];   // act, World.py:25-43, :61-73
+        if (action == 0u) y += 1; else if (action == 1u) x += 1; else if (action == 2u) y -= 1; else if (action == 3u) x -= 1;
+        else if (ostrich && action == 4u) role = 0u; else if (ostrich && action == 5u) role = 1u;
+        const uint32_t nob = pack_xy(x, y);
+        if (nob != ob) gent[e] = nob;
         uint32_t tx, ty;
         if (turn == 0u) {          // tables may be stale after reset_world: the full wrap of the object coordinates
             tx = (uint32_t)pymod(x, W); ty = (uint32_t)pymod(y, H);
         } else {                   // afterwards the table follows the object one cell at a time
-            int nx = (int)(atab & 0xFFu) + (x - unpack_x(obj[a])), ny = (int)((atab >> 8) & 0xFFu) + (y - unpack_y(obj[a]));
+            int nx = (int)(t & 0xFFu) + (x - unpack_x(ob)), ny = (int)((t >> 8) & 0xFFu) + (y - unpack_y(ob));
             nx += nx < 0 ? W : 0; nx -= nx >= W ? W : 0;
             ny += ny < 0 ? H : 0; ny -= ny >= H ? H : 0;
             tx = (uint32_t)nx; ty = (uint32_t)ny;
         }
-        const uint32_t old_cell = atab & 0xFFFFu, new_cell = tx | (ty << 8);
-        const uint32_t vis = (atab >> 16) & 1u;
-        atab = tab_pack(tx, ty, vis, role, (atab >> 18) & 3u);
-        __syncwarp();
-        if (lane == 0) { obj[a] = pack_xy(x, y); tab[a] = atab; }
-        __syncwarp();
-        if (vis && old_cell != new_cell) {
-            if (lane == 0) col_set(cols, W, at, tx, ty);
-            recount_cell(P, tab, cols, at, old_cell, lane);
+        newtab[e] = tab_pack(tx, ty, 0u, role, 0u);
+    }
+    __syncwarp();
+
+    // ---- 2. the entities in order
+    const uint32_t inv_s = ((1u << 20) + (uint32_t)S - 1u) / (uint32_t)S;
+    const uint32_t inv_ob = 0xFFFFFFFFu / (uint32_t)obs_bytes + 1u;   // ceil(2^32 / obs_bytes)
+    uint8_t* o_planes = out.planes ? out.planes + idx * A * obs_bytes : nullptr;
+    const bool observe_any = o_planes != nullptr;
+    const int dx = lane - R;
+    bool bush_dirty = turn == 0u;
+    uint32_t bush_ob = 0u;
+    int g0 = 0;                                                       // first entity of the staged group
+    for (int a = 0; a < last; ++a) {
+        const bool acting = a < A;
+        const uint32_t at = a < nO ? T_OSTRICH : (acting ? T_WOLF : T_BUSH);
+        const uint32_t ot = tab[a];
+        if (observe_any && acting && lane < S) {                     // get_observations(a), World.py:360-377
+            uint32_t* sg = stage + (a - g0) * SW + lane;             // one lane per column offset: the three type planes share
+            const int ax = (int)(ot & 0xFFu), ay = (int)((ot >> 8) & 0xFFu);   // x, rotation, circle mask and quirks
+            const bool gatherer = (ot >> 17) & 1u;
+            const int r = at == T_WOLF ? rad[2] : (gatherer ? rad[1] : rad[0]);
+            uint32_t mask = at == T_WOLF ? cmask[2] : (gatherer ? cmask[1] : cmask[0]);
+            // no division: 0 <= ax < W, 0 <= ay < H and R < W, H, so one conditional add wraps
+            const int sy = ay - R + (ay < R ? H : 0);
+            int x = ax + dx;
+            x += x < 0 ? W : 0;
+            x -= x >= W ? W : 0;
+            if (dx == r && ax + r == W) mask = 0u;                    // World.py:264 strict test: this image is missed
+            if (dx == 0 && ay + r == H) mask &= ~(1u << (R + r));     // World.py:285, same on the y axis
+            const uint32_t* cx = cols + (x << 1);
+#pragma unroll
+            for (int type_p = 0; type_p < 3; ++type_p) {
+                const uint2 cw = *reinterpret_cast<const uint2*>(cx + type_p * 2 * W);
+                uint32_t bits;
+                if (H64) {                                            // bits (sy + k) mod 64, k < 32: one funnel shift
+                    const uint32_t lo = sy & 32 ? cw.y : cw.x, hi = sy & 32 ? cw.x : cw.y;
+                    bits = __funnelshift_r(lo, hi, (uint32_t)sy & 31u);
+                } else {
+                    bits = (uint32_t)rot_window((uint64_t)cw.x | ((uint64_t)cw.y << 32), sy, H);
+                }
+                sg[type_p * S] = bits & mask;
+            }
+        }
+        // ---- take_action(a): the pending row becomes the table row (World.py:331-332); Visible and status are whatever
+        // the others made of them meanwhile
+        uint32_t merged;
+        if (acting) {
+            const uint32_t nt = newtab[a];
+            const uint32_t own = at == T_OSTRICH ? 0x2FFFFu : 0xFFFFu;   // X, Y (+ an ostrich's role)
+            merged = (ot & ~own) | (nt & own);
+        } else {                                                      // a bush in the first turn: the wrap of its coordinates
+            if (((a - A) & 31) == 0) bush_ob = a + lane < E ? gent[a + lane] : 0u;      // 32 bushes' coordinates per load
+            const uint32_t ob = __shfl_sync(FULL, bush_ob, (a - A) & 31);
+            merged = (ot & ~0xFFFFu) | (uint32_t)pymod(unpack_x(ob), W) | ((uint32_t)pymod(unpack_y(ob), H) << 8);
+        }
+        const uint32_t tx = merged & 0xFFu, ty = (merged >> 8) & 0xFFu;
+        __syncwarp();                                                 // the window columns were read from the planes as they were
+        if (merged != ot) {
+            if (lane == 0) tab[a] = merged;
+            if (((ot >> 16) & 1u) && ((ot ^ merged) & 0xFFFFu)) {
+                plane_arrive(cols, W, at, tx, ty, lane);              // (its barrier also publishes tab[a])
+                plane_leave(P, tab, cols, at, ot & 0xFFFFu, lane);
+            } else {
+                __syncwarp();
+            }
         }
         // ---- default_game_update (World.py:93-132)
         if (at != T_BUSH) {
             const uint32_t want = at == T_WOLF ? T_OSTRICH : T_BUSH;
-            if (col_test(cols, W, want, tx, ty)) {
+            if ((cols[col_word(W, want, tx, ty)] >> (ty & 31)) & 1u) {
                 int lo, hi;
                 type_range(P, want, lo, hi);
-                const uint32_t cellv = new_cell | (1u << 16);
+                const uint32_t cellv = (merged & 0xFFFFu) | (1u << 16);
                 int k = 0;
                 for (int base = lo; base < hi; base += 32) {
                     const int q = base + lane;
@@ -205,7 +318,7 @@ __global__ void __launch_bounds__(128) wab2_grid_turn_kernel(const __grid_consta
                             tab[j] = tab[j] & ~(1u << 16);                                         // :115 hides LABEL j
                         }
                         __syncwarp();
-                        if ((jt >> 16) & 1u) recount_cell(P, tab, cols, entity_type(P, j), jt & 0xFFFFu, lane);
+                        if ((jt >> 16) & 1u) plane_leave(P, tab, cols, entity_type(P, j), jt & 0xFFFFu, lane);
                     } else {
                         if (lane == 0) {                                                           // Bush.take_food
                             int32_t bf = (int32_t)food[pick], got;
@@ -214,25 +327,32 @@ __global__ void __launch_bounds__(128) wab2_grid_turn_kernel(const __grid_consta
                             food[pick] = (uint32_t)bf;
                             food[a] += (uint32_t)got;                                              // :127
                         }
+                        bush_dirty = true;
                         __syncwarp();
                     }
                 }
             }
         }
-        if (acting && lane == 0) {                                   // compute_reward / is_done
-            const uint32_t now = tab[a];
-            float reward; uint32_t done;
-            if (at == T_OSTRICH) { const uint32_t s2 = (now >> 18) & 3u; reward = s2 == 0u ? 1.f : 0.f; done = s2 != 0u; }
-            else { reward = (int32_t)food[a] > 10 ? 1.f : 0.f; done = (((now >> 18) & 3u) == 1u); }
-            out.reward[o] = reward;
-            out.done[o] = (uint8_t)done;
+        // ---- 3. a full group (or the last observer): windows out
+        if (observe_any && acting && (a - g0 == kGridGroup - 1 || a == A - 1)) {
+            __syncwarp();
+            grid_flush_group(stage, lut, o_planes + (int64_t)g0 * obs_bytes, a - g0 + 1, S, SW, inv_s, inv_ob, obs_bytes, lane);
+            __syncwarp();
+            g0 = a + 1;
         }
-        __syncwarp();
     }
-    turn += 1;
-    uint32_t* dst = st.ent + idx * st.stride_world;
-    for (int k = lane; k < 3 * E; k += 32) dst[k] = obj[(k % 3) * E + k / 3];
-    if (lane == 0) st.turn[idx] = turn;
+    __syncwarp();
+    // a wolf's reward is its own food after its own action (World.py:84-85); nobody else touches it
+    for (int e = nO + lane; e < A; e += 32) {
+        o_reward[e] = (int32_t)food[e] > 10 ? 1.f : 0.f;
+        o_done[e] = (uint8_t)(((tab[e] >> 18) & 3u) == 1u);
+    }
+    // table rows and food back; the bushes' only if a bush was eaten from (or moved, in the first turn)
+    for (int k = lane; k < 2 * E; k += 32) {
+        const int e = k < E ? k : k - E;
+        if (e < A || bush_dirty) gent[E + k] = tab[k];
+    }
+    if (lane == 0) st.turn[idx] = turn + 1u;
 }
 
 }  // namespace

@@ -10,36 +10,37 @@
 namespace {
 
 struct State2Ptrs {
-    uint32_t* ent;      // entity words (wab2_core.cuh): word k of world i at ent[k * stride_word + i * stride_world]
+    uint32_t* ent;      // entity words (wab2_core.cuh): word f (0 object coords, 1 table row, 2 food) of entity k of world i
+                        // at ent[k * stride_ent + f * stride_word + i * stride_world]
     uint32_t* episode;  // [N]
     uint32_t* turn;     // [N]
     int64_t n;
-    int64_t stride_word, stride_world;   // [3E][N] (thread per world: n, 1) or [N][3E] (warp per world: 1, 3E)
+    int64_t stride_ent, stride_word, stride_world;   // [E][3][N] (thread per world: 3n, n, 1) or [N][3][E] (warp per world: 1, E, 3E)
 };
-struct Out2Ptrs {
-    uint8_t* planes;    // [A][N][3][S][S] u8 or null (entity-major: the 32 worlds of a warp are contiguous)
-    int32_t* internal;  // [A][N][5] or null
-    float* reward;      // [A][N]
-    uint8_t* done;      // [A][N]
+struct Out2Ptrs {       // thread per world: entity-major (the 32 worlds of a warp are contiguous); warp per world: world-major
+    uint8_t* planes;    // [A][N][3][S][S] | [N][A][3][S][S] u8, or null
+    int32_t* internal;  // [A][N][5] | [N][A][5], or null
+    float* reward;      // [A][N] | [N][A]
+    uint8_t* done;      // [A][N] | [N][A]
 };
 
 // thread-per-world kernels: table rows and food are staged in shared memory, object coords are used in place
 __device__ __forceinline__ void bind_world(const State2Ptrs& st, int64_t idx, World2& W) {
-    W.obj = st.ent + idx * st.stride_world; W.ostride = 3 * st.stride_word;
+    W.obj = st.ent + idx * st.stride_world; W.ostride = st.stride_ent;
 }
 __device__ __forceinline__ void load_world(const Params2& P, const State2Ptrs& st, int64_t idx, World2& W) {
     bind_world(st, idx, W);
     for (int k = 0; k < P.n_entities; ++k) {
-        W.base[(2 * k) * W.stride] = st.ent[(3 * k + 1) * st.stride_word + idx * st.stride_world];
-        W.base[(2 * k + 1) * W.stride] = st.ent[(3 * k + 2) * st.stride_word + idx * st.stride_world];
+        W.base[(2 * k) * W.stride] = st.ent[k * st.stride_ent + st.stride_word + idx * st.stride_world];
+        W.base[(2 * k + 1) * W.stride] = st.ent[k * st.stride_ent + 2 * st.stride_word + idx * st.stride_world];
     }
     W.episode = st.episode[idx]; W.turn = st.turn[idx];
     W.env_id = (uint32_t)(P.env_id_base + (uint64_t)idx);
 }
 __device__ __forceinline__ void store_world(const Params2& P, const State2Ptrs& st, int64_t idx, const World2& W) {
     for (int k = 0; k < P.n_entities; ++k) {
-        st.ent[(3 * k + 1) * st.stride_word + idx * st.stride_world] = W.base[(2 * k) * W.stride];
-        st.ent[(3 * k + 2) * st.stride_word + idx * st.stride_world] = W.base[(2 * k + 1) * W.stride];
+        st.ent[k * st.stride_ent + st.stride_word + idx * st.stride_world] = W.base[(2 * k) * W.stride];
+        st.ent[k * st.stride_ent + 2 * st.stride_word + idx * st.stride_world] = W.base[(2 * k + 1) * W.stride];
     }
     st.episode[idx] = W.episode; st.turn[idx] = W.turn;
 }
@@ -194,8 +195,10 @@ int wab2_create(const Wab2Config* cfg, int64_t n_envs, uint64_t seed, uint64_t e
     h->bs = bs; h->smem_turn = need(bs); h->smem_init = sizeof(uint32_t) * (size_t)2 * E * bs;
     cudaError_t e = cudaSuccess;
     if (h->grid) {
-        h->smem_turn = sizeof(uint32_t) * ((size_t)4 * grid_geom(E, cfg->width, h->stream_words).total + 512);
-        e = cudaFuncSetAttribute(wab2_grid_turn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_turn);
+        h->smem_turn = sizeof(uint32_t) * ((size_t)4 * grid_geom(E, P.n_acting, cfg->width, S).total + 512);
+        e = cfg->height == 64
+            ? cudaFuncSetAttribute(wab2_grid_turn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_turn)
+            : cudaFuncSetAttribute(wab2_grid_turn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_turn);
     } else
         e = cudaFuncSetAttribute(wab2_turn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_turn);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(wab2_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_init);
@@ -210,7 +213,8 @@ int wab2_create(const Wab2Config* cfg, int64_t n_envs, uint64_t seed, uint64_t e
     uint8_t* base = (uint8_t*)h->slab;
     h->st.ent = (uint32_t*)(base + o_ent); h->st.episode = (uint32_t*)(base + o_ep); h->st.turn = (uint32_t*)(base + o_turn);
     h->st.n = n_envs;
-    h->st.stride_word = h->grid ? 1 : n_envs;
+    h->st.stride_ent = h->grid ? 1 : 3 * n_envs;
+    h->st.stride_word = h->grid ? E : n_envs;
     h->st.stride_world = h->grid ? 3 * E : 1;
     wab2_init_kernel<<<(unsigned)((n_envs + bs - 1) / bs), bs, h->smem_init, 0>>>(h->P, h->st, 0);
     e = cudaGetLastError();
@@ -228,6 +232,7 @@ void wab2_destroy(Wab2World* h) {
 }
 
 int wab2_kernel_kind(const Wab2World* h) { return h && h->grid ? 1 : 0; }
+int wab2_output_layout(const Wab2World* h) { return h && h->grid ? 1 : 0; }
 
 int wab2_reset(Wab2World* h, void* stream) {
     if (!h) return fail(WAB_E_NULL, "null argument");
@@ -243,9 +248,10 @@ int wab2_turn(Wab2World* h, const uint8_t* d_actions, uint8_t* d_planes, int32_t
     if (d_planes) if (int rc = check_ptr_align(d_planes, "d_planes")) return rc;
     DeviceGuard guard(h->device);
     Out2Ptrs out{d_planes, d_internal, d_reward, d_done};
-    if (h->grid)
-        wab2_grid_turn_kernel<<<(unsigned)((h->n + 3) / 4), 128, h->smem_turn, (cudaStream_t)stream>>>(
-            h->P, h->st, d_actions, out, h->stream_words);
+    if (h->grid && h->P.height == 64)
+        wab2_grid_turn_kernel<true><<<(unsigned)((h->n + 3) / 4), 128, h->smem_turn, (cudaStream_t)stream>>>(h->P, h->st, d_actions, out);
+    else if (h->grid)
+        wab2_grid_turn_kernel<false><<<(unsigned)((h->n + 3) / 4), 128, h->smem_turn, (cudaStream_t)stream>>>(h->P, h->st, d_actions, out);
     else
         wab2_turn_kernel<<<(unsigned)((h->n + h->bs - 1) / h->bs), h->bs, h->smem_turn, (cudaStream_t)stream>>>(
             h->P, h->st, d_actions, out, h->stream_words);
@@ -267,9 +273,8 @@ int wab2_export_state(Wab2World* h, int32_t* out9, int32_t* turn, void* stream) 
         for (size_t i = 0; i < n; ++i) {
             if (turn) turn[i] = (int32_t)tr[i];
             for (int k = 0; k < E; ++k) {
-                const size_t sw = (size_t)h->st.stride_word, si = (size_t)h->st.stride_world;
-                const uint32_t obj = ent[(size_t)(3 * k) * sw + i * si], tab = ent[(size_t)(3 * k + 1) * sw + i * si],
-                               food = ent[(size_t)(3 * k + 2) * sw + i * si];
+                const size_t se = (size_t)h->st.stride_ent, sw = (size_t)h->st.stride_word, si = (size_t)h->st.stride_world;
+                const uint32_t obj = ent[k * se + i * si], tab = ent[k * se + sw + i * si], food = ent[k * se + 2 * sw + i * si];
                 int32_t* o = out9 + (i * E + k) * 9;
                 o[0] = (int32_t)entity_type(h->P, k); o[1] = unpack_x(obj); o[2] = unpack_y(obj);
                 o[3] = (int32_t)(tab & 0xFFu); o[4] = (int32_t)((tab >> 8) & 0xFFu); o[5] = (int32_t)((tab >> 16) & 1u);
@@ -287,7 +292,7 @@ int wab2_import_state(Wab2World* h, const int32_t* in9, const int32_t* turn, voi
     WAB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     const size_t n = (size_t)h->n;
     const int E = h->P.n_entities;
-    const size_t sw = (size_t)h->st.stride_word, si = (size_t)h->st.stride_world;
+    const size_t se = (size_t)h->st.stride_ent, sw = (size_t)h->st.stride_word, si = (size_t)h->st.stride_world;
     uint32_t* ent = new uint32_t[n * 3 * E];
     int bad = 0;
     for (size_t i = 0; i < n && !bad; ++i)
@@ -295,9 +300,9 @@ int wab2_import_state(Wab2World* h, const int32_t* in9, const int32_t* turn, voi
             const int32_t* o = in9 + (i * E + k) * 9;
             if (o[0] != (int32_t)entity_type(h->P, k) || o[3] < 0 || o[3] > 255 || o[4] < 0 || o[4] > 255 || o[6] < 0 ||
                 o[1] < -32768 || o[1] > 32767 || o[2] < -32768 || o[2] > 32767) { bad = 1; break; }
-            ent[(size_t)(3 * k) * sw + i * si] = pack_xy(o[1], o[2]);
-            ent[(size_t)(3 * k + 1) * sw + i * si] = tab_pack((uint32_t)o[3], (uint32_t)o[4], o[5] ? 1u : 0u, (uint32_t)o[7] & 1u, (uint32_t)o[8] & 3u);
-            ent[(size_t)(3 * k + 2) * sw + i * si] = (uint32_t)o[6];
+            ent[k * se + i * si] = pack_xy(o[1], o[2]);
+            ent[k * se + sw + i * si] = tab_pack((uint32_t)o[3], (uint32_t)o[4], o[5] ? 1u : 0u, (uint32_t)o[7] & 1u, (uint32_t)o[8] & 3u);
+            ent[k * se + 2 * sw + i * si] = (uint32_t)o[6];
         }
     cudaError_t e = cudaSuccess;
     if (!bad) e = cudaMemcpy(h->st.ent, ent, 4 * n * 3 * E, cudaMemcpyHostToDevice);

@@ -70,11 +70,34 @@ class VecWorld2:
                                         self.device.index, ctypes.byref(h)))
         self._h = h
         n, a, s = self.num_envs, self.n_acting, 2 * self.R + 1
-        # entity-major: [A, N, ...] (the worlds of a warp are contiguous for every acting entity)
-        self.planes = torch.empty((a, n, 3, s, s), dtype=torch.uint8, device=self.device) if observations else None
-        self.internal = torch.empty((a, n, 5), dtype=torch.int32, device=self.device) if observations else None
-        self.reward = torch.empty((a, n), dtype=torch.float32, device=self.device)
-        self.done = torch.empty((a, n), dtype=torch.uint8, device=self.device)
+        # storage in the handle's layout: entity-major [A, N, ...] (thread per world: the worlds of a warp are contiguous for
+        # every acting entity) or world-major [N, A, ...] (warp per world: a world's windows are one run). What turn()
+        # returns is always indexed [entity, world, ...] — a transposed view of the storage in the second case.
+        self.world_major = bool(self.lib.wab2_output_layout(self._h))
+        lead = (n, a) if self.world_major else (a, n)
+        self.planes_store = torch.empty(lead + (3, s, s), dtype=torch.uint8, device=self.device) if observations else None
+        self.internal_store = torch.empty(lead + (5,), dtype=torch.int32, device=self.device) if observations else None
+        self.reward_store = torch.empty(lead, dtype=torch.float32, device=self.device)
+        self.done_store = torch.empty(lead, dtype=torch.uint8, device=self.device)
+
+    def _view(self, t):
+        return None if t is None else (t.transpose(0, 1) if self.world_major else t)
+
+    @property
+    def planes(self):
+        return self._view(self.planes_store)
+
+    @property
+    def internal(self):
+        return self._view(self.internal_store)
+
+    @property
+    def reward(self):
+        return self._view(self.reward_store)
+
+    @property
+    def done(self):
+        return self._view(self.done_store)
 
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -85,14 +108,15 @@ class VecWorld2:
 
     def turn(self, actions: torch.Tensor):
         """One world turn. ``actions`` u8[A, N], A = n_ostriches + n_wolves (ostrich 0-5, wolf 0-4; bushes always act
-        with 0). Returns (planes u8[A, N, 3, 2R+1, 2R+1], internal i32[A, N, 5], reward f32[A, N], done bool[A, N]) —
-        entity-major; the observation of entity i is what ``get_obs(i)`` returns right before it acts (World.py:360-377)."""
+        with 0). Returns (planes u8[A, N, 3, 2R+1, 2R+1], internal i32[A, N, 5], reward f32[A, N], done bool[A, N]),
+        indexed [entity, world] (views of ``*_store``, which is world-major for the warp-per-world kernel); the
+        observation of entity i is what ``get_obs(i)`` returns right before it acts (World.py:360-377)."""
         if tuple(actions.shape) != (self.n_acting, self.num_envs):
             raise ValueError("actions must have shape (n_ostriches + n_wolves, num_envs)")
         a = actions.to(device=self.device, dtype=torch.uint8).contiguous()
-        _lib.check(self.lib.wab2_turn(self._h, _ptr(a), _ptr(self.planes), _ptr(self.internal), _ptr(self.reward),
-                                      _ptr(self.done), self._stream()))
-        return self.planes, self.internal, self.reward, self.done.view(torch.bool)
+        _lib.check(self.lib.wab2_turn(self._h, _ptr(a), _ptr(self.planes_store), _ptr(self.internal_store),
+                                      _ptr(self.reward_store), _ptr(self.done_store), self._stream()))
+        return self.planes, self.internal, self.reward, self._view(self.done_store.view(torch.bool))
 
     def kernel_name(self) -> str:
         return "wab2_grid_turn_kernel (warp per world)" if self.lib.wab2_kernel_kind(self._h) else "wab2_turn_kernel (thread per world)"
