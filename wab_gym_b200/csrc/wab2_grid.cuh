@@ -99,43 +99,49 @@ __device__ __forceinline__ void plane_leave(const Params2& P, const uint32_t* ta
     __syncwarp();
 }
 
-// Windows of the `g` observations staged in `stage` (slot e = entity a0 + e) -> `dst`, the first byte of entity a0's
-// window. The outputs of this kernel are WORLD-major, so the g windows are one run of g * obs_bytes bytes: bit p =
-// (type*S + dxi)*S + dyi of window e is byte e * obs_bytes + p of the run, which starts at ANY byte address — whole
-// 16-byte chunks go out as one streaming store per lane, the < 16 bytes at either end of the run byte by byte.
-__device__ __forceinline__ uint32_t window_bits16(const uint32_t* stage, int S, int SW, uint32_t inv_s, uint32_t e, uint32_t p) {
-    const uint32_t q = (p * inv_s) >> 20, r = p - q * (uint32_t)S;       // column word, bit in it; 16 bits from there on
-    const uint32_t* col = stage + e * SW + q;
-    uint32_t h = (col[0] >> r) | (col[1] << (S - r));
-    if (S < 15)                                                          // narrow windows: more than two columns in 16 bits
-        for (int filled = 2 * S - (int)r, k = 2; filled < 16; filled += S, ++k) h |= col[k] << filled;
+// Shared memory by 32-bit shared-window address: the ordered loop and the flush touch it on almost every instruction, and
+// with generic pointers the compiler rebuilds the window base (S2R SR_CgaCtaId, LEA) in front of most accesses.
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+
+// Windows of the `g` observations staged at shared address `s_stage` (slot e = entity a0 + e) -> `dst`, the first byte of
+// entity a0's window. The outputs of this kernel are WORLD-major, so the g windows are one run of g * obs_bytes bytes:
+// bit p = (type*S + dxi)*S + dyi of window e is byte e * obs_bytes + p of the run, which starts at ANY byte address —
+// whole 16-byte chunks go out as one streaming store per lane, the < 16 bytes at either end of the run byte by byte.
+// inv_s = ceil(2^20 / S): (p * inv_s) >> 20 == p / S for p < 3 S^2 (p * S < 2^20); inv_ob = ceil(2^32 / obs_bytes):
+// __umulhi(b, inv_ob) == b / obs_bytes for b < kGridGroup * obs_bytes (b * obs_bytes < 2^32).
+__device__ __forceinline__ uint32_t window_bits16(uint32_t s_col, int S, uint32_t r) {   // 16 bits from bit r of column word s_col on
+    uint32_t h = (lds32(s_col) >> r) | (lds32(s_col + 4u) << (S - r));
+    if (S < 15)                                                      // narrow windows: more than two columns in 16 bits
+        for (int filled = 2 * S - (int)r, k = 2; filled < 16; filled += S, ++k) h |= lds32(s_col + 4u * k) << filled;
     return h;
 }
-__device__ __forceinline__ void grid_flush_group(const uint32_t* stage, const uint2* lut, uint8_t* dst, int g, int S, int SW,
+__device__ __forceinline__ void grid_flush_group(uint32_t s_stage, uint32_t s_lut, uint8_t* dst, int g, int S, int SW,
                                                  uint32_t inv_s, uint32_t inv_ob, int obs_bytes, int lane) {
-    // inv_s = ceil(2^20 / S): (p * inv_s) >> 20 == p / S for p < 3 S^2 (p * S < 2^20); inv_ob = ceil(2^32 / obs_bytes):
-    // __umulhi(b, inv_ob) == b / obs_bytes for b < kGridGroup * obs_bytes (b * obs_bytes < 2^32)
     const int total = g * obs_bytes;
     const int off = (int)(reinterpret_cast<uintptr_t>(dst) & 15);
     const int head = off ? min(16 - off, total) : 0;             // bytes before the first whole chunk
     const int n_chunks = (total - head) >> 4;
-    uint4* out16 = reinterpret_cast<uint4*>(dst + head);
-    for (int c = lane; c < n_chunks; c += 32) {
-        const uint32_t pg = (uint32_t)(head + (c << 4));             // byte of the run = window e, bit p
+    uint4* out16 = reinterpret_cast<uint4*>(dst + head) + lane;
+    uint32_t pg = (uint32_t)(head + (lane << 4));                // byte of the run = window e, bit p
+#pragma unroll 1
+    for (int c = lane; c < n_chunks; c += 32, pg += 512u, out16 += 32) {
         const uint32_t e = __umulhi(pg, inv_ob), p = pg - e * (uint32_t)obs_bytes;
-        uint32_t h = window_bits16(stage, S, SW, inv_s, e, p);
-        const int have = obs_bytes - (int)p;                         // the zero words behind a slot's last column end its bits
-        if (have < 16) h |= window_bits16(stage, S, SW, inv_s, e + 1u, 0u) << have;
-        h &= 0xFFFFu;
-        const uint2 lo = lut[h & 0xFFu], hi = lut[h >> 8];
-        __stcs(out16 + c, make_uint4(lo.x, lo.y, hi.x, hi.y));
+        const uint32_t q = (p * inv_s) >> 20, r = p - q * (uint32_t)S;
+        const uint32_t s_slot = s_stage + e * (uint32_t)(SW * 4);
+        uint32_t h = window_bits16(s_slot + q * 4u, S, r);
+        const int have = obs_bytes - (int)p;                     // the zero words behind a slot's last column end its bits
+        if (have < 16) h |= window_bits16(s_slot + (uint32_t)(SW * 4), S, 0u) << have;
+        const uint2 lo = lds64(s_lut + ((h & 0xFFu) << 3)), hi = lds64(s_lut + ((h >> 5) & 0x7F8u));
+        __stcs(out16, make_uint4(lo.x, lo.y, hi.x, hi.y));
     }
     const int tail0 = head + (n_chunks << 4);
     const int pb = lane < 16 ? lane : tail0 + lane - 16;             // ragged head (lanes 0-15) and tail (lanes 16-31)
     if (lane < 16 ? pb < head : pb < total) {
         const uint32_t e = __umulhi((uint32_t)pb, inv_ob), p = (uint32_t)pb - e * (uint32_t)obs_bytes;
         const uint32_t q = (p * inv_s) >> 20, r = p - q * (uint32_t)S;
-        dst[pb] = (uint8_t)((stage[e * SW + q] >> r) & 1u);
+        dst[pb] = (uint8_t)((lds32(s_stage + (e * (uint32_t)SW + q) * 4u) >> r) & 1u);
     }
 }
 
@@ -157,6 +163,9 @@ __global__ void __launch_bounds__(128) wab2_grid_turn_kernel(const __grid_consta
     uint32_t* newtab = smem2 + warp * g.total + g.newtab;
     uint32_t* cols = smem2 + warp * g.total + g.cols;
     uint32_t* stage = smem2 + warp * g.total + g.stage;
+    const uint32_t s_tab = (uint32_t)__cvta_generic_to_shared(tab), s_new = (uint32_t)__cvta_generic_to_shared(newtab),
+                   s_cols = (uint32_t)__cvta_generic_to_shared(cols), s_stage = (uint32_t)__cvta_generic_to_shared(stage),
+                   s_lut = (uint32_t)__cvta_generic_to_shared(lut);
     uint32_t* gent = st.ent + idx * st.stride_world;        // this world: [obj | table row | food][E], planar
     for (int k = lane; k < 2 * E; k += 32) tab[k] = gent[E + k];
     for (int k = lane; k < 5 * W * 2; k += 32) cols[k] = 0u;
@@ -182,9 +191,6 @@ __global__ void __launch_bounds__(128) wab2_grid_turn_kernel(const __grid_consta
             if ((old & bit) && ty != T_BUSH) atomicOr(cols + col_word(W, 3u + ty, x, y), bit);
         }
     }
-    // bushes never move: their "action" only refreshes a table position left stale by reset_world (World.py:353-356),
-    // i.e. it is a no-op except in the first turn of an episode
-    const int last = turn == 0u ? E : A;
     // world-major outputs: entity e of this world
     int32_t* o_internal = out.internal ? out.internal + idx * A * 5 : nullptr;
     float* o_reward = out.reward + idx * A;
@@ -223,73 +229,79 @@ __global__ void __launch_bounds__(128) wab2_grid_turn_kernel(const __grid_consta
     }
     __syncwarp();
 
-    // ---- 2. the entities in order
+    // ---- 2. the acting entities in order: ostriches, then wolves (the type is a compile-time constant of the loop body)
     const uint32_t inv_s = ((1u << 20) + (uint32_t)S - 1u) / (uint32_t)S;
     const uint32_t inv_ob = 0xFFFFFFFFu / (uint32_t)obs_bytes + 1u;   // ceil(2^32 / obs_bytes)
     uint8_t* o_planes = out.planes ? out.planes + idx * A * obs_bytes : nullptr;
-    const bool observe_any = o_planes != nullptr;
+    const bool observe = o_planes != nullptr;
     const int dx = lane - R;
+    const uint32_t plane_bytes = (uint32_t)W * 8u;                    // one occupancy plane
     bool bush_dirty = turn == 0u;
-    uint32_t bush_ob = 0u;
     int g0 = 0;                                                       // first entity of the staged group
-    for (int a = 0; a < last; ++a) {
-        const bool acting = a < A;
-        const uint32_t at = a < nO ? T_OSTRICH : (acting ? T_WOLF : T_BUSH);
-        const uint32_t ot = tab[a];
-        if (observe_any && acting && lane < S) {                     // get_observations(a), World.py:360-377
-            uint32_t* sg = stage + (a - g0) * SW + lane;             // one lane per column offset: the three type planes share
-            const int ax = (int)(ot & 0xFFu), ay = (int)((ot >> 8) & 0xFFu);   // x, rotation, circle mask and quirks
-            const bool gatherer = (ot >> 17) & 1u;
-            const int r = at == T_WOLF ? rad[2] : (gatherer ? rad[1] : rad[0]);
-            uint32_t mask = at == T_WOLF ? cmask[2] : (gatherer ? cmask[1] : cmask[0]);
-            // no division: 0 <= ax < W, 0 <= ay < H and R < W, H, so one conditional add wraps
-            const int sy = ay - R + (ay < R ? H : 0);
-            int x = ax + dx;
-            x += x < 0 ? W : 0;
-            x -= x >= W ? W : 0;
-            if (dx == r && ax + r == W) mask = 0u;                    // World.py:264 strict test: this image is missed
-            if (dx == 0 && ay + r == H) mask &= ~(1u << (R + r));     // World.py:285, same on the y axis
-            const uint32_t* cx = cols + (x << 1);
+    auto entities = [&](auto type_tag, const int a_begin, const int a_end) {
+        constexpr uint32_t AT = decltype(type_tag)::value;
+#pragma unroll 1
+        for (int a = a_begin; a < a_end; ++a) {
+            const uint32_t ot = lds32(s_tab + 4u * a);
+            const int ox = (int)(ot & 0xFFu), oy = (int)((ot >> 8) & 0xFFu);
+            if (observe && lane < S) {                               // get_observations(a), World.py:360-377: one lane per column
+                const bool gatherer = AT == T_OSTRICH && ((ot >> 17) & 1u);   // offset — the three type planes share x, rotation,
+                const int r = AT == T_WOLF ? rad[2] : (gatherer ? rad[1] : rad[0]);          // circle mask and quirks
+                uint32_t mask = AT == T_WOLF ? cmask[2] : (gatherer ? cmask[1] : cmask[0]);
+                // no division: 0 <= ox < W, 0 <= oy < H and R < W, H, so one conditional add wraps
+                const int sy = H64 ? ((oy - R) & 63) : (oy - R + (oy < R ? H : 0));
+                int x = ox + dx;
+                x += x < 0 ? W : 0;
+                x -= x >= W ? W : 0;
+                if (dx == r && ox + r == W) mask = 0u;                // World.py:264 strict test: this image is missed
+                if (dx == 0 && oy + r == H) mask &= ~(1u << (R + r)); // World.py:285, same on the y axis
+                const uint32_t s_col = s_cols + ((uint32_t)x << 3);
+                const uint32_t s_out = s_stage + (uint32_t)((a - g0) * SW + lane) * 4u;
 #pragma unroll
-            for (int type_p = 0; type_p < 3; ++type_p) {
-                const uint2 cw = *reinterpret_cast<const uint2*>(cx + type_p * 2 * W);
-                uint32_t bits;
-                if (H64) {                                            // bits (sy + k) mod 64, k < 32: one funnel shift
-                    const uint32_t lo = sy & 32 ? cw.y : cw.x, hi = sy & 32 ? cw.x : cw.y;
-                    bits = __funnelshift_r(lo, hi, (uint32_t)sy & 31u);
-                } else {
-                    bits = (uint32_t)rot_window((uint64_t)cw.x | ((uint64_t)cw.y << 32), sy, H);
+                for (int type_p = 0; type_p < 3; ++type_p) {
+                    const uint2 cw = lds64(s_col + type_p * plane_bytes);
+                    uint32_t bits;
+                    if (H64) {                                        // bits (sy + k) mod 64, k < 32: one funnel shift
+                        const uint32_t lo = sy & 32 ? cw.y : cw.x, hi = sy & 32 ? cw.x : cw.y;
+                        bits = __funnelshift_r(lo, hi, (uint32_t)sy & 31u);
+                    } else {
+                        bits = (uint32_t)rot_window((uint64_t)cw.x | ((uint64_t)cw.y << 32), sy, H);
+                    }
+                    sts32(s_out + type_p * (uint32_t)(S * 4), bits & mask);
                 }
-                sg[type_p * S] = bits & mask;
             }
-        }
-        // ---- take_action(a): the pending row becomes the table row (World.py:331-332); Visible and status are whatever
-        // the others made of them meanwhile
-        uint32_t merged;
-        if (acting) {
-            const uint32_t nt = newtab[a];
-            const uint32_t own = at == T_OSTRICH ? 0x2FFFFu : 0xFFFFu;   // X, Y (+ an ostrich's role)
-            merged = (ot & ~own) | (nt & own);
-        } else {                                                      // a bush in the first turn: the wrap of its coordinates
-            if (((a - A) & 31) == 0) bush_ob = a + lane < E ? gent[a + lane] : 0u;      // 32 bushes' coordinates per load
-            const uint32_t ob = __shfl_sync(FULL, bush_ob, (a - A) & 31);
-            merged = (ot & ~0xFFFFu) | (uint32_t)pymod(unpack_x(ob), W) | ((uint32_t)pymod(unpack_y(ob), H) << 8);
-        }
-        const uint32_t tx = merged & 0xFFu, ty = (merged >> 8) & 0xFFu;
-        __syncwarp();                                                 // the window columns were read from the planes as they were
-        if (merged != ot) {
-            if (lane == 0) tab[a] = merged;
-            if (((ot >> 16) & 1u) && ((ot ^ merged) & 0xFFFFu)) {
-                plane_arrive(cols, W, at, tx, ty, lane);              // (its barrier also publishes tab[a])
-                plane_leave(P, tab, cols, at, ot & 0xFFFFu, lane);
-            } else {
-                __syncwarp();
+            // ---- take_action(a): the pending row becomes the table row (World.py:331-332); Visible and status are
+            // whatever the others made of them meanwhile
+            const uint32_t nt = lds32(s_new + 4u * a);
+            constexpr uint32_t own = AT == T_OSTRICH ? 0x2FFFFu : 0xFFFFu;   // X, Y (+ an ostrich's role)
+            const uint32_t merged = (ot & ~own) | (nt & own);
+            const uint32_t tx = merged & 0xFFu, ty = (merged >> 8) & 0xFFu;
+            __syncwarp();                                             // the window columns were read from the planes as they were
+            if (merged != ot) {
+                if (lane == 0) sts32(s_tab + 4u * a, merged);
+                if (((ot >> 16) & 1u) && ((ot ^ merged) & 0xFFFFu)) {
+                    const uint32_t bit_n = 1u << (ty & 31u), bit_o = 1u << ((uint32_t)oy & 31u);
+                    const uint32_t s_n = s_cols + AT * plane_bytes + (tx << 3) + ((ty >> 5) << 2);
+                    const uint32_t s_o = s_cols + AT * plane_bytes + ((uint32_t)ox << 3) + (((uint32_t)oy >> 5) << 2);
+                    if (!(lds32(s_o + 3u * plane_bytes) & bit_o)) {   // nobody else was in the old cell: no scan
+                        if (lane == 0) {
+                            const uint32_t on = lds32(s_n);
+                            sts32(s_n, on | bit_n);
+                            if (on & bit_n) sts32(s_n + 3u * plane_bytes, lds32(s_n + 3u * plane_bytes) | bit_n);
+                            sts32(s_o, lds32(s_o) & ~bit_o);
+                        }
+                        __syncwarp();
+                    } else {
+                        plane_arrive(cols, W, AT, tx, ty, lane);      // (its barrier also publishes tab[a])
+                        plane_leave(P, tab, cols, AT, ot & 0xFFFFu, lane);
+                    }
+                } else {
+                    __syncwarp();
+                }
             }
-        }
-        // ---- default_game_update (World.py:93-132)
-        if (at != T_BUSH) {
-            const uint32_t want = at == T_WOLF ? T_OSTRICH : T_BUSH;
-            if ((cols[col_word(W, want, tx, ty)] >> (ty & 31)) & 1u) {
+            // ---- default_game_update (World.py:93-132)
+            constexpr uint32_t want = AT == T_WOLF ? T_OSTRICH : T_BUSH;
+            if ((lds32(s_cols + want * plane_bytes + (tx << 3) + ((ty >> 5) << 2)) >> (ty & 31u)) & 1u) {
                 int lo, hi;
                 type_range(P, want, lo, hi);
                 const uint32_t cellv = (merged & 0xFFFFu) | (1u << 16);
@@ -309,7 +321,7 @@ __global__ void __launch_bounds__(128) wab2_grid_turn_kernel(const __grid_consta
                         seen += c;
                     }
                     __syncwarp();
-                    if (at == T_WOLF) {
+                    if (AT == T_WOLF) {
                         const uint32_t jt = tab[j];
                         __syncwarp();              // every lane holds the old row of label j before lane 0 rewrites it
                         if (lane == 0) {
@@ -332,13 +344,35 @@ __global__ void __launch_bounds__(128) wab2_grid_turn_kernel(const __grid_consta
                     }
                 }
             }
+            // ---- 3. a full group (or the last observer): windows out
+            if (observe && (a - g0 == kGridGroup - 1 || a == A - 1)) {
+                __syncwarp();
+                grid_flush_group(s_stage, s_lut, o_planes + (int64_t)g0 * obs_bytes, a - g0 + 1, S, SW, inv_s, inv_ob, obs_bytes, lane);
+                __syncwarp();
+                g0 = a + 1;
+            }
         }
-        // ---- 3. a full group (or the last observer): windows out
-        if (observe_any && acting && (a - g0 == kGridGroup - 1 || a == A - 1)) {
+    };
+    entities(std::integral_constant<uint32_t, T_OSTRICH>(), 0, nO);
+    entities(std::integral_constant<uint32_t, T_WOLF>(), nO, A);
+    // bushes never move: their "action" only refreshes a table position left stale by reset_world (World.py:353-356),
+    // i.e. it is a no-op except in the first turn of an episode
+    if (turn == 0u) {
+        uint32_t bush_ob = 0u;
+        for (int a = A; a < E; ++a) {
+            if (((a - A) & 31) == 0) bush_ob = a + lane < E ? gent[a + lane] : 0u;      // 32 bushes' coordinates per load
+            const uint32_t ob = __shfl_sync(FULL, bush_ob, (a - A) & 31), ot = tab[a];
+            const uint32_t merged = (ot & ~0xFFFFu) | (uint32_t)pymod(unpack_x(ob), W) | ((uint32_t)pymod(unpack_y(ob), H) << 8);
             __syncwarp();
-            grid_flush_group(stage, lut, o_planes + (int64_t)g0 * obs_bytes, a - g0 + 1, S, SW, inv_s, inv_ob, obs_bytes, lane);
-            __syncwarp();
-            g0 = a + 1;
+            if (merged != ot) {
+                if (lane == 0) tab[a] = merged;
+                if ((ot >> 16) & 1u) {
+                    plane_arrive(cols, W, T_BUSH, merged & 0xFFu, (merged >> 8) & 0xFFu, lane);
+                    plane_leave(P, tab, cols, T_BUSH, ot & 0xFFFFu, lane);
+                } else {
+                    __syncwarp();
+                }
+            }
         }
     }
     __syncwarp();

@@ -20,6 +20,7 @@
 
 #include <new>
 #include <string>
+#include <type_traits>
 
 #include "../../include/wab_b200.h"
 #include "wab_core.cuh"
