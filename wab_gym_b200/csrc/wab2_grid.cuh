@@ -111,12 +111,14 @@ __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st
 // whole 16-byte chunks go out as one streaming store per lane, the < 16 bytes at either end of the run byte by byte.
 // inv_s = ceil(2^20 / S): (p * inv_s) >> 20 == p / S for p < 3 S^2 (p * S < 2^20); inv_ob = ceil(2^32 / obs_bytes):
 // __umulhi(b, inv_ob) == b / obs_bytes for b < kGridGroup * obs_bytes (b * obs_bytes < 2^32).
+template <bool NARROW>
 __device__ __forceinline__ uint32_t window_bits16(uint32_t s_col, int S, uint32_t r) {   // 16 bits from bit r of column word s_col on
     uint32_t h = (lds32(s_col) >> r) | (lds32(s_col + 4u) << (S - r));
-    if (S < 15)                                                      // narrow windows: more than two columns in 16 bits
+    if (NARROW)                                                      // windows narrower than 15: more than two columns in 16 bits
         for (int filled = 2 * S - (int)r, k = 2; filled < 16; filled += S, ++k) h |= lds32(s_col + 4u * k) << filled;
     return h;
 }
+template <bool NARROW>
 __device__ __forceinline__ void grid_flush_group(uint32_t s_stage, uint32_t s_lut, uint8_t* dst, int g, int S, int SW,
                                                  uint32_t inv_s, uint32_t inv_ob, int obs_bytes, int lane) {
     const int total = g * obs_bytes;
@@ -124,29 +126,34 @@ __device__ __forceinline__ void grid_flush_group(uint32_t s_stage, uint32_t s_lu
     const int head = off ? min(16 - off, total) : 0;             // bytes before the first whole chunk
     const int n_chunks = (total - head) >> 4;
     uint4* out16 = reinterpret_cast<uint4*>(dst + head) + lane;
-    uint32_t pg = (uint32_t)(head + (lane << 4));                // byte of the run = window e, bit p
+    // this lane's chunk: byte head + 16 c of the run = bit p of the window in slot s_slot; 32 chunks = 512 bytes further per round
+    uint32_t p = (uint32_t)(head + (lane << 4));
+    const uint32_t e0 = __umulhi(p, inv_ob);
+    p -= e0 * (uint32_t)obs_bytes;
+    uint32_t s_slot = s_stage + e0 * (uint32_t)(SW * 4);
 #pragma unroll 1
-    for (int c = lane; c < n_chunks; c += 32, pg += 512u, out16 += 32) {
-        const uint32_t e = __umulhi(pg, inv_ob), p = pg - e * (uint32_t)obs_bytes;
+    for (int c = lane; c < n_chunks; c += 32, out16 += 32) {
         const uint32_t q = (p * inv_s) >> 20, r = p - q * (uint32_t)S;
-        const uint32_t s_slot = s_stage + e * (uint32_t)(SW * 4);
-        uint32_t h = window_bits16(s_slot + q * 4u, S, r);
+        uint32_t h = window_bits16<NARROW>(s_slot + q * 4u, S, r);
         const int have = obs_bytes - (int)p;                     // the zero words behind a slot's last column end its bits
-        if (have < 16) h |= window_bits16(s_slot + (uint32_t)(SW * 4), S, 0u) << have;
+        if (have < 16) h |= window_bits16<NARROW>(s_slot + (uint32_t)(SW * 4), S, 0u) << have;
         const uint2 lo = lds64(s_lut + ((h & 0xFFu) << 3)), hi = lds64(s_lut + ((h >> 5) & 0x7F8u));
         __stcs(out16, make_uint4(lo.x, lo.y, hi.x, hi.y));
+        p += 512u;
+        while (p >= (uint32_t)obs_bytes) { p -= (uint32_t)obs_bytes; s_slot += (uint32_t)(SW * 4); }
     }
     const int tail0 = head + (n_chunks << 4);
     const int pb = lane < 16 ? lane : tail0 + lane - 16;             // ragged head (lanes 0-15) and tail (lanes 16-31)
     if (lane < 16 ? pb < head : pb < total) {
-        const uint32_t e = __umulhi((uint32_t)pb, inv_ob), p = (uint32_t)pb - e * (uint32_t)obs_bytes;
-        const uint32_t q = (p * inv_s) >> 20, r = p - q * (uint32_t)S;
+        const uint32_t e = __umulhi((uint32_t)pb, inv_ob), pw = (uint32_t)pb - e * (uint32_t)obs_bytes;
+        const uint32_t q = (pw * inv_s) >> 20, r = pw - q * (uint32_t)S;
         dst[pb] = (uint8_t)((lds32(s_stage + (e * (uint32_t)SW + q) * 4u) >> r) & 1u);
     }
 }
 
-// One world turn, one warp per world. H64: the world is 64 high (a window column is one funnel shift of the plane column).
-template <bool H64>
+// One world turn, one warp per world. H64: the world is 64 high (a window column is one funnel shift of the plane column);
+// NARROW: the window is narrower than 15 cells.
+template <bool H64, bool NARROW>
 __global__ void __launch_bounds__(128) wab2_grid_turn_kernel(const __grid_constant__ Params2 P, const State2Ptrs st,
                                                              const uint8_t* __restrict__ actions, const Out2Ptrs out) {
     extern __shared__ uint32_t smem2[];
@@ -237,8 +244,7 @@ __global__ void __launch_bounds__(128) wab2_grid_turn_kernel(const __grid_consta
     const int dx = lane - R;
     const uint32_t plane_bytes = (uint32_t)W * 8u;                    // one occupancy plane
     bool bush_dirty = turn == 0u;
-    int g0 = 0;                                                       // first entity of the staged group
-    auto entities = [&](auto type_tag, const int a_begin, const int a_end) {
+    auto entities = [&](auto type_tag, const int g0, const int a_begin, const int a_end) {   // g0: first entity of the staged group
         constexpr uint32_t AT = decltype(type_tag)::value;
 #pragma unroll 1
         for (int a = a_begin; a < a_end; ++a) {
@@ -276,12 +282,13 @@ __global__ void __launch_bounds__(128) wab2_grid_turn_kernel(const __grid_consta
             constexpr uint32_t own = AT == T_OSTRICH ? 0x2FFFFu : 0xFFFFu;   // X, Y (+ an ostrich's role)
             const uint32_t merged = (ot & ~own) | (nt & own);
             const uint32_t tx = merged & 0xFFu, ty = (merged >> 8) & 0xFFu;
+            const uint32_t s_cell = s_cols + (tx << 3) + ((ty >> 5) << 2);   // the new cell's word in plane 0
             __syncwarp();                                             // the window columns were read from the planes as they were
             if (merged != ot) {
                 if (lane == 0) sts32(s_tab + 4u * a, merged);
                 if (((ot >> 16) & 1u) && ((ot ^ merged) & 0xFFFFu)) {
                     const uint32_t bit_n = 1u << (ty & 31u), bit_o = 1u << ((uint32_t)oy & 31u);
-                    const uint32_t s_n = s_cols + AT * plane_bytes + (tx << 3) + ((ty >> 5) << 2);
+                    const uint32_t s_n = s_cell + AT * plane_bytes;
                     const uint32_t s_o = s_cols + AT * plane_bytes + ((uint32_t)ox << 3) + (((uint32_t)oy >> 5) << 2);
                     if (!(lds32(s_o + 3u * plane_bytes) & bit_o)) {   // nobody else was in the old cell: no scan
                         if (lane == 0) {
@@ -301,7 +308,7 @@ __global__ void __launch_bounds__(128) wab2_grid_turn_kernel(const __grid_consta
             }
             // ---- default_game_update (World.py:93-132)
             constexpr uint32_t want = AT == T_WOLF ? T_OSTRICH : T_BUSH;
-            if ((lds32(s_cols + want * plane_bytes + (tx << 3) + ((ty >> 5) << 2)) >> (ty & 31u)) & 1u) {
+            if ((lds32(s_cell + want * plane_bytes) >> (ty & 31u)) & 1u) {
                 int lo, hi;
                 type_range(P, want, lo, hi);
                 const uint32_t cellv = (merged & 0xFFFFu) | (1u << 16);
@@ -344,17 +351,18 @@ __global__ void __launch_bounds__(128) wab2_grid_turn_kernel(const __grid_consta
                     }
                 }
             }
-            // ---- 3. a full group (or the last observer): windows out
-            if (observe && (a - g0 == kGridGroup - 1 || a == A - 1)) {
-                __syncwarp();
-                grid_flush_group(s_stage, s_lut, o_planes + (int64_t)g0 * obs_bytes, a - g0 + 1, S, SW, inv_s, inv_ob, obs_bytes, lane);
-                __syncwarp();
-                g0 = a + 1;
-            }
         }
     };
-    entities(std::integral_constant<uint32_t, T_OSTRICH>(), 0, nO);
-    entities(std::integral_constant<uint32_t, T_WOLF>(), nO, A);
+    for (int g0 = 0; g0 < A; g0 += kGridGroup) {
+        const int g1 = min(g0 + kGridGroup, A);
+        entities(std::integral_constant<uint32_t, T_OSTRICH>(), g0, g0, min(g1, nO));
+        entities(std::integral_constant<uint32_t, T_WOLF>(), g0, max(g0, nO), g1);
+        if (observe) {                                                // ---- 3. a full group (or the last observers): windows out
+            __syncwarp();
+            grid_flush_group<NARROW>(s_stage, s_lut, o_planes + (int64_t)g0 * obs_bytes, g1 - g0, S, SW, inv_s, inv_ob, obs_bytes, lane);
+            __syncwarp();
+        }
+    }
     // bushes never move: their "action" only refreshes a table position left stale by reset_world (World.py:353-356),
     // i.e. it is a no-op except in the first turn of an episode
     if (turn == 0u) {

@@ -130,6 +130,13 @@ __global__ void wab2_turn_kernel(const __grid_constant__ Params2 P, const State2
 
 #include "wab2_grid.cuh"
 
+typedef void (*GridKernel)(const Params2, const State2Ptrs, const uint8_t*, const Out2Ptrs);
+static GridKernel grid_kernel_for(const Params2& P) {
+    const bool h64 = P.height == 64, narrow = 2 * P.window_r + 1 < 15;
+    return h64 ? (narrow ? wab2_grid_turn_kernel<true, true> : wab2_grid_turn_kernel<true, false>)
+               : (narrow ? wab2_grid_turn_kernel<false, true> : wab2_grid_turn_kernel<false, false>);
+}
+
 struct Wab2World {
     Wab2Config cfg;
     Params2 P;
@@ -196,9 +203,7 @@ int wab2_create(const Wab2Config* cfg, int64_t n_envs, uint64_t seed, uint64_t e
     cudaError_t e = cudaSuccess;
     if (h->grid) {
         h->smem_turn = sizeof(uint32_t) * ((size_t)4 * grid_geom(E, P.n_acting, cfg->width, S).total + 512);
-        e = cfg->height == 64
-            ? cudaFuncSetAttribute(wab2_grid_turn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_turn)
-            : cudaFuncSetAttribute(wab2_grid_turn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_turn);
+        e = cudaFuncSetAttribute(grid_kernel_for(h->P), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_turn);
     } else
         e = cudaFuncSetAttribute(wab2_turn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_turn);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(wab2_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_init);
@@ -248,10 +253,8 @@ int wab2_turn(Wab2World* h, const uint8_t* d_actions, uint8_t* d_planes, int32_t
     if (d_planes) if (int rc = check_ptr_align(d_planes, "d_planes")) return rc;
     DeviceGuard guard(h->device);
     Out2Ptrs out{d_planes, d_internal, d_reward, d_done};
-    if (h->grid && h->P.height == 64)
-        wab2_grid_turn_kernel<true><<<(unsigned)((h->n + 3) / 4), 128, h->smem_turn, (cudaStream_t)stream>>>(h->P, h->st, d_actions, out);
-    else if (h->grid)
-        wab2_grid_turn_kernel<false><<<(unsigned)((h->n + 3) / 4), 128, h->smem_turn, (cudaStream_t)stream>>>(h->P, h->st, d_actions, out);
+    if (h->grid)
+        grid_kernel_for(h->P)<<<(unsigned)((h->n + 3) / 4), 128, h->smem_turn, (cudaStream_t)stream>>>(h->P, h->st, d_actions, out);
     else
         wab2_turn_kernel<<<(unsigned)((h->n + h->bs - 1) / h->bs), h->bs, h->smem_turn, (cudaStream_t)stream>>>(
             h->P, h->st, d_actions, out, h->stream_words);
