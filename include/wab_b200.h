@@ -206,6 +206,18 @@ int wab_sample_categorical(const void *d_probs, int32_t probs_bf16, int64_t n, i
 int wab_vec_enable_ego(WabVec *h);
 int wab_vec_ego_proximities(WabVec *h, uint8_t *d_out10, void *stream);
 
+/* The first layer of the reference's Policy on the tensor cores (actor_critic.py:59, :88-90, :188-189), fp32 accuracy:
+ * d_out f32[n_rows][128] = leaky_relu(affine1(flatten(obs) + noise_scale * U[0,1))) straight from the 28 feature bytes per
+ * row (d_features as in wab_vec_flatten_features) — the 449-wide input is generated inside the kernel, with the SAME keyed
+ * noise as wab_vec_flatten_features_noisy for the same *d_counter, and never written to memory. One tcgen05 kernel
+ * (bf16 x 3 operand splits, fp32 accumulation in tensor memory; the result equals the fp32 GEMM to rounding).
+ * wab_policy_affine1_prepare packs affine1.weight f32[128][in_dim] (in_dim = wab_vec_flat_dim, at most 512) into
+ * d_packed (wab_policy_affine1_packed_bytes() bytes, 16-byte aligned) — once per weight update; d_bias f32[128]. */
+int64_t wab_policy_affine1_packed_bytes(void);
+int wab_policy_affine1_prepare(const float *d_weight, int32_t in_dim, void *d_packed, void *stream);
+int wab_policy_affine1(WabVec *h, const uint8_t *d_features, int64_t n_rows, const void *d_packed, const float *d_bias,
+                       float noise_scale, float leaky_slope, const uint64_t *d_counter, float *d_out, void *stream);
+
 /* The tail of the reference's Policy.forward + select_action (actor_critic.py:84-97, :108-125) for n_rows rows in one
  * pass, fp32: d_z3 f32[n_rows][128] is the PRE-activation output of affine3; x = clamp(leaky_relu(z3), lo, hi);
  * logits = W[0..A) x + b, value = W[A] x + b[A] (d_w_heads f32[A + 1][128] = action_head.weight stacked on

@@ -77,3 +77,60 @@ def test_rollout_runs_on_the_fused_tail(use_graph):
     assert st["steps"] - before == 2048 * 120 and st["bad_actions"] == 0 and st["episodes"] > 2048
     assert len(torch.unique(ro.actions)) > 1 and torch.isfinite(ro.values).all()
     env.close()
+
+
+@pytest.mark.parametrize("noise", [0.0, 0.01])
+@pytest.mark.parametrize("n", [128, 1000, 4099])
+def test_tensor_core_first_layer_matches_torch_fp32(n, noise):
+    """wab_policy_affine1 (tcgen05, bf16 x 3 operand splits) against what it replaces: the materialised policy input
+    (flatten + the same keyed noise, ``actor_critic.py:188-189``) through ``Policy.affine1`` and ``leaky_relu`` (``:59``,
+    ``:88-90``) in plain torch (fp64 as the yardstick, the library's fp32 GEMM beside it). fp32 accuracy: 2e-6 of the largest sum."""
+    from wab_gym_b200 import VecEnv
+    from wab_gym_b200.policy import Affine1TC
+    env = VecEnv(n, seed=5, features=True)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(n)
+    for _ in range(30):                                              # envs of every age, both roles, wolves around
+        env.step(torch.randint(0, env.n_actions, (n,), dtype=torch.uint8, device="cuda", generator=g))
+    pol = _policy(env.n_actions, seed=3)
+    with torch.no_grad():
+        pol.affine1.weight.mul_(3.0)                                 # both signs of the activation well populated
+    ctr = torch.full((1,), 7, dtype=torch.int64, device="cuda")
+    flat = torch.empty(n, env.flat_dim, dtype=torch.float32, device="cuda")
+    env.flatten_features_noisy(env.last_features, flat, noise, ctr)
+    tc = Affine1TC(env, pol)
+    got = torch.full((n, 128), float("nan"), device="cuda")
+    tc(env.last_features, got, noise, ctr)
+    with torch.no_grad():
+        want = F.leaky_relu(F.linear(flat.double(), pol.affine1.weight.double(), pol.affine1.bias.double())).float()
+        lib32 = F.leaky_relu(pol.affine1(flat))
+    err, err32 = float((got - want).abs().max()), float((lib32 - want).abs().max())
+    assert torch.isfinite(got).all()
+    scale = float(want.abs().max())                                  # sums of ~50 products of size <= 0.5
+    assert err <= 2e-6 * max(scale, 1.0), (err, err32, scale)        # the library's fp32 GEMM itself is ~1.5e-6 off the fp64 result
+    if noise:                                                        # a different draw counter -> different noise
+        ctr += 1
+        other = torch.empty_like(got)
+        tc(env.last_features, other, noise, ctr)
+        assert float((other - got).abs().max()) > 1e-4
+    env.close()
+
+
+def test_rollout_with_tensor_core_first_layer_equals_library_first_layer():
+    """Same seeds, same noise counter: the rollout with the tcgen05 first layer takes the same actions as the one that
+    materialises the input and calls the library GEMM (fp32 differences of 1e-6 do not move a sampled action here)."""
+    from wab_gym_b200 import VecEnv
+    from wab_gym_b200.policy import Rollout
+    acts = []
+    for tc in (False, True):
+        torch.manual_seed(0)
+        env = VecEnv(2048, seed=9, features=True)
+        ro = Rollout(env, _policy(env.n_actions, seed=1), tc_first_layer=tc)
+        seq = []
+        for _ in range(12):
+            ro.step()
+            seq.append(ro.actions.clone())
+        acts.append(torch.stack(seq))
+        env.close()
+    same = (acts[0] == acts[1]).float().mean().item()
+    assert same > 0.999, same

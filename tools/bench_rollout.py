@@ -23,11 +23,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--graph", action="store_true")
     ap.add_argument("--bf16", action="store_true")
+    ap.add_argument("--no-tc", action="store_true", help="first layer as flatten kernel + library GEMM instead of the tcgen05 kernel")
     args = ap.parse_args()
     torch.manual_seed(0)
     env = VecEnv(args.num_envs, seed=0, features=True)
     ro = Rollout(env, Policy(env.flat_dim, env.n_actions), use_graph=args.graph,
-                 dtype=torch.bfloat16 if args.bf16 else torch.float32)
+                 dtype=torch.bfloat16 if args.bf16 else torch.float32, tc_first_layer=False if (args.no_tc or args.bf16) else None)
     ro.run(args.warmup)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -39,7 +40,7 @@ def main():
     st = env.stats()
     print(json.dumps({"workload": "config 5: actor-critic rollout, %d v1 envs on 1 GPU, policy 449-128-150-128-{5,1} %s, %s" % (
                           args.num_envs, "bf16" if args.bf16 else "fp32", "CUDA graph" if args.graph else "eager"),
-                      "env_steps_per_s": args.num_envs * args.steps / (ms * 1e-3), "ms_per_step": ms / args.steps,
+                      "path": ro.describe(), "env_steps_per_s": args.num_envs * args.steps / (ms * 1e-3), "ms_per_step": ms / args.steps,
                       "episodes": st["episodes"], "mean_episode_length": st["steps"] / max(st["episodes"], 1),
                       "finished": st["finished"], "starved": st["starved"], "killed": st["killed"]}))
     env.close()

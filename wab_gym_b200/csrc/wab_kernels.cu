@@ -731,6 +731,10 @@ __global__ void __launch_bounds__(256) wab_flatten_noisy_kernel(const __grid_con
     }
 }
 
+}  // namespace
+#include "wab_policy_tc.cuh"
+namespace {
+
 // The tail of the reference's Policy.forward and select_action in one pass (actor_critic.py:84-97, :108-125): from the
 // pre-activation output z3 of affine3, x = clamp(leaky_relu(z3), -4, 4); logits = action_head(x); value = value_head(x);
 // probs = softmax(logits); action = Categorical(probs).sample() (inverse CDF on one keyed uniform per row) and its
@@ -1557,6 +1561,39 @@ int wab_vec_flatten_features_noisy(WabVec* h, const uint8_t* d_features, int64_t
         wab_flatten_noisy_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(h->P, d_features, n_rows, food_dim, d_out, noise_scale, ctr);
     else
         wab_flatten_noisy_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(h->P, d_features, n_rows, food_dim, d_out, noise_scale, ctr);
+    WAB_CUDA(cudaGetLastError());
+    return WAB_OK;
+}
+
+int64_t wab_policy_affine1_packed_bytes(void) { return (int64_t)TC_CHUNKS * 3 * TC_PART_BYTES; }
+
+int wab_policy_affine1_prepare(const float* d_weight, int32_t in_dim, void* d_packed, void* stream) {
+    if (!d_weight || !d_packed) return fail(WAB_E_NULL, "null argument");
+    if (in_dim < 1 || in_dim > TC_CHUNKS * TC_KC) return fail(WAB_E_UNSUPPORTED, "wab_policy_affine1: the input is at most 512 columns wide");
+    if (((uintptr_t)d_packed & 15u) != 0) return fail(WAB_E_CONFIG, "d_packed must be 16-byte aligned");
+    const int total = TC_CHUNKS * TC_N * TC_KC;
+    wab_affine1_prepare_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_weight, in_dim, reinterpret_cast<uint16_t*>(d_packed));
+    WAB_CUDA(cudaGetLastError());
+    return WAB_OK;
+}
+
+int wab_policy_affine1(WabVec* h, const uint8_t* d_features, int64_t n_rows, const void* d_packed, const float* d_bias,
+                       float noise_scale, float leaky_slope, const uint64_t* d_counter, float* d_out, void* stream) {
+    if (!h || !d_features || !d_packed || !d_bias || !d_out) return fail(WAB_E_NULL, "null argument");
+    if (n_rows <= 0) return WAB_OK;
+    if (((uintptr_t)d_out & 15u) != 0 || ((uintptr_t)d_packed & 15u) != 0 || ((uintptr_t)d_features & 3u) != 0)
+        return fail(WAB_E_CONFIG, "d_out and d_packed must be 16-byte aligned, d_features 4-byte aligned");
+    if (wab_vec_flat_dim(h) > TC_CHUNKS * TC_KC) return fail(WAB_E_UNSUPPORTED, "wab_policy_affine1: the input is at most 512 columns wide");
+    DeviceGuard guard(h->device);
+    static bool attr_set[64] = {false};
+    if (h->device < 64 && !attr_set[h->device]) {
+        WAB_CUDA(cudaFuncSetAttribute(wab_affine1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_TOTAL));
+        attr_set[h->device] = true;
+    }
+    const unsigned grid = (unsigned)((n_rows + TC_TILE_M - 1) / TC_TILE_M);
+    wab_affine1_tc_kernel<<<grid, 256, TC_SMEM_TOTAL, (cudaStream_t)stream>>>(
+        h->P, d_features, n_rows, (int)h->cfg.food_obs_scale + 1, reinterpret_cast<const uint4*>(d_packed), d_bias, noise_scale,
+        leaky_slope, reinterpret_cast<const unsigned long long*>(d_counter), d_out);
     WAB_CUDA(cudaGetLastError());
     return WAB_OK;
 }

@@ -1,0 +1,278 @@
+// wab_policy_tc.cuh — the first layer of the reference's Policy (actor_critic.py:59, :88-90) on the 5th-generation tensor
+// cores: h1 = leaky_relu(affine1(flatten(obs) + U[0,1)/100)) for a batch of environments, straight from the 28 feature
+// bytes per environment (wab_features.cuh). Included by wab_kernels.cu.
+//
+// This is the one dense contraction on the consumer side of the path (32,768 x 449 x 128 per rollout step). The library
+// route is three passes — write the 449-wide input (wab_flatten_noisy_kernel), an fp32 SIMT GEMM (cuBLAS), the activation —
+// and spends 54 us of a 281 us rollout step in the GEMM alone. Here ONE kernel does all of it and the input matrix never
+// exists in HBM:
+//   * a CTA owns a tile of 128 environments; its 256 threads GENERATE the A operand of each K-chunk in shared memory:
+//     the one-hot columns from the feature bytes, the same keyed noise as wab_flatten_noisy_kernel (one Philox4x32 call
+//     per 4 columns), x = onehot + scale * u in fp32 exactly as that kernel computes it;
+//   * fp32 accuracy on bf16 tensor cores: W is split into three bf16 terms (W = W0 + W1 + W2, 24 mantissa bits) and x into
+//     its one-hot part o (0 or 1: exact in bf16) and its noise part n = x - o (exact in fp32; n = n0 + n1 to 2^-16 of
+//     its size, which is <= noise_scale); six products are accumulated in fp32 in tensor memory:
+//     o W0 + o W1 + o W2 + n0 W0 + n0 W1 + n1 W0 (what is dropped is below 2^-24 of the sum, i.e. fp32 rounding);
+//   * tcgen05.mma (M 128, N 128, K 16, kind::f16, operands by shared-memory descriptor, no swizzle), issued by one
+//     thread, completion through tcgen05.commit on an mbarrier; accumulators read back with tcgen05.ld for the
+//     epilogue (bias, leaky-ReLU, 16-byte stores of the 128 outputs).
+//   * The K order inside the product is free, so it is chosen for the generator: chunk c (64 columns) holds the columns
+//     k = 128 (c >> 1) + 32 s + j, s = 0..3, j = 16 (c & 1) .. + 16 — the four words of 16 Philox calls — and
+//     wab_policy_affine1_prepare lays the split weights out in the same order (and in the canonical core-matrix
+//     layout), once per weight update.
+#pragma once
+
+namespace {
+
+constexpr int TC_TILE_M = 128;          // environments per CTA
+constexpr int TC_N = 128;               // affine1 outputs (actor_critic.py:59)
+constexpr int TC_KC = 64;               // K columns per chunk
+constexpr int TC_CHUNKS = 8;            // 512 >= 449 columns (the padding columns are zero on both sides)
+constexpr int TC_PART_BYTES = TC_TILE_M * TC_KC * 2;        // one bf16 operand part of one chunk: 16 KB
+constexpr int TC_ROWBITS_STRIDE = 17;   // words per row of the one-hot bit vectors (16 + 1: conflict-free for a thread per row)
+constexpr int TC_SMEM_A = 0, TC_SMEM_B = 3 * TC_PART_BYTES, TC_SMEM_BITS = 6 * TC_PART_BYTES,
+              TC_SMEM_BAR = TC_SMEM_BITS + TC_TILE_M * TC_ROWBITS_STRIDE * 4, TC_SMEM_TOTAL = TC_SMEM_BAR + 16;
+
+// canonical K-major layout without swizzle (UMMA "interleave"): core matrix = 8 rows x 16 bytes, contiguous (128 B);
+// core matrices adjacent in K 128 B apart (leading byte offset), 8-row groups 1024 B apart (stride byte offset)
+__host__ __device__ inline int tc_elem_offset(int row, int kc, int e) { return (row >> 3) * 512 + kc * 64 + (row & 7) * 8 + e; }
+// chunk c, core-matrix column kc (0..7), element e (0..7) -> column of the 449-wide input (may be >= dim: padding)
+__host__ __device__ inline int tc_column(int c, int kc, int e) {
+    const int h = kc >> 2, s = kc & 3, j = 16 * (c & 1) + 8 * h + e;
+    return 128 * (c >> 1) + 32 * s + j;
+}
+
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {   // matrix descriptor: start, LBO 128 B, SBO 1024 B, version 1, no swizzle
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46);
+}
+// instruction descriptor, kind::f16: D fp32 (bits 4-5 = 1), A and B bf16 (bits 7-9, 10-12 = 1), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_TILE_M >> 4) << 24);
+
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(TC_IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (uint32_t spins = 0; !ok; ++spins) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (spins > (1u << 26)) __trap();          // a wrong descriptor must fail loudly, never hang the device
+    }
+}
+// v = p0 + p1 + p2 exactly (three bf16 terms carry 24 mantissa bits)
+__device__ __forceinline__ void tc_split3(float v, uint32_t& p0, uint32_t& p1, uint32_t& p2) {
+    const __nv_bfloat16 b0 = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(b0);
+    const __nv_bfloat16 b1 = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(b1);
+    const __nv_bfloat16 b2 = __float2bfloat16_rn(r2);
+    p0 = (uint32_t)__bfloat16_as_ushort(b0); p1 = (uint32_t)__bfloat16_as_ushort(b1); p2 = (uint32_t)__bfloat16_as_ushort(b2);
+}
+
+// W f32[128][dim] (nn.Linear weight) -> packed bf16 [chunk][part][tc_elem_offset(n, kc, e)], parts W0, W1, W2
+__global__ void wab_affine1_prepare_kernel(const float* __restrict__ w, int dim, uint16_t* __restrict__ packed) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;            // (chunk, n, kc, e)
+    if (idx >= TC_CHUNKS * TC_N * TC_KC) return;
+    const int e = idx & 7, kc = (idx >> 3) & 7, n = (idx >> 6) & 127, c = idx >> 13;
+    const int k = tc_column(c, kc, e);
+    const float v = k < dim ? w[(int64_t)n * dim + k] : 0.f;
+    uint32_t p0, p1, p2;
+    tc_split3(v, p0, p1, p2);
+    const int off = tc_elem_offset(n, kc, e), part = TC_TILE_M * TC_KC;
+    packed[(c * 3 + 0) * part + off] = (uint16_t)p0;
+    packed[(c * 3 + 1) * part + off] = (uint16_t)p1;
+    packed[(c * 3 + 2) * part + off] = (uint16_t)p2;
+}
+
+// 32 consecutive accumulator columns of this thread's tensor-memory lane (issue only; tcgen05.wait::ld before use)
+__device__ __forceinline__ void tc_tmem_ld32(uint32_t taddr, uint32_t v[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                   "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                   "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr) : "memory");
+}
+
+// two fp32 -> one word of two bf16 (round to nearest even), `lo` in the low half
+__device__ __forceinline__ uint32_t tc_pack_bf16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+
+__global__ void __launch_bounds__(256, 2)
+wab_affine1_tc_kernel(const __grid_constant__ Params P, const uint8_t* __restrict__ features, int64_t rows, int food_dim,
+                      const uint4* __restrict__ wpacked, const float* __restrict__ bias, float noise_scale, float slope,
+                      const unsigned long long* __restrict__ d_counter, float* __restrict__ out) {
+    extern __shared__ __align__(1024) uint8_t tc_smem[];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(tc_smem);
+    const uint32_t s_a = s_base + TC_SMEM_A, s_b = s_base + TC_SMEM_B, s_bar = s_base + TC_SMEM_BAR;
+    uint32_t* rowbits = reinterpret_cast<uint32_t*>(tc_smem + TC_SMEM_BITS);
+    const int64_t row0 = (int64_t)blockIdx.x * TC_TILE_M;
+
+    if (warp == 0) {                                      // two fp32 accumulators of 128 columns in tensor memory
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(&tmem_slot)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(s_bar), "r"(1u) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // ---- the one-hot part of the tile's rows as bit vectors (bit k = column k of gym.spaces.flatten, wab_env.py:710-724):
+    // one thread per row walks the 28 features instead of the 449 columns
+    if (tid >= 128) {
+        const int rr = tid - 128;
+        const int64_t grow = row0 + rr;
+        uint32_t* bits = rowbits + rr * TC_ROWBITS_STRIDE;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) bits[k] = 0u;
+        if (grow < rows) {
+            uint32_t fw[7];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) fw[k] = reinterpret_cast<const uint32_t*>(features)[grow * 7 + k];
+            auto fbyte = [&](int i) { return (int)((fw[i >> 2] >> (8 * (i & 3))) & 0xFFu); };
+            auto hot = [&](int col) { bits[col >> 5] |= 1u << (col & 31); };
+#pragma unroll
+            for (int species = 0; species < 2; ++species) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { const int v = fbyte(species * 12 + i); if (v < 12) hot(species * 140 + i * 12 + v); }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { const int v = fbyte(species * 12 + 8 + i); if (v < 11) hot(species * 140 + 96 + i * 11 + v); }
+            }
+            { const int v = fbyte(24); if (v < 2) hot(280 + v); }
+            { const int v = fbyte(25); if (v < food_dim) hot(282 + v); }
+            { const int v = fbyte(26); if (v < 2) hot(282 + food_dim + v); }
+            { const int v = fbyte(27); if (v < 3) hot(284 + food_dim + v); }
+            if (P.restrict_view) {                                    // the 121-cell view mask of the role (obs[6])
+                const uint32_t* vm = fbyte(26) == 1 ? P.mask_gath : P.mask_look;
+                const int base = 287 + food_dim;
+#pragma unroll
+                for (int wd = 0; wd < 4; ++wd) {
+                    const uint32_t m = wd == 3 ? vm[3] & ((1u << (CELLS - 96)) - 1u) : vm[wd];
+                    const int pos = base + 32 * wd;
+                    bits[pos >> 5] |= m << (pos & 31);
+                    if (pos & 31) bits[(pos >> 5) + 1] |= m >> (32 - (pos & 31));
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+
+    const int r = tid & 127, h = tid >> 7;                // this thread's row of the tile and half of each chunk's lanes
+    const int64_t row = row0 + r;
+    const uint32_t* mybits = rowbits + r * TC_ROWBITS_STRIDE;
+    const unsigned long long ctr = d_counter ? *d_counter : 0ull;
+    const bool noisy = noise_scale != 0.f;
+    const float scale = noise_scale * (1.0f / 16777216.0f);
+    const uint32_t a_row = (uint32_t)((r >> 3) * 1024 + (r & 7) * 16);
+    uint32_t parity = 0;
+
+    for (int c = 0; c < TC_CHUNKS; ++c) {
+        // ---- A: 8 Philox calls -> 32 columns of this row (4 core-matrix columns of 8): x = onehot + scale * m in fp32 exactly
+        // as wab_flatten_noisy_kernel computes it; parts o (one-hot), n0, n1 (the noise x - o in two bf16 terms)
+        float x[4][8];
+        const int jb = 16 * (c & 1) + 8 * h;              // this thread's lanes j = jb .. jb + 7 of the chunk's Philox calls
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+            if (noisy)
+                philox(P, (uint32_t)row, (uint32_t)(row >> 32) ^ ((uint32_t)(c >> 1) << 24) ^ ((uint32_t)(jb + e) << 16), (uint32_t)ctr,
+                       (uint32_t)(ctr >> 32) ^ 0x464C4154u, w);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) x[s][e] = scale * (float)(w[s] >> 8);
+        }
+        uint32_t pk[3][4][4];                             // [part][s][word of the 16-byte vector]
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const uint32_t ob = (mybits[4 * (c >> 1) + s] >> jb) & 0xFFu;     // one-hot bits of columns 128 (c >> 1) + 32 s + jb ..
+#pragma unroll
+            for (int e2 = 0; e2 < 4; ++e2) {
+                const float oa = (float)((ob >> (2 * e2)) & 1u), obb = (float)((ob >> (2 * e2 + 1)) & 1u);
+                const float na = (oa + x[s][2 * e2]) - oa, nb = (obb + x[s][2 * e2 + 1]) - obb;   // the noise as it survives in x
+                const uint32_t n0 = tc_pack_bf16x2(na, nb);
+                const float ra = na - __uint_as_float(n0 << 16), rb = nb - __uint_as_float(n0 & 0xFFFF0000u);
+                pk[0][s][e2] = (((ob >> (2 * e2)) & 1u) * 0x3F80u) | (((ob >> (2 * e2 + 1)) & 1u) * 0x3F800000u);
+                pk[1][s][e2] = n0;
+                pk[2][s][e2] = tc_pack_bf16x2(ra, rb);
+            }
+        }
+        if (c > 0) { tc_mbar_wait(s_bar, parity); parity ^= 1u; }    // the MMAs of the previous chunk have read the operands
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(s_a + p * TC_PART_BYTES + a_row + (uint32_t)(h * 4 + s) * 128u),
+                             "r"(pk[p][s][0]), "r"(pk[p][s][1]), "r"(pk[p][s][2]), "r"(pk[p][s][3]) : "memory");
+        // ---- B: the chunk's three weight parts, 48 KB already in operand layout
+        const uint4* src = wpacked + (size_t)c * (3 * TC_PART_BYTES / 16);
+#pragma unroll 4
+        for (int k = tid; k < 3 * TC_PART_BYTES / 16; k += 256) {
+            const uint4 v = src[k];
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(s_b + (uint32_t)k * 16u), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core's reads
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int ks = 0; ks < TC_KC / 16; ++ks) {                  // K = 16 per instruction = two core-matrix columns = 256 B
+                const uint32_t ko = (uint32_t)ks * 256u;
+                const uint64_t a0 = tc_smem_desc(s_a + ko), a1 = tc_smem_desc(s_a + TC_PART_BYTES + ko), a2 = tc_smem_desc(s_a + 2 * TC_PART_BYTES + ko);
+                const uint64_t b0 = tc_smem_desc(s_b + ko), b1 = tc_smem_desc(s_b + TC_PART_BYTES + ko), b2 = tc_smem_desc(s_b + 2 * TC_PART_BYTES + ko);
+                // the tensor core's fp32 accumulation truncates: the leading term o W0 gets an accumulator of its own (one add per
+                // K step), the five corrections — 2^-8 of it and smaller — share the second; the epilogue adds the two
+                tc_mma(tmem, a0, b0, (c | ks) ? 1u : 0u);
+                tc_mma(tmem + 128u, a0, b1, (c | ks) ? 1u : 0u);
+                tc_mma(tmem + 128u, a1, b0, 1u);
+                tc_mma(tmem + 128u, a0, b2, 1u);
+                tc_mma(tmem + 128u, a1, b1, 1u);
+                tc_mma(tmem + 128u, a2, b0, 1u);
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(s_bar) : "memory");
+        }
+    }
+    tc_mbar_wait(s_bar, parity);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // ---- epilogue: warp w reads lanes 32 (w & 3) .. + 32 (its rows), columns 64 (w >> 2) .. + 64
+    {
+        const int q = warp & 3, ch = warp >> 2;
+        const int64_t orow = row0 + q * 32 + lane;
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+            const int col0 = ch * 64 + part * 32;
+            uint32_t v[32], u[32];
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
+            tc_tmem_ld32(taddr, v);
+            tc_tmem_ld32(taddr + 128u, u);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (orow < rows) {
+                float4* dst = reinterpret_cast<float4*>(out + orow * TC_N + col0);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float4 o;
+                    float t;
+                    t = (__uint_as_float(v[4 * i + 0]) + __uint_as_float(u[4 * i + 0])) + bias[col0 + 4 * i + 0]; o.x = t > 0.f ? t : t * slope;
+                    t = (__uint_as_float(v[4 * i + 1]) + __uint_as_float(u[4 * i + 1])) + bias[col0 + 4 * i + 1]; o.y = t > 0.f ? t : t * slope;
+                    t = (__uint_as_float(v[4 * i + 2]) + __uint_as_float(u[4 * i + 2])) + bias[col0 + 4 * i + 2]; o.z = t > 0.f ? t : t * slope;
+                    t = (__uint_as_float(v[4 * i + 3]) + __uint_as_float(u[4 * i + 3])) + bias[col0 + 4 * i + 3]; o.w = t > 0.f ? t : t * slope;
+                    dst[i] = o;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(256u) : "memory");
+}
+
+}  // namespace

@@ -68,6 +68,39 @@ def stacked_heads(policy: "Policy") -> tuple:
     return w, b
 
 
+class Affine1TC:
+    """``leaky_relu(policy.affine1(flatten(obs) + noise))`` (``actor_critic.py:59``, ``:88-90``, ``:188-189``) as ONE tcgen05
+    kernel of the library (``wab_policy_affine1``): the 449-wide input is generated inside the kernel from the 28 feature
+    bytes per environment — same keyed noise as ``VecEnv.flatten_features_noisy`` — and the product runs on the tensor
+    cores with bf16 x 3 operand splits and fp32 accumulation, i.e. to fp32 accuracy. ``refresh()`` re-packs the weights
+    after an optimiser step."""
+
+    def __init__(self, env: VecEnv, policy: "Policy"):
+        if policy.affine1.out_features != 128 or policy.affine1.in_features != env.flat_dim:
+            raise ValueError("Affine1TC is built for the reference's affine1: flat_dim -> 128")
+        self.env, self.policy, self.lib = env, policy, _lib.load()
+        self.packed = torch.empty(int(self.lib.wab_policy_affine1_packed_bytes()), dtype=torch.uint8, device=env.device)
+        self.bias = None
+        self.refresh()
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.env.device).cuda_stream)
+
+    @torch.no_grad()
+    def refresh(self):
+        w = self.policy.affine1.weight.detach().float().contiguous()
+        self.bias = self.policy.affine1.bias.detach().float().contiguous()
+        _lib.check(self.lib.wab_policy_affine1_prepare(_ptr(w), w.shape[1], _ptr(self.packed), self._stream()))
+
+    def __call__(self, features: torch.Tensor, out: torch.Tensor, noise_scale: float = 0.01,
+                 counter: Optional[torch.Tensor] = None, slope: float = 0.01) -> torch.Tensor:
+        if out.dtype != torch.float32 or not out.is_contiguous() or tuple(out.shape) != (features.shape[0], 128):
+            raise ValueError("out must be a contiguous float32 [N, 128] tensor")
+        _lib.check(self.lib.wab_policy_affine1(self.env._h, _ptr(features), features.shape[0], _ptr(self.packed), _ptr(self.bias),
+                                               float(noise_scale), float(slope), _ptr(counter), _ptr(out), self._stream()))
+        return out
+
+
 class Rollout:
     """N-environment rollout with every tensor resident on the device.
 
@@ -76,7 +109,8 @@ class Rollout:
     for small batches)."""
 
     def __init__(self, env: VecEnv, policy: Optional[Policy] = None, noise: bool = True, use_graph: bool = False,
-                 dtype: torch.dtype = torch.float32, fused_tail: Optional[bool] = None, track_reward: bool = False):
+                 dtype: torch.dtype = torch.float32, fused_tail: Optional[bool] = None, track_reward: bool = False,
+                 tc_first_layer: Optional[bool] = None):
         if not env.with_features:
             raise ValueError("Rollout needs VecEnv(features=True)")
         self.env, self.noise, self.dtype = env, noise, dtype
@@ -93,6 +127,12 @@ class Rollout:
         if self.fused_tail and dtype != torch.float32:
             raise ValueError("the fused policy tail is an fp32 kernel")
         self.heads = stacked_heads(self.policy) if self.fused_tail else None
+        # fp32: the first layer (input generation + 449 x 128 product + activation) is one tcgen05 kernel of this library
+        self.tc_first_layer = self.fused_tail if tc_first_layer is None else bool(tc_first_layer)
+        if self.tc_first_layer and not self.fused_tail:
+            raise ValueError("the tensor-core first layer belongs to the fp32 fused path")
+        self.affine1_tc = Affine1TC(env, self.policy) if self.tc_first_layer else None
+        self.h1 = torch.empty(env.num_envs, 128, dtype=torch.float32, device=env.device) if self.tc_first_layer else None
         env.reset()
         self.graph = None
         if use_graph:
@@ -110,12 +150,17 @@ class Rollout:
     @torch.no_grad()
     def _step_eager(self):
         env = self.env
-        # gym.spaces.flatten (actor_critic.py:188) + U[0,1)/100 input noise (:189) + cast, one kernel
-        env.flatten_features_noisy(env.last_features, self.flat, 0.01 if self.noise else 0.0, self.noise_ctr)
+        if self.tc_first_layer:
+            # flatten (actor_critic.py:188) + U[0,1)/100 noise (:189) + affine1 + leaky_relu (:88-90): one tcgen05 kernel
+            h = self.affine1_tc(env.last_features, self.h1, 0.01 if self.noise else 0.0, self.noise_ctr)
+        else:
+            # gym.spaces.flatten (actor_critic.py:188) + U[0,1)/100 input noise (:189) + cast, one kernel
+            env.flatten_features_noisy(env.last_features, self.flat, 0.01 if self.noise else 0.0, self.noise_ctr)
         self.noise_ctr += 1
         if self.fused_tail:
             p = self.policy
-            h = F.leaky_relu(p.affine1(self.flat))                                       # :88-90 (cuBLAS)
+            if not self.tc_first_layer:
+                h = F.leaky_relu(p.affine1(self.flat))                                   # :88-90 (cuBLAS)
             z3 = p.affine3(F.leaky_relu(p.affine2(h)))
             policy_tail(p, z3, self.heads, self.actions, value=self.values, counter=self.noise_ctr, seed=self.sample_seed)
         else:
@@ -127,6 +172,10 @@ class Rollout:
             self.reward_sum += reward.sum(dtype=torch.float64)
 
     def describe(self) -> str:
+        if self.tc_first_layer:
+            return ("wab_affine1_tc_kernel (flatten + noise + affine1 + leaky_relu: tcgen05, bf16 x 3 splits, fp32 accumulate) -> "
+                    "affine2, affine3 fp32 (cuBLAS) + leaky_relu -> wab_policy_tail_kernel (activation, clamp, both heads, softmax, "
+                    "Categorical sample) -> wab_step_kernel; one CUDA graph per step")
         if self.fused_tail:
             return ("wab_flatten_noisy_kernel (flatten + noise) -> affine1..3 fp32 (cuBLAS) + leaky_relu -> wab_policy_tail_kernel "
                     "(activation, clamp, both heads, softmax, Categorical sample) -> wab_step_kernel; one CUDA graph per step")
