@@ -218,6 +218,20 @@ int wab_policy_affine1_prepare(const float *d_weight, int32_t in_dim, void *d_pa
 int wab_policy_affine1(WabVec *h, const uint8_t *d_features, int64_t n_rows, const void *d_packed, const float *d_bias,
                        float noise_scale, float leaky_slope, const uint64_t *d_counter, float *d_out, void *stream);
 
+/* The whole trunk of the reference's Policy.forward (actor_critic.py:88-92) in the same tcgen05 kernel, fp32 accuracy:
+ * d_z3 f32[n_rows][128] = affine3(leaky_relu(affine2(leaky_relu(affine1(flatten(obs) + noise))))) — the PRE-activation
+ * output of affine3, which is what wab_policy_tail takes. The hidden activations never leave the SM: accumulators ->
+ * registers (bias, leaky-ReLU, three-way bf16 split) -> shared memory as the next layer's operand. d_packed1 / d_bias1 as
+ * for wab_policy_affine1; d_packed2 = wab_policy_linear_prepare(affine2.weight f32[150][128]), d_packed3 =
+ * wab_policy_linear_prepare(affine3.weight f32[128][150]) (wab_policy_linear_packed_bytes(n_out, n_in) bytes each,
+ * 16-byte aligned; once per weight update); hidden2 must be 150. */
+int64_t wab_policy_linear_packed_bytes(int32_t n_out, int32_t n_in);
+int wab_policy_linear_prepare(const float *d_weight, int32_t n_out, int32_t n_in, void *d_packed, void *stream);
+int wab_policy_trunk(WabVec *h, const uint8_t *d_features, int64_t n_rows, const void *d_packed1, const float *d_bias1,
+                     const void *d_packed2, const float *d_bias2, int32_t hidden2, const void *d_packed3,
+                     const float *d_bias3, float noise_scale, float leaky_slope, const uint64_t *d_counter, float *d_z3,
+                     void *stream);
+
 /* The tail of the reference's Policy.forward + select_action (actor_critic.py:84-97, :108-125) for n_rows rows in one
  * pass, fp32: d_z3 f32[n_rows][128] is the PRE-activation output of affine3; x = clamp(leaky_relu(z3), lo, hi);
  * logits = W[0..A) x + b, value = W[A] x + b[A] (d_w_heads f32[A + 1][128] = action_head.weight stacked on

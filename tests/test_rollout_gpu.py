@@ -116,21 +116,55 @@ def test_tensor_core_first_layer_matches_torch_fp32(n, noise):
     env.close()
 
 
+@pytest.mark.parametrize("noise", [0.0, 0.01])
+@pytest.mark.parametrize("n", [128, 1000, 4099])
+def test_tensor_core_trunk_matches_torch(n, noise):
+    """wab_policy_trunk (one tcgen05 kernel: input generation, affine1..3, the two hidden activations) against the
+    materialised input through the three ``nn.Linear`` layers of ``Policy`` (``actor_critic.py:59-61``, ``:88-92``) in
+    fp64, with the library's fp32 path beside it."""
+    from wab_gym_b200 import VecEnv
+    from wab_gym_b200.policy import PolicyTrunkTC
+    env = VecEnv(n, seed=6, features=True)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(n + 1)
+    for _ in range(30):
+        env.step(torch.randint(0, env.n_actions, (n,), dtype=torch.uint8, device="cuda", generator=g))
+    pol = _policy(env.n_actions, seed=4)
+    with torch.no_grad():
+        for lin in (pol.affine1, pol.affine2, pol.affine3):
+            lin.weight.mul_(2.0)
+    ctr = torch.full((1,), 9, dtype=torch.int64, device="cuda")
+    flat = torch.empty(n, env.flat_dim, dtype=torch.float32, device="cuda")
+    env.flatten_features_noisy(env.last_features, flat, noise, ctr)
+    got = torch.full((n, 128), float("nan"), device="cuda")
+    PolicyTrunkTC(env, pol)(env.last_features, got, noise, ctr)
+    with torch.no_grad():
+        d = pol.double()
+        want = d.affine3(F.leaky_relu(d.affine2(F.leaky_relu(d.affine1(flat.double()))))).float()
+        pol.float()
+        lib32 = pol.affine3(F.leaky_relu(pol.affine2(F.leaky_relu(pol.affine1(flat)))))
+    err, err32, scale = float((got - want).abs().max()), float((lib32 - want).abs().max()), float(want.abs().max())
+    assert torch.isfinite(got).all()
+    assert err <= 3e-6 * max(scale, 1.0), (err, err32, scale)
+    env.close()
+
+
 def test_rollout_with_tensor_core_first_layer_equals_library_first_layer():
     """Same seeds, same noise counter: the rollout with the tcgen05 first layer takes the same actions as the one that
     materialises the input and calls the library GEMM (fp32 differences of 1e-6 do not move a sampled action here)."""
     from wab_gym_b200 import VecEnv
     from wab_gym_b200.policy import Rollout
     acts = []
-    for tc in (False, True):
+    for tc in (False, True, None):                       # library GEMMs | tcgen05 first layer | tcgen05 trunk (the default)
         torch.manual_seed(0)
         env = VecEnv(2048, seed=9, features=True)
-        ro = Rollout(env, _policy(env.n_actions, seed=1), tc_first_layer=tc)
+        ro = Rollout(env, _policy(env.n_actions, seed=1), tc_first_layer=tc, tc_trunk=None if tc is None else False)
         seq = []
         for _ in range(12):
             ro.step()
             seq.append(ro.actions.clone())
         acts.append(torch.stack(seq))
         env.close()
-    same = (acts[0] == acts[1]).float().mean().item()
-    assert same > 0.999, same
+    for other in acts[1:]:
+        same = (acts[0] == other).float().mean().item()
+        assert same > 0.999, same

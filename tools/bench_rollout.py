@@ -24,11 +24,13 @@ def main():
     ap.add_argument("--graph", action="store_true")
     ap.add_argument("--bf16", action="store_true")
     ap.add_argument("--no-tc", action="store_true", help="first layer as flatten kernel + library GEMM instead of the tcgen05 kernel")
+    ap.add_argument("--no-trunk", action="store_true", help="tcgen05 first layer only; affine2 / affine3 as library GEMMs")
     args = ap.parse_args()
     torch.manual_seed(0)
     env = VecEnv(args.num_envs, seed=0, features=True)
     ro = Rollout(env, Policy(env.flat_dim, env.n_actions), use_graph=args.graph,
-                 dtype=torch.bfloat16 if args.bf16 else torch.float32, tc_first_layer=False if (args.no_tc or args.bf16) else None)
+                 dtype=torch.bfloat16 if args.bf16 else torch.float32, tc_first_layer=False if (args.no_tc or args.bf16) else None,
+                 tc_trunk=False if (args.no_tc or args.bf16 or args.no_trunk) else None)
     ro.run(args.warmup)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

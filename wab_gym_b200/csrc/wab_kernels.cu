@@ -1587,13 +1587,54 @@ int wab_policy_affine1(WabVec* h, const uint8_t* d_features, int64_t n_rows, con
     DeviceGuard guard(h->device);
     static bool attr_set[64] = {false};
     if (h->device < 64 && !attr_set[h->device]) {
-        WAB_CUDA(cudaFuncSetAttribute(wab_affine1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_TOTAL));
+        WAB_CUDA(cudaFuncSetAttribute(wab_affine1_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_TOTAL));
         attr_set[h->device] = true;
     }
     const unsigned grid = (unsigned)((n_rows + TC_TILE_M - 1) / TC_TILE_M);
-    wab_affine1_tc_kernel<<<grid, 256, TC_SMEM_TOTAL, (cudaStream_t)stream>>>(
+    wab_affine1_tc_kernel<false><<<grid, 256, TC_SMEM_TOTAL, (cudaStream_t)stream>>>(
         h->P, d_features, n_rows, (int)h->cfg.food_obs_scale + 1, reinterpret_cast<const uint4*>(d_packed), d_bias, noise_scale,
-        leaky_slope, reinterpret_cast<const unsigned long long*>(d_counter), d_out);
+        leaky_slope, reinterpret_cast<const unsigned long long*>(d_counter), d_out, TrunkWeights());
+    WAB_CUDA(cudaGetLastError());
+    return WAB_OK;
+}
+
+int64_t wab_policy_linear_packed_bytes(int32_t n_out, int32_t n_in) {
+    const int64_t n_pad = (n_out + 15) / 16 * 16, k_pad = (n_in + T2_KC - 1) / T2_KC * T2_KC;
+    return 3 * n_pad * k_pad * 2;
+}
+
+int wab_policy_linear_prepare(const float* d_weight, int32_t n_out, int32_t n_in, void* d_packed, void* stream) {
+    if (!d_weight || !d_packed) return fail(WAB_E_NULL, "null argument");
+    if (n_out < 1 || n_out > 256 || n_in < 1 || n_in > 512) return fail(WAB_E_UNSUPPORTED, "wab_policy_linear_prepare: at most 256 outputs and 512 inputs");
+    if (((uintptr_t)d_packed & 15u) != 0) return fail(WAB_E_CONFIG, "d_packed must be 16-byte aligned");
+    const int n_pad = (n_out + 15) / 16 * 16, k_pad = (n_in + T2_KC - 1) / T2_KC * T2_KC, total = n_pad * k_pad;
+    wab_linear_prepare_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_weight, n_out, n_in, n_pad, k_pad, reinterpret_cast<uint16_t*>(d_packed));
+    WAB_CUDA(cudaGetLastError());
+    return WAB_OK;
+}
+
+int wab_policy_trunk(WabVec* h, const uint8_t* d_features, int64_t n_rows, const void* d_packed1, const float* d_bias1,
+                     const void* d_packed2, const float* d_bias2, int32_t hidden2, const void* d_packed3, const float* d_bias3,
+                     float noise_scale, float leaky_slope, const uint64_t* d_counter, float* d_z3, void* stream) {
+    if (!h || !d_features || !d_packed1 || !d_bias1 || !d_packed2 || !d_bias2 || !d_packed3 || !d_bias3 || !d_z3) return fail(WAB_E_NULL, "null argument");
+    if (hidden2 != 150) return fail(WAB_E_UNSUPPORTED, "wab_policy_trunk is built for the reference's trunk 128 -> 150 -> 128 (actor_critic.py:59-61)");
+    if (n_rows <= 0) return WAB_OK;
+    if (((uintptr_t)d_z3 & 15u) != 0 || ((uintptr_t)d_packed1 & 15u) != 0 || ((uintptr_t)d_packed2 & 15u) != 0 || ((uintptr_t)d_packed3 & 15u) != 0 ||
+        ((uintptr_t)d_features & 3u) != 0)
+        return fail(WAB_E_CONFIG, "d_z3 and the packed weights must be 16-byte aligned, d_features 4-byte aligned");
+    if (wab_vec_flat_dim(h) > TC_CHUNKS * TC_KC) return fail(WAB_E_UNSUPPORTED, "wab_policy_trunk: the input is at most 512 columns wide");
+    DeviceGuard guard(h->device);
+    static bool attr_set[64] = {false};
+    if (h->device < 64 && !attr_set[h->device]) {
+        WAB_CUDA(cudaFuncSetAttribute(wab_affine1_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_TOTAL));
+        attr_set[h->device] = true;
+    }
+    TrunkWeights tw;
+    tw.w2 = reinterpret_cast<const uint4*>(d_packed2); tw.b2 = d_bias2; tw.w3 = reinterpret_cast<const uint4*>(d_packed3); tw.b3 = d_bias3; tw.n2 = hidden2;
+    const unsigned grid = (unsigned)((n_rows + TC_TILE_M - 1) / TC_TILE_M);
+    wab_affine1_tc_kernel<true><<<grid, 256, TC_SMEM_TOTAL, (cudaStream_t)stream>>>(
+        h->P, d_features, n_rows, (int)h->cfg.food_obs_scale + 1, reinterpret_cast<const uint4*>(d_packed1), d_bias1, noise_scale,
+        leaky_slope, reinterpret_cast<const unsigned long long*>(d_counter), d_z3, tw);
     WAB_CUDA(cudaGetLastError());
     return WAB_OK;
 }

@@ -42,23 +42,36 @@ __host__ __device__ inline int tc_column(int c, int kc, int e) {
     return 128 * (c >> 1) + 32 * s + j;
 }
 
-__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {   // matrix descriptor: start, LBO 128 B, SBO 1024 B, version 1, no swizzle
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46);
+// matrix descriptor: start address, LBO 128 B (core matrices adjacent in K), SBO = 8-row group stride (16 bytes x the chunk's K), version 1, no swizzle
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr, uint32_t sbo_bytes = 1024u) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
 }
 // instruction descriptor, kind::f16: D fp32 (bits 4-5 = 1), A and B bf16 (bits 7-9, 10-12 = 1), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_TILE_M >> 4) << 24);
+__host__ __device__ constexpr uint32_t tc_idesc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_TILE_M >> 4) << 24);
+}
+constexpr uint32_t TC_IDESC = tc_idesc(TC_N);
+constexpr int T2_KC = 32;                                  // layers 2 and 3: K columns per chunk
+constexpr int T2_A_PART = TC_TILE_M * T2_KC * 2;           // 8 KB: one part of a 128-row operand chunk
+constexpr int T2_B160_PART = 160 * T2_KC * 2;              // 10 KB: one part of a 160-row weight chunk
 
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(TC_IDESC), "r"(accumulate) : "memory");
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void tc_mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok = 0;
+    unsigned long long t0 = 0ull;
     for (uint32_t spins = 0; !ok; ++spins) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (spins > (1u << 26)) __trap();          // a wrong descriptor must fail loudly, never hang the device
+        if (!ok && (spins & 1023u) == 1023u) {     // a wrong descriptor or phase must fail loudly within a second, never hang the device
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0ull) t0 = now;
+            else if (now - t0 > 1000000000ull) __trap();
+        }
     }
 }
 // v = p0 + p1 + p2 exactly (three bf16 terms carry 24 mantissa bits)
@@ -97,6 +110,29 @@ __device__ __forceinline__ void tc_tmem_ld32(uint32_t taddr, uint32_t v[32]) {
                  : "r"(taddr) : "memory");
 }
 
+__device__ __forceinline__ void tc_tmem_ld16(uint32_t taddr, uint32_t v[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+}
+
+// W f32[n_out][n_in] (nn.Linear weight) -> bf16 [K chunk of 32][part][(n >> 3) * 256 + kcol * 64 + (n & 7) * 8 + e], n padded to
+// n_pad rows and K to k_pad columns with zeros: the operand chunks of layers 2 and 3
+__global__ void wab_linear_prepare_kernel(const float* __restrict__ w, int n_out, int n_in, int n_pad, int k_pad, uint16_t* __restrict__ packed) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;            // (n, k)
+    if (idx >= n_pad * k_pad) return;
+    const int n = idx / k_pad, k = idx - n * k_pad;
+    const float v = (n < n_out && k < n_in) ? w[(int64_t)n * n_in + k] : 0.f;
+    uint32_t p0, p1, p2;
+    tc_split3(v, p0, p1, p2);
+    const int chunk = k / T2_KC, kk = k - chunk * T2_KC, part = n_pad * T2_KC;
+    const int off = (n >> 3) * (T2_KC * 8) + (kk >> 3) * 64 + (n & 7) * 8 + (kk & 7);
+    packed[(chunk * 3 + 0) * part + off] = (uint16_t)p0;
+    packed[(chunk * 3 + 1) * part + off] = (uint16_t)p1;
+    packed[(chunk * 3 + 2) * part + off] = (uint16_t)p2;
+}
+
 // two fp32 -> one word of two bf16 (round to nearest even), `lo` in the low half
 __device__ __forceinline__ uint32_t tc_pack_bf16x2(float lo, float hi) {
     uint32_t d;
@@ -104,10 +140,20 @@ __device__ __forceinline__ uint32_t tc_pack_bf16x2(float lo, float hi) {
     return d;
 }
 
+// TRUNK = false: out = h1 f32[rows][128] = leaky_relu(affine1(x)). TRUNK = true: the whole trunk of Policy.forward
+// (actor_critic.py:88-92) without leaving the SM — h1 and h2 go from the accumulators through registers (bias, leaky-ReLU,
+// three-way bf16 split) straight back into shared memory as the next layer's A operand — and out = z3 f32[rows][128], the
+// PRE-activation output of affine3 (what wab_policy_tail takes).
+struct TrunkWeights {
+    const uint4* w2; const float* b2;      // affine2 128 -> 150, packed by wab_policy_linear_prepare (N padded to 160)
+    const uint4* w3; const float* b3;      // affine3 150 -> 128 (K padded to 160)
+    int n2;                                // 150
+};
+template <bool TRUNK>
 __global__ void __launch_bounds__(256, 2)
 wab_affine1_tc_kernel(const __grid_constant__ Params P, const uint8_t* __restrict__ features, int64_t rows, int food_dim,
                       const uint4* __restrict__ wpacked, const float* __restrict__ bias, float noise_scale, float slope,
-                      const unsigned long long* __restrict__ d_counter, float* __restrict__ out) {
+                      const unsigned long long* __restrict__ d_counter, float* __restrict__ out, const TrunkWeights tw) {
     extern __shared__ __align__(1024) uint8_t tc_smem[];
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -230,42 +276,149 @@ wab_affine1_tc_kernel(const __grid_constant__ Params P, const uint8_t* __restric
                 const uint64_t b0 = tc_smem_desc(s_b + ko), b1 = tc_smem_desc(s_b + TC_PART_BYTES + ko), b2 = tc_smem_desc(s_b + 2 * TC_PART_BYTES + ko);
                 // the tensor core's fp32 accumulation truncates: the leading term o W0 gets an accumulator of its own (one add per
                 // K step), the five corrections — 2^-8 of it and smaller — share the second; the epilogue adds the two
-                tc_mma(tmem, a0, b0, (c | ks) ? 1u : 0u);
-                tc_mma(tmem + 128u, a0, b1, (c | ks) ? 1u : 0u);
-                tc_mma(tmem + 128u, a1, b0, 1u);
-                tc_mma(tmem + 128u, a0, b2, 1u);
-                tc_mma(tmem + 128u, a1, b1, 1u);
-                tc_mma(tmem + 128u, a2, b0, 1u);
+                tc_mma(tmem, a0, b0, TC_IDESC, (c | ks) ? 1u : 0u);
+                tc_mma(tmem + 128u, a0, b1, TC_IDESC, (c | ks) ? 1u : 0u);
+                tc_mma(tmem + 128u, a1, b0, TC_IDESC, 1u);
+                tc_mma(tmem + 128u, a0, b2, TC_IDESC, 1u);
+                tc_mma(tmem + 128u, a1, b1, TC_IDESC, 1u);
+                tc_mma(tmem + 128u, a2, b0, TC_IDESC, 1u);
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(s_bar) : "memory");
         }
     }
-    tc_mbar_wait(s_bar, parity);
+    tc_mbar_wait(s_bar, parity); parity ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    // ---- epilogue: warp w reads lanes 32 (w & 3) .. + 32 (its rows), columns 64 (w >> 2) .. + 64
+    // ---- epilogue of layer 1: warp w reads lanes 32 (w & 3) .. + 32 (its rows = r), columns 64 h .. + 64 of both accumulators
+    const int q = warp & 3;
+    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+    float h1[64];
     {
-        const int q = warp & 3, ch = warp >> 2;
-        const int64_t orow = row0 + q * 32 + lane;
+        uint32_t v[32], u[32];
 #pragma unroll
         for (int part = 0; part < 2; ++part) {
-            const int col0 = ch * 64 + part * 32;
-            uint32_t v[32], u[32];
-            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
-            tc_tmem_ld32(taddr, v);
-            tc_tmem_ld32(taddr + 128u, u);
+            const int col0 = h * 64 + part * 32;
+            tc_tmem_ld32(tlane + (uint32_t)col0, v);
+            tc_tmem_ld32(tlane + 128u + (uint32_t)col0, u);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (orow < rows) {
-                float4* dst = reinterpret_cast<float4*>(out + orow * TC_N + col0);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float4 o;
-                    float t;
-                    t = (__uint_as_float(v[4 * i + 0]) + __uint_as_float(u[4 * i + 0])) + bias[col0 + 4 * i + 0]; o.x = t > 0.f ? t : t * slope;
-                    t = (__uint_as_float(v[4 * i + 1]) + __uint_as_float(u[4 * i + 1])) + bias[col0 + 4 * i + 1]; o.y = t > 0.f ? t : t * slope;
-                    t = (__uint_as_float(v[4 * i + 2]) + __uint_as_float(u[4 * i + 2])) + bias[col0 + 4 * i + 2]; o.z = t > 0.f ? t : t * slope;
-                    t = (__uint_as_float(v[4 * i + 3]) + __uint_as_float(u[4 * i + 3])) + bias[col0 + 4 * i + 3]; o.w = t > 0.f ? t : t * slope;
-                    dst[i] = o;
+            for (int i = 0; i < 32; ++i) {
+                const float t = (__uint_as_float(v[i]) + __uint_as_float(u[i])) + bias[col0 + i];
+                h1[part * 32 + i] = t > 0.f ? t : t * slope;
+            }
+        }
+    }
+    if (!TRUNK) {
+        if (row < rows) {
+            float4* dst = reinterpret_cast<float4*>(out + row * TC_N + h * 64);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dst[i] = make_float4(h1[4 * i], h1[4 * i + 1], h1[4 * i + 2], h1[4 * i + 3]);
+        }
+    } else {
+        // ---- layers 2 and 3: K chunks of 32 (operand parts of 8 KB / 10 KB), one accumulator per layer (48 and 60 adds)
+        const uint32_t s_a2 = s_base, s_b2 = s_base + 3 * T2_A_PART;
+        const uint32_t a2_row = (uint32_t)((r >> 3) * 512 + (r & 7) * 16);
+        auto put_core = [&](int kcol, const float* v8) {                 // 8 consecutive K values of this row -> core column kcol, 3 parts
+            uint32_t p0[4], p1[4], p2[4];
+#pragma unroll
+            for (int e2 = 0; e2 < 4; ++e2) {
+                const float a = v8[2 * e2], b = v8[2 * e2 + 1];
+                p0[e2] = tc_pack_bf16x2(a, b);
+                const float ra = a - __uint_as_float(p0[e2] << 16), rb = b - __uint_as_float(p0[e2] & 0xFFFF0000u);
+                p1[e2] = tc_pack_bf16x2(ra, rb);
+                p2[e2] = tc_pack_bf16x2(ra - __uint_as_float(p1[e2] << 16), rb - __uint_as_float(p1[e2] & 0xFFFF0000u));
+            }
+            const uint32_t dst = s_a2 + a2_row + (uint32_t)kcol * 128u;
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(dst), "r"(p0[0]), "r"(p0[1]), "r"(p0[2]), "r"(p0[3]) : "memory");
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(dst + T2_A_PART), "r"(p1[0]), "r"(p1[1]), "r"(p1[2]), "r"(p1[3]) : "memory");
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(dst + 2 * T2_A_PART), "r"(p2[0]), "r"(p2[1]), "r"(p2[2]), "r"(p2[3]) : "memory");
+        };
+        auto copy_b = [&](const uint4* src, int n16) {                   // the chunk's three weight parts, already in operand layout
+#pragma unroll 4
+            for (int k = tid; k < n16; k += 256) {
+                const uint4 v = src[k];
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(s_b2 + (uint32_t)k * 16u), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+            }
+        };
+        auto issue = [&](uint32_t b_part, uint32_t idesc, bool first) {  // one chunk: 2 K steps x 6 products, then commit
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    const uint32_t ko = (uint32_t)ks * 256u;
+                    const uint64_t a0 = tc_smem_desc(s_a2 + ko, 512u), a1 = tc_smem_desc(s_a2 + T2_A_PART + ko, 512u), a2 = tc_smem_desc(s_a2 + 2 * T2_A_PART + ko, 512u);
+                    const uint64_t b0 = tc_smem_desc(s_b2 + ko, 512u), b1 = tc_smem_desc(s_b2 + b_part + ko, 512u), b2 = tc_smem_desc(s_b2 + 2 * b_part + ko, 512u);
+                    tc_mma(tmem, a2, b0, idesc, (first && ks == 0) ? 0u : 1u);     // smallest terms first
+                    tc_mma(tmem, a1, b1, idesc, 1u);
+                    tc_mma(tmem, a0, b2, idesc, 1u);
+                    tc_mma(tmem, a1, b0, idesc, 1u);
+                    tc_mma(tmem, a0, b1, idesc, 1u);
+                    tc_mma(tmem, a0, b0, idesc, 1u);
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(s_bar) : "memory");
+            }
+        };
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();                                                  // every thread has read its layer-1 accumulators
+        // ---- layer 2: h1 (K = 128: this thread holds columns 64 h .. + 64) x W2 (N = 150 padded to 160)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j > 0) { tc_mbar_wait(s_bar, parity); parity ^= 1u; }
+            if (h == (j >> 1)) {
+#pragma unroll
+                for (int kcol = 0; kcol < 4; ++kcol) put_core(kcol, h1 + 32 * (j & 1) + 8 * kcol);
+            }
+            copy_b(tw.w2 + (size_t)j * (3 * T2_B160_PART / 16), 3 * T2_B160_PART / 16);
+            issue(T2_B160_PART, tc_idesc(160), j == 0);
+        }
+        tc_mbar_wait(s_bar, parity); parity ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float h2[80];                                                     // columns 80 h .. + 80 of this row
+        {
+            uint32_t v[16];
+#pragma unroll
+            for (int part = 0; part < 5; ++part) {
+                const int col0 = h * 80 + part * 16;
+                tc_tmem_ld16(tlane + (uint32_t)col0, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float t = __uint_as_float(v[i]) + (col0 + i < tw.n2 ? tw.b2[col0 + i] : 0.f);
+                    h2[part * 16 + i] = t > 0.f ? t : t * slope;
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        // ---- layer 3: h2 (K = 160: core columns 10 h .. + 10 are this thread's) x W3 (N = 128)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            if (j > 0) { tc_mbar_wait(s_bar, parity); parity ^= 1u; }
+#pragma unroll
+            for (int kcol = 0; kcol < 4; ++kcol) {
+                const int g = 4 * j + kcol;                               // core column of the whole K
+                if (h == (g >= 10 ? 1 : 0)) put_core(kcol, h2 + 8 * (g >= 10 ? g - 10 : g));
+            }
+            copy_b(tw.w3 + (size_t)j * (3 * T2_A_PART / 16), 3 * T2_A_PART / 16);
+            issue(T2_A_PART, tc_idesc(128), j == 0);
+        }
+        tc_mbar_wait(s_bar, parity); parity ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        {
+            uint32_t v[32];
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+                const int col0 = h * 64 + part * 32;
+                tc_tmem_ld32(tlane + (uint32_t)col0, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < rows) {
+                    float4* dst = reinterpret_cast<float4*>(out + row * TC_N + col0);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        dst[i] = make_float4(__uint_as_float(v[4 * i]) + tw.b3[col0 + 4 * i], __uint_as_float(v[4 * i + 1]) + tw.b3[col0 + 4 * i + 1],
+                                             __uint_as_float(v[4 * i + 2]) + tw.b3[col0 + 4 * i + 2], __uint_as_float(v[4 * i + 3]) + tw.b3[col0 + 4 * i + 3]);
                 }
             }
         }

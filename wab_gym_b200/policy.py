@@ -101,6 +101,39 @@ class Affine1TC:
         return out
 
 
+class PolicyTrunkTC(Affine1TC):
+    """The whole trunk ``affine3(leaky_relu(affine2(leaky_relu(affine1(flatten(obs) + noise)))))`` (``actor_critic.py:88-92``)
+    as ONE tcgen05 kernel (``wab_policy_trunk``): returns ``z3`` f32[N, 128], the pre-activation output of ``affine3`` that
+    ``policy_tail`` takes. The hidden activations never leave the SM."""
+
+    def __init__(self, env: VecEnv, policy: "Policy"):
+        if (policy.affine2.in_features, policy.affine2.out_features, policy.affine3.in_features, policy.affine3.out_features) != (128, 150, 150, 128):
+            raise ValueError("PolicyTrunkTC is built for the reference's trunk: 128 -> 150 -> 128")
+        lib = _lib.load()
+        self.packed2 = torch.empty(int(lib.wab_policy_linear_packed_bytes(150, 128)), dtype=torch.uint8, device=env.device)
+        self.packed3 = torch.empty(int(lib.wab_policy_linear_packed_bytes(128, 150)), dtype=torch.uint8, device=env.device)
+        self.bias2 = self.bias3 = None
+        super().__init__(env, policy)
+
+    @torch.no_grad()
+    def refresh(self):
+        super().refresh()
+        p = self.policy
+        w2, w3 = p.affine2.weight.detach().float().contiguous(), p.affine3.weight.detach().float().contiguous()
+        self.bias2, self.bias3 = p.affine2.bias.detach().float().contiguous(), p.affine3.bias.detach().float().contiguous()
+        _lib.check(self.lib.wab_policy_linear_prepare(_ptr(w2), 150, 128, _ptr(self.packed2), self._stream()))
+        _lib.check(self.lib.wab_policy_linear_prepare(_ptr(w3), 128, 150, _ptr(self.packed3), self._stream()))
+
+    def __call__(self, features: torch.Tensor, out: torch.Tensor, noise_scale: float = 0.01,
+                 counter: Optional[torch.Tensor] = None, slope: float = 0.01) -> torch.Tensor:
+        if out.dtype != torch.float32 or not out.is_contiguous() or tuple(out.shape) != (features.shape[0], 128):
+            raise ValueError("out must be a contiguous float32 [N, 128] tensor")
+        _lib.check(self.lib.wab_policy_trunk(self.env._h, _ptr(features), features.shape[0], _ptr(self.packed), _ptr(self.bias),
+                                             _ptr(self.packed2), _ptr(self.bias2), 150, _ptr(self.packed3), _ptr(self.bias3),
+                                             float(noise_scale), float(slope), _ptr(counter), _ptr(out), self._stream()))
+        return out
+
+
 class Rollout:
     """N-environment rollout with every tensor resident on the device.
 
@@ -110,7 +143,7 @@ class Rollout:
 
     def __init__(self, env: VecEnv, policy: Optional[Policy] = None, noise: bool = True, use_graph: bool = False,
                  dtype: torch.dtype = torch.float32, fused_tail: Optional[bool] = None, track_reward: bool = False,
-                 tc_first_layer: Optional[bool] = None):
+                 tc_first_layer: Optional[bool] = None, tc_trunk: Optional[bool] = None):
         if not env.with_features:
             raise ValueError("Rollout needs VecEnv(features=True)")
         self.env, self.noise, self.dtype = env, noise, dtype
@@ -131,7 +164,11 @@ class Rollout:
         self.tc_first_layer = self.fused_tail if tc_first_layer is None else bool(tc_first_layer)
         if self.tc_first_layer and not self.fused_tail:
             raise ValueError("the tensor-core first layer belongs to the fp32 fused path")
-        self.affine1_tc = Affine1TC(env, self.policy) if self.tc_first_layer else None
+        # ... and so is the whole trunk (the default): features -> z3 without the hidden activations leaving the SM
+        self.tc_trunk = self.tc_first_layer if tc_trunk is None else bool(tc_trunk)
+        if self.tc_trunk and not self.tc_first_layer:
+            raise ValueError("the tensor-core trunk includes the tensor-core first layer")
+        self.affine1_tc = (PolicyTrunkTC if self.tc_trunk else Affine1TC)(env, self.policy) if self.tc_first_layer else None
         self.h1 = torch.empty(env.num_envs, 128, dtype=torch.float32, device=env.device) if self.tc_first_layer else None
         env.reset()
         self.graph = None
@@ -161,7 +198,7 @@ class Rollout:
             p = self.policy
             if not self.tc_first_layer:
                 h = F.leaky_relu(p.affine1(self.flat))                                   # :88-90 (cuBLAS)
-            z3 = p.affine3(F.leaky_relu(p.affine2(h)))
+            z3 = h if self.tc_trunk else p.affine3(F.leaky_relu(p.affine2(h)))           # the trunk kernel already returned z3
             policy_tail(p, z3, self.heads, self.actions, value=self.values, counter=self.noise_ctr, seed=self.sample_seed)
         else:
             probs, value = self.policy(self.flat)
@@ -172,6 +209,10 @@ class Rollout:
             self.reward_sum += reward.sum(dtype=torch.float64)
 
     def describe(self) -> str:
+        if self.tc_trunk:
+            return ("wab_affine1_tc_kernel<trunk> (flatten + noise + affine1..3 + leaky_relu: one tcgen05 kernel, bf16 x 3 splits, fp32 "
+                    "accumulate, activations stay on the SM) -> wab_policy_tail_kernel (activation, clamp, both heads, softmax, "
+                    "Categorical sample) -> wab_step_kernel; one CUDA graph per step")
         if self.tc_first_layer:
             return ("wab_affine1_tc_kernel (flatten + noise + affine1 + leaky_relu: tcgen05, bf16 x 3 splits, fp32 accumulate) -> "
                     "affine2, affine3 fp32 (cuBLAS) + leaky_relu -> wab_policy_tail_kernel (activation, clamp, both heads, softmax, "
