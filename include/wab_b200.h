@@ -232,6 +232,17 @@ int wab_policy_trunk(WabVec *h, const uint8_t *d_features, int64_t n_rows, const
                      const float *d_bias3, float noise_scale, float leaky_slope, const uint64_t *d_counter, float *d_z3,
                      void *stream);
 
+/* Policy.forward + select_action (actor_critic.py:84-97, :108-125) for n_rows environments as ONE kernel: wab_policy_trunk
+ * followed, in the same launch, by what wab_policy_tail does (x = clamp(leaky_relu(z3), lo, hi), both heads, softmax, one
+ * action per row by inverse CDF on a uniform keyed by (sample_seed, row, *d_counter)). Arguments as for those two calls;
+ * d_value, d_probs, d_logp and d_z3 may be NULL. */
+int wab_policy_forward(WabVec *h, const uint8_t *d_features, int64_t n_rows, const void *d_packed1, const float *d_bias1,
+                       const void *d_packed2, const float *d_bias2, int32_t hidden2, const void *d_packed3,
+                       const float *d_bias3, const float *d_w_heads, const float *d_b_heads, int32_t n_actions,
+                       float noise_scale, float leaky_slope, float clamp_lo, float clamp_hi, uint64_t sample_seed,
+                       const uint64_t *d_counter, uint8_t *d_actions, float *d_value, float *d_probs, float *d_logp,
+                       float *d_z3, void *stream);
+
 /* The tail of the reference's Policy.forward + select_action (actor_critic.py:84-97, :108-125) for n_rows rows in one
  * pass, fp32: d_z3 f32[n_rows][128] is the PRE-activation output of affine3; x = clamp(leaky_relu(z3), lo, hi);
  * logits = W[0..A) x + b, value = W[A] x + b[A] (d_w_heads f32[A + 1][128] = action_head.weight stacked on

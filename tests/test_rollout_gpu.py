@@ -69,7 +69,7 @@ def test_rollout_runs_on_the_fused_tail(use_graph):
     torch.manual_seed(0)
     env = VecEnv(2048, seed=3, features=True)
     ro = Rollout(env, Policy(env.flat_dim, env.n_actions), use_graph=use_graph)
-    assert ro.fused_tail and "wab_policy_tail_kernel" in ro.describe()
+    assert ro.fused_tail and ro.tc_trunk and "wab_affine1_tc_kernel<2>" in ro.describe()     # the default fp32 path: one policy kernel
     before = env.stats()["steps"]
     ro.run(120)
     torch.cuda.synchronize()
@@ -146,6 +146,39 @@ def test_tensor_core_trunk_matches_torch(n, noise):
     err, err32, scale = float((got - want).abs().max()), float((lib32 - want).abs().max()), float(want.abs().max())
     assert torch.isfinite(got).all()
     assert err <= 3e-6 * max(scale, 1.0), (err, err32, scale)
+    env.close()
+
+
+def test_policy_forward_in_one_launch_equals_trunk_then_tail():
+    """wab_policy_forward (trunk + tail in one launch) against wab_policy_trunk followed by wab_policy_tail: same z3, same
+    value to fp32 rounding of a 128-term sum, same sampled action except where the uniform lands within that rounding of a
+    CDF step."""
+    from wab_gym_b200 import VecEnv
+    from wab_gym_b200.policy import PolicyTrunkTC, policy_tail, stacked_heads
+    n = 5000
+    env = VecEnv(n, seed=8, features=True)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    for _ in range(25):
+        env.step(torch.randint(0, env.n_actions, (n,), dtype=torch.uint8, device="cuda", generator=g))
+    pol = _policy(env.n_actions, seed=5)
+    with torch.no_grad():
+        pol.action_head.weight.mul_(6.0)
+    heads = stacked_heads(pol)
+    trunk = PolicyTrunkTC(env, pol)
+    ctr = torch.full((1,), 4, dtype=torch.int64, device="cuda")
+    z3 = torch.empty(n, 128, device="cuda")
+    trunk(env.last_features, z3, 0.01, ctr)
+    a_ref = torch.empty(n, dtype=torch.uint8, device="cuda")
+    v_ref, lp_ref, p_ref = torch.empty(n, device="cuda"), torch.empty(n, device="cuda"), torch.empty(n, env.n_actions, device="cuda")
+    policy_tail(pol, z3, heads, a_ref, value=v_ref, probs=p_ref, logp=lp_ref, counter=ctr, seed=21)
+    a, v, lp, p = torch.full_like(a_ref, 255), torch.empty_like(v_ref), torch.empty_like(lp_ref), torch.empty_like(p_ref)
+    z3b = torch.empty_like(z3)
+    trunk.forward_sample(env.last_features, heads, a, value=v, probs=p, logp=lp, noise_scale=0.01, counter=ctr, seed=21, z3=z3b)
+    assert torch.equal(z3b, z3)
+    assert torch.allclose(v, v_ref, rtol=1e-5, atol=1e-5) and torch.allclose(p, p_ref, rtol=1e-5, atol=1e-6)
+    same = (a == a_ref)
+    assert same.float().mean().item() > 0.999 and torch.allclose(lp[same], lp_ref[same], rtol=1e-5, atol=1e-5)
     env.close()
 
 

@@ -18,7 +18,7 @@ EXPORTS = [
     "wab_vec_reset_host", "wab_vec_stats", "wab_vec_stats_device", "wab_vec_export_state", "wab_vec_num_envs", "wab_vec_lanes_per_env", "wab_vec_kernel_kind",
     "wab_vec_destroy", "wab_philox_device", "wab_vec_bind_features", "wab_pragmatic_features",
     "wab_vec_flatten_features", "wab_vec_flatten_features_noisy", "wab_sample_categorical", "wab_policy_tail", "wab_vec_enable_ego", "wab_vec_ego_proximities", "wab_vec_flat_dim", "wab_vec_host_block_layout", "wab_vec_step_host_packed",
-    "wab_policy_affine1_packed_bytes", "wab_policy_affine1_prepare", "wab_policy_affine1", "wab_policy_linear_packed_bytes", "wab_policy_linear_prepare", "wab_policy_trunk", "wab2_create", "wab2_kernel_kind", "wab2_output_layout", "wab2_reset", "wab2_turn", "wab2_export_state", "wab2_import_state", "wab2_destroy", "wab_last_error", "wab_abi_version",
+    "wab_policy_affine1_packed_bytes", "wab_policy_affine1_prepare", "wab_policy_affine1", "wab_policy_linear_packed_bytes", "wab_policy_linear_prepare", "wab_policy_trunk", "wab_policy_forward", "wab2_create", "wab2_kernel_kind", "wab2_output_layout", "wab2_reset", "wab2_turn", "wab2_export_state", "wab2_import_state", "wab2_destroy", "wab_last_error", "wab_abi_version",
 ]
 
 
@@ -87,6 +87,8 @@ def load():
     L.wab_policy_linear_packed_bytes.restype = i64
     L.wab_policy_linear_prepare.argtypes = [vp, i32, i32, vp, vp]
     L.wab_policy_trunk.argtypes = [vp, vp, i64, vp, vp, vp, vp, i32, vp, vp, ctypes.c_float, ctypes.c_float, vp, vp, vp]
+    L.wab_policy_forward.argtypes = [vp, vp, i64, vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, ctypes.c_float, ctypes.c_float,
+                                     ctypes.c_float, ctypes.c_float, u64, vp, vp, vp, vp, vp, vp, vp]
     L.wab2_create.argtypes = [vp, i64, u64, u64, i32, ctypes.POINTER(vp)]
     L.wab2_reset.argtypes = [vp, vp]
     L.wab2_turn.argtypes = [vp] * 7

@@ -1587,11 +1587,11 @@ int wab_policy_affine1(WabVec* h, const uint8_t* d_features, int64_t n_rows, con
     DeviceGuard guard(h->device);
     static bool attr_set[64] = {false};
     if (h->device < 64 && !attr_set[h->device]) {
-        WAB_CUDA(cudaFuncSetAttribute(wab_affine1_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_TOTAL));
+        WAB_CUDA(cudaFuncSetAttribute(wab_affine1_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_TOTAL));
         attr_set[h->device] = true;
     }
     const unsigned grid = (unsigned)((n_rows + TC_TILE_M - 1) / TC_TILE_M);
-    wab_affine1_tc_kernel<false><<<grid, 256, TC_SMEM_TOTAL, (cudaStream_t)stream>>>(
+    wab_affine1_tc_kernel<0><<<grid, 256, TC_SMEM_TOTAL, (cudaStream_t)stream>>>(
         h->P, d_features, n_rows, (int)h->cfg.food_obs_scale + 1, reinterpret_cast<const uint4*>(d_packed), d_bias, noise_scale,
         leaky_slope, reinterpret_cast<const unsigned long long*>(d_counter), d_out, TrunkWeights());
     WAB_CUDA(cudaGetLastError());
@@ -1613,10 +1613,11 @@ int wab_policy_linear_prepare(const float* d_weight, int32_t n_out, int32_t n_in
     return WAB_OK;
 }
 
-int wab_policy_trunk(WabVec* h, const uint8_t* d_features, int64_t n_rows, const void* d_packed1, const float* d_bias1,
-                     const void* d_packed2, const float* d_bias2, int32_t hidden2, const void* d_packed3, const float* d_bias3,
-                     float noise_scale, float leaky_slope, const uint64_t* d_counter, float* d_z3, void* stream) {
-    if (!h || !d_features || !d_packed1 || !d_bias1 || !d_packed2 || !d_bias2 || !d_packed3 || !d_bias3 || !d_z3) return fail(WAB_E_NULL, "null argument");
+static int policy_trunk_launch(WabVec* h, const uint8_t* d_features, int64_t n_rows, const void* d_packed1, const float* d_bias1,
+                               const void* d_packed2, const float* d_bias2, int32_t hidden2, const void* d_packed3, const float* d_bias3,
+                               float noise_scale, float leaky_slope, const uint64_t* d_counter, float* d_z3, void* stream,
+                               const TrunkWeights* tail) {
+    if (!h || !d_features || !d_packed1 || !d_bias1 || !d_packed2 || !d_bias2 || !d_packed3 || !d_bias3 || (!d_z3 && !tail)) return fail(WAB_E_NULL, "null argument");
     if (hidden2 != 150) return fail(WAB_E_UNSUPPORTED, "wab_policy_trunk is built for the reference's trunk 128 -> 150 -> 128 (actor_critic.py:59-61)");
     if (n_rows <= 0) return WAB_OK;
     if (((uintptr_t)d_z3 & 15u) != 0 || ((uintptr_t)d_packed1 & 15u) != 0 || ((uintptr_t)d_packed2 & 15u) != 0 || ((uintptr_t)d_packed3 & 15u) != 0 ||
@@ -1626,17 +1627,49 @@ int wab_policy_trunk(WabVec* h, const uint8_t* d_features, int64_t n_rows, const
     DeviceGuard guard(h->device);
     static bool attr_set[64] = {false};
     if (h->device < 64 && !attr_set[h->device]) {
-        WAB_CUDA(cudaFuncSetAttribute(wab_affine1_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_TOTAL));
+        WAB_CUDA(cudaFuncSetAttribute(wab_affine1_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_TOTAL));
+        WAB_CUDA(cudaFuncSetAttribute(wab_affine1_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_TOTAL));
         attr_set[h->device] = true;
     }
     TrunkWeights tw;
+    if (tail) tw = *tail; else memset(&tw, 0, sizeof(tw));
     tw.w2 = reinterpret_cast<const uint4*>(d_packed2); tw.b2 = d_bias2; tw.w3 = reinterpret_cast<const uint4*>(d_packed3); tw.b3 = d_bias3; tw.n2 = hidden2;
     const unsigned grid = (unsigned)((n_rows + TC_TILE_M - 1) / TC_TILE_M);
-    wab_affine1_tc_kernel<true><<<grid, 256, TC_SMEM_TOTAL, (cudaStream_t)stream>>>(
-        h->P, d_features, n_rows, (int)h->cfg.food_obs_scale + 1, reinterpret_cast<const uint4*>(d_packed1), d_bias1, noise_scale,
-        leaky_slope, reinterpret_cast<const unsigned long long*>(d_counter), d_z3, tw);
+    if (tail)
+        wab_affine1_tc_kernel<2><<<grid, 256, TC_SMEM_TOTAL, (cudaStream_t)stream>>>(
+            h->P, d_features, n_rows, (int)h->cfg.food_obs_scale + 1, reinterpret_cast<const uint4*>(d_packed1), d_bias1, noise_scale,
+            leaky_slope, reinterpret_cast<const unsigned long long*>(d_counter), d_z3, tw);
+    else
+        wab_affine1_tc_kernel<1><<<grid, 256, TC_SMEM_TOTAL, (cudaStream_t)stream>>>(
+            h->P, d_features, n_rows, (int)h->cfg.food_obs_scale + 1, reinterpret_cast<const uint4*>(d_packed1), d_bias1, noise_scale,
+            leaky_slope, reinterpret_cast<const unsigned long long*>(d_counter), d_z3, tw);
     WAB_CUDA(cudaGetLastError());
     return WAB_OK;
+}
+
+int wab_policy_trunk(WabVec* h, const uint8_t* d_features, int64_t n_rows, const void* d_packed1, const float* d_bias1,
+                     const void* d_packed2, const float* d_bias2, int32_t hidden2, const void* d_packed3, const float* d_bias3,
+                     float noise_scale, float leaky_slope, const uint64_t* d_counter, float* d_z3, void* stream) {
+    if (!d_z3) return fail(WAB_E_NULL, "null argument");
+    return policy_trunk_launch(h, d_features, n_rows, d_packed1, d_bias1, d_packed2, d_bias2, hidden2, d_packed3, d_bias3, noise_scale,
+                               leaky_slope, d_counter, d_z3, stream, nullptr);
+}
+
+int wab_policy_forward(WabVec* h, const uint8_t* d_features, int64_t n_rows, const void* d_packed1, const float* d_bias1,
+                       const void* d_packed2, const float* d_bias2, int32_t hidden2, const void* d_packed3, const float* d_bias3,
+                       const float* d_w_heads, const float* d_b_heads, int32_t n_actions, float noise_scale, float leaky_slope,
+                       float clamp_lo, float clamp_hi, uint64_t sample_seed, const uint64_t* d_counter, uint8_t* d_actions,
+                       float* d_value, float* d_probs, float* d_logp, float* d_z3, void* stream) {
+    if (!d_w_heads || !d_b_heads || !d_actions) return fail(WAB_E_NULL, "null argument");
+    if (n_actions < 1 || n_actions > 8) return fail(WAB_E_CONFIG, "n_actions must be in [1, 8]");
+    TrunkWeights tw;
+    memset(&tw, 0, sizeof(tw));
+    uint32_t k0 = (uint32_t)sample_seed, k1 = (uint32_t)(sample_seed >> 32);
+    for (int r = 0; r < 10; ++r) { tw.rk0[r] = k0; tw.rk1[r] = k1; k0 += PHILOX_W0; k1 += PHILOX_W1; }
+    tw.w_heads = d_w_heads; tw.b_heads = d_b_heads; tw.n_actions = n_actions; tw.clamp_lo = clamp_lo; tw.clamp_hi = clamp_hi;
+    tw.actions = d_actions; tw.value = d_value; tw.probs = d_probs; tw.logp = d_logp;
+    return policy_trunk_launch(h, d_features, n_rows, d_packed1, d_bias1, d_packed2, d_bias2, hidden2, d_packed3, d_bias3, noise_scale,
+                               leaky_slope, d_counter, d_z3, stream, &tw);
 }
 
 int wab_policy_tail(const float* d_z3, int32_t hidden, const float* d_w_heads, const float* d_b_heads, int64_t n_rows,

@@ -148,8 +148,14 @@ struct TrunkWeights {
     const uint4* w2; const float* b2;      // affine2 128 -> 150, packed by wab_policy_linear_prepare (N padded to 160)
     const uint4* w3; const float* b3;      // affine3 150 -> 128 (K padded to 160)
     int n2;                                // 150
+    // MODE 2 only — the tail of Policy.forward + select_action (actor_critic.py:92-97, :108-125), as wab_policy_tail_kernel
+    uint32_t rk0[10], rk1[10];             // Philox round keys of the sampling seed
+    const float* w_heads; const float* b_heads;   // f32[A + 1][128], f32[A + 1]: action_head stacked on value_head
+    int n_actions; float clamp_lo, clamp_hi;
+    uint8_t* actions; float* value; float* probs; float* logp;
 };
-template <bool TRUNK>
+// MODE 0: first layer only; 1: the trunk (out = z3); 2: trunk + tail (clamp, both heads, softmax, Categorical sample; out = z3 or null)
+template <int MODE>
 __global__ void __launch_bounds__(256, 2)
 wab_affine1_tc_kernel(const __grid_constant__ Params P, const uint8_t* __restrict__ features, int64_t rows, int food_dim,
                       const uint4* __restrict__ wpacked, const float* __restrict__ bias, float noise_scale, float slope,
@@ -308,7 +314,7 @@ wab_affine1_tc_kernel(const __grid_constant__ Params P, const uint8_t* __restric
             }
         }
     }
-    if (!TRUNK) {
+    if (MODE == 0) {
         if (row < rows) {
             float4* dst = reinterpret_cast<float4*>(out + row * TC_N + h * 64);
 #pragma unroll
@@ -406,6 +412,7 @@ wab_affine1_tc_kernel(const __grid_constant__ Params P, const uint8_t* __restric
         }
         tc_mbar_wait(s_bar, parity); parity ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float z3[64];                                                     // columns 64 h .. + 64 of this row
         {
             uint32_t v[32];
 #pragma unroll
@@ -413,12 +420,74 @@ wab_affine1_tc_kernel(const __grid_constant__ Params P, const uint8_t* __restric
                 const int col0 = h * 64 + part * 32;
                 tc_tmem_ld32(tlane + (uint32_t)col0, v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (row < rows) {
-                    float4* dst = reinterpret_cast<float4*>(out + row * TC_N + col0);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        dst[i] = make_float4(__uint_as_float(v[4 * i]) + tw.b3[col0 + 4 * i], __uint_as_float(v[4 * i + 1]) + tw.b3[col0 + 4 * i + 1],
-                                             __uint_as_float(v[4 * i + 2]) + tw.b3[col0 + 4 * i + 2], __uint_as_float(v[4 * i + 3]) + tw.b3[col0 + 4 * i + 3]);
+                for (int i = 0; i < 32; ++i) z3[part * 32 + i] = __uint_as_float(v[i]) + tw.b3[col0 + i];
+            }
+        }
+        if (out && row < rows) {
+            float4* dst = reinterpret_cast<float4*>(out + row * TC_N + h * 64);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dst[i] = make_float4(z3[4 * i], z3[4 * i + 1], z3[4 * i + 2], z3[4 * i + 3]);
+        }
+        if (MODE == 2) {
+            // ---- the tail: x = clamp(leaky_relu(z3)); the A + 1 head rows as two 64-term partial sums per row (the two threads
+            // of a row meet in shared memory — the operand area is free now); softmax; inverse-CDF sample on one keyed uniform
+            float* wsm = reinterpret_cast<float*>(tc_smem);               // [A + 1][128]
+            float* partial = wsm + 9 * 128;                               // [128 rows][2 halves][9]
+            const int n_out = tw.n_actions + 1;
+            for (int k = tid; k < n_out * 128; k += 256) wsm[k] = tw.w_heads[k];
+            __syncthreads();
+            float acc[9];
+#pragma unroll
+            for (int o = 0; o < 9; ++o) acc[o] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 64; ++i) {
+                float v = z3[i];
+                v = v > 0.f ? v : v * slope;                              // F.leaky_relu, :92
+                v = fminf(fmaxf(v, tw.clamp_lo), tw.clamp_hi);            // torch.clamp(x, -4, 4), :93
+#pragma unroll
+                for (int o = 0; o < 9; ++o)
+                    if (o < n_out) acc[o] = fmaf(v, wsm[o * 128 + h * 64 + i], acc[o]);
+            }
+#pragma unroll
+            for (int o = 0; o < 9; ++o) partial[(r * 2 + h) * 9 + o] = acc[o];
+            __syncthreads();
+            if (h == 0 && row < rows) {
+                const int A = tw.n_actions;
+#pragma unroll
+                for (int o = 0; o < 9; ++o) acc[o] = o < n_out ? (partial[(r * 2) * 9 + o] + partial[(r * 2 + 1) * 9 + o]) + tw.b_heads[o] : 0.f;
+                float mx = -3.4e38f;
+#pragma unroll
+                for (int o = 0; o < 8; ++o) if (o < A) mx = fmaxf(mx, acc[o]);
+                float ex[8], tot = 0.f;
+#pragma unroll
+                for (int o = 0; o < 8; ++o) { ex[o] = o < A ? expf(acc[o] - mx) : 0.f; tot += ex[o]; }   // F.softmax, :96
+                uint32_t c0 = (uint32_t)(row >> 2), c1 = (uint32_t)(row >> 34), c2 = (uint32_t)ctr, c3 = (uint32_t)(ctr >> 32) ^ 0x53414D50u;
+#pragma unroll
+                for (int rd = 0; rd < 10; ++rd) {                         // Philox4x32-10 under the sampling seed's round keys
+                    const uint64_t p0 = (uint64_t)PHILOX_M0 * c0, p1 = (uint64_t)PHILOX_M1 * c2;
+                    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ tw.rk0[rd], n2 = (uint32_t)(p0 >> 32) ^ c3 ^ tw.rk1[rd];
+                    c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+                }
+                const uint32_t wd[4] = {c0, c1, c2, c3};
+                const float u = (float)(pick4(wd, (uint32_t)row & 3u) >> 8) * (1.0f / 16777216.0f);
+                const float target = u * tot;
+                float cum = 0.f, p_pick = 0.f;
+                int pick = A - 1;
+                bool found = false;
+#pragma unroll
+                for (int o = 0; o < 8; ++o) {                             // smallest a with target < e[0] + ... + e[a]
+                    cum += ex[o];
+                    if (!found && o < A && target < cum) { pick = o; found = true; }
+                }
+#pragma unroll
+                for (int o = 0; o < 8; ++o) if (o == pick) p_pick = ex[o];
+                tw.actions[row] = (uint8_t)pick;
+                if (tw.value) tw.value[row] = acc[A < 8 ? A : 8];
+                if (tw.logp) tw.logp[row] = logf(p_pick / tot);
+                if (tw.probs) {
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) if (o < A) tw.probs[row * A + o] = ex[o] / tot;
                 }
             }
         }

@@ -134,6 +134,22 @@ class PolicyTrunkTC(Affine1TC):
         return out
 
 
+    def forward_sample(self, features: torch.Tensor, heads: tuple, actions: torch.Tensor, value: Optional[torch.Tensor] = None,
+                       probs: Optional[torch.Tensor] = None, logp: Optional[torch.Tensor] = None, noise_scale: float = 0.01,
+                       counter: Optional[torch.Tensor] = None, seed: int = 0, z3: Optional[torch.Tensor] = None,
+                       slope: float = 0.01) -> torch.Tensor:
+        """``Policy.forward`` + ``select_action`` (``actor_critic.py:84-97``, ``:108-125``) in ONE launch (``wab_policy_forward``):
+        the trunk above, then clamp, both heads, softmax and the Categorical sample of ``policy_tail`` on the accumulators'
+        registers. ``heads`` = ``stacked_heads(policy)``; fills ``actions`` u8[N] (and ``value``, ``probs``, ``logp``, ``z3`` when given)."""
+        w, b = heads
+        _lib.check(self.lib.wab_policy_forward(self.env._h, _ptr(features), features.shape[0], _ptr(self.packed), _ptr(self.bias),
+                                               _ptr(self.packed2), _ptr(self.bias2), 150, _ptr(self.packed3), _ptr(self.bias3),
+                                               _ptr(w), _ptr(b), w.shape[0] - 1, float(noise_scale), float(slope), -4.0, 4.0,
+                                               int(seed) & (2 ** 64 - 1), _ptr(counter), _ptr(actions), _ptr(value), _ptr(probs),
+                                               _ptr(logp), _ptr(z3), self._stream()))
+        return actions
+
+
 class Rollout:
     """N-environment rollout with every tensor resident on the device.
 
@@ -187,6 +203,15 @@ class Rollout:
     @torch.no_grad()
     def _step_eager(self):
         env = self.env
+        if self.tc_trunk:
+            # Policy.forward + select_action (actor_critic.py:84-97, :108-125, :188-189) in one tcgen05 kernel
+            self.noise_ctr += 1
+            self.affine1_tc.forward_sample(env.last_features, self.heads, self.actions, value=self.values,
+                                           noise_scale=0.01 if self.noise else 0.0, counter=self.noise_ctr, seed=self.sample_seed)
+            _, reward, _, _ = env.step(self.actions)
+            if self.track_reward:
+                self.reward_sum += reward.sum(dtype=torch.float64)
+            return
         if self.tc_first_layer:
             # flatten (actor_critic.py:188) + U[0,1)/100 noise (:189) + affine1 + leaky_relu (:88-90): one tcgen05 kernel
             h = self.affine1_tc(env.last_features, self.h1, 0.01 if self.noise else 0.0, self.noise_ctr)
@@ -210,9 +235,9 @@ class Rollout:
 
     def describe(self) -> str:
         if self.tc_trunk:
-            return ("wab_affine1_tc_kernel<trunk> (flatten + noise + affine1..3 + leaky_relu: one tcgen05 kernel, bf16 x 3 splits, fp32 "
-                    "accumulate, activations stay on the SM) -> wab_policy_tail_kernel (activation, clamp, both heads, softmax, "
-                    "Categorical sample) -> wab_step_kernel; one CUDA graph per step")
+            return ("wab_affine1_tc_kernel<2> (ONE tcgen05 kernel: flatten + noise + affine1..3 + leaky_relu with bf16 x 3 splits and fp32 "
+                    "accumulation, activations stay on the SM; then clamp, both heads, softmax, Categorical sample) -> wab_step_kernel; "
+                    "one CUDA graph per step")
         if self.tc_first_layer:
             return ("wab_affine1_tc_kernel (flatten + noise + affine1 + leaky_relu: tcgen05, bf16 x 3 splits, fp32 accumulate) -> "
                     "affine2, affine3 fp32 (cuBLAS) + leaky_relu -> wab_policy_tail_kernel (activation, clamp, both heads, softmax, "
