@@ -489,13 +489,29 @@ def rollout_leg(ctx, n, K, min_ms):
     ms = ctx.max_over_ranks(e0.elapsed_time(e1))
     st = env.stats()
     desc = ro.describe() if hasattr(ro, "describe") else "flatten+noise kernel -> torch fp32 MLP (cuBLAS) -> sampling kernel -> wab_step_kernel"
+    tc = bool(getattr(ro, "tc_trunk", False))
     env.close()
+    # the same loop with the policy as library calls (flatten kernel -> three cuBLAS fp32 GEMMs -> tail kernel), for comparison
+    lib = None
+    if tc:
+        env2 = VecEnv(n, seed=ctx.args.seed, device=ctx.dev, env_id_base=ctx.rank * n, features=True)
+        ro2 = Rollout(env2, Policy(env2.flat_dim, env2.n_actions), use_graph=True, dtype=torch.float32, tc_first_layer=False, tc_trunk=False)
+        ro2.run(10)
+        ctx.barrier()
+        s2 = max(32, steps // 4)
+        e0.record(); ro2.run(s2); e1.record()
+        ctx.barrier()
+        ms2 = ctx.max_over_ranks(e0.elapsed_time(e1))
+        lib = {"value": ctx.world * n * s2 / (ms2 * 1e-3), "ms_per_step": ms2 / s2, "steps": s2, "path": ro2.describe()}
+        env2.close()
     flops = 2.0 * (env.flat_dim * 128 + 128 * 150 + 150 * 128 + 128 * (env.n_actions + 1))
     v = n * steps / (ms * 1e-3)
     return {"workload": "configs[4]: actor_critic.py rollout, policy %d-128-150-128-{%d,1} fp32 in the loop, %d v1 envs per GPU" % (
                 env.flat_dim, env.n_actions, n),
             "value": ctx.world * v, "unit": "env-steps/s", "ms_per_step": ms / steps, "window_ms": ms, "steps": steps,
-            "dtype": "fp32 policy", "num_envs_per_gpu": n, "global_envs": ctx.world * n, "path": desc,
+            "dtype": ("fp32 policy (fp32-accurate on the tensor cores: bf16 x 3 operand splits, fp32 accumulation; "
+                      "tests/test_rollout_gpu.py holds it to 3e-6 of the fp64 result)") if tc else "fp32 policy",
+            "num_envs_per_gpu": n, "global_envs": ctx.world * n, "path": desc, "library_path": lib,
             "policy_flops_per_env_step": flops, "policy_tflops": v * flops / 1e12,
             "mean_episode_length": st["steps"] / max(st["episodes"], 1)}
 

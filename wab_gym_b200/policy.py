@@ -89,7 +89,8 @@ class Affine1TC:
     @torch.no_grad()
     def refresh(self):
         w = self.policy.affine1.weight.detach().float().contiguous()
-        self.bias = self.policy.affine1.bias.detach().float().contiguous()
+        b = self.policy.affine1.bias.detach().float().contiguous()
+        self.bias = b.clone() if self.bias is None else self.bias.copy_(b)           # in place: captured graphs hold the pointer
         _lib.check(self.lib.wab_policy_affine1_prepare(_ptr(w), w.shape[1], _ptr(self.packed), self._stream()))
 
     def __call__(self, features: torch.Tensor, out: torch.Tensor, noise_scale: float = 0.01,
@@ -120,7 +121,9 @@ class PolicyTrunkTC(Affine1TC):
         super().refresh()
         p = self.policy
         w2, w3 = p.affine2.weight.detach().float().contiguous(), p.affine3.weight.detach().float().contiguous()
-        self.bias2, self.bias3 = p.affine2.bias.detach().float().contiguous(), p.affine3.bias.detach().float().contiguous()
+        b2, b3 = p.affine2.bias.detach().float().contiguous(), p.affine3.bias.detach().float().contiguous()
+        self.bias2 = b2.clone() if self.bias2 is None else self.bias2.copy_(b2)
+        self.bias3 = b3.clone() if self.bias3 is None else self.bias3.copy_(b3)
         _lib.check(self.lib.wab_policy_linear_prepare(_ptr(w2), 150, 128, _ptr(self.packed2), self._stream()))
         _lib.check(self.lib.wab_policy_linear_prepare(_ptr(w3), 128, 150, _ptr(self.packed3), self._stream()))
 
@@ -246,6 +249,15 @@ class Rollout:
             return ("wab_flatten_noisy_kernel (flatten + noise) -> affine1..3 fp32 (cuBLAS) + leaky_relu -> wab_policy_tail_kernel "
                     "(activation, clamp, both heads, softmax, Categorical sample) -> wab_step_kernel; one CUDA graph per step")
         return "wab_flatten_noisy_kernel -> torch MLP (cuBLAS) -> wab_sample_kernel -> wab_step_kernel; one CUDA graph per step"
+
+    def refresh_weights(self):
+        """After an optimiser step: re-pack what the kernels hold of the policy (stacked heads, split tensor-core operands).
+        The buffers are updated in place, so a captured graph keeps working."""
+        if self.heads is not None:
+            w, b = stacked_heads(self.policy)
+            self.heads[0].copy_(w); self.heads[1].copy_(b)
+        if self.affine1_tc is not None:
+            self.affine1_tc.refresh()
 
     def step(self):
         if self.graph is not None:
