@@ -77,6 +77,8 @@ def parse_args():
     ap.add_argument("--legs", default="all", help="all | none | comma list of " + ",".join(ALL_LEGS))
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--numa", default="auto", choices=["auto", "off"],
+                    help="auto: every rank binds its threads and pinned memory to its GPU's NUMA node (sharding.bind_to_gpu_numa)")
     ap.add_argument("--skip-e2e", action="store_true", help="sweeps only: skip the host-buffer leg")
     ap.add_argument("--skip-cpu", action="store_true", help="sweeps only: skip the cpu_baseline leg")
     return ap.parse_args()
@@ -253,6 +255,13 @@ class Ctx:
             raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
+        self.numa = None
+        if getattr(args, "numa", "auto") == "auto":      # before any pinned allocation: the host-buffer step is host-side bound
+            try:
+                from wab_gym_b200.sharding import bind_to_gpu_numa
+                self.numa = bind_to_gpu_numa(self.local_rank)
+            except Exception as exc:
+                self.numa = {"error": "%s: %s" % (type(exc).__name__, exc)}
         if self.world > 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             # keep stdout to the one JSON line: NCCL prints its version banner on fd 1 (NCCL_DEBUG=VERSION may come from
@@ -373,7 +382,7 @@ def v1_fused_leg(ctx, n, K, W, T, min_ms, with_collective):
                 samples.append(e0.elapsed_time(e1) * 1e3)
             collective_us = sorted(samples)[2]
     stats = env.stats()
-    lpe = env.lanes_per_env
+    kernel_name = env.step_kernel_name(int(round(total_steps / n_launch)))
     env.close()
     del ring
     torch.cuda.empty_cache()
@@ -384,7 +393,7 @@ def v1_fused_leg(ctx, n, K, W, T, min_ms, with_collective):
     roof = {"bound": "hbm", "achieved": achieved, "peak": ctx.peak, "unit": "GB/s", "frac": achieved / ctx.peak,
             "traffic": bpe * n * steps_per_launch, "traffic_source": bpe_src,
             "frac_dram": achieved / B_ALG * bpe / ctx.peak,
-            "kernel": "wab_step_kernel<false, LPE=%d>" % lpe, "peak_source": ctx.peak_src,
+            "kernel": kernel_name, "peak_source": ctx.peak_src,
             "bytes_per_env_step": B_ALG, "dram_bytes_per_env_step": bpe, "env_steps_per_launch": n * steps_per_launch,
             "avg_launch_ms": per_launch_ms,
             "how": "algorithmic bytes of all launches of the timed window / the window (CUDA events on the launching stream; "
@@ -545,17 +554,19 @@ def e2e_leg(ctx, n, K, W):
     torch.cuda.synchronize(ctx.dev)
     mine_ms = (time.perf_counter() - t0) * 1e3
     e2e_ms = ctx.max_over_ranks(mine_ms)
-    per_rank = None
+    per_rank, numa = None, [ctx.numa]
     if ctx.world > 1:
         t = torch.zeros(ctx.world, dtype=torch.float64, device=ctx.dev)
         t[ctx.rank] = n * Ke / (mine_ms * 1e-3)
         ctx.dist.all_reduce(t)
         per_rank = [float(x) for x in t.cpu()]
+        numa = [None] * ctx.world
+        ctx.dist.all_gather_object(numa, ctx.numa)
     mapped = n <= 16384
     env.close()
     return {"value": ctx.world * n * Ke / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": n,
             "d2h_bytes_per_step": n * (363 + 1 + 1 + 1 + 4 + 1 + 1), "steps": Ke, "ms_per_step": e2e_ms / Ke,
-            "per_rank": per_rank,
+            "per_rank": per_rank, "numa": numa,
             "path": ("wab_vec_step_host_packed, <= 16,384 envs: wab_step_kernel reads the pinned host actions and streams grids/food/"
                      "role/status/reward/done/info straight into the pinned host block over PCIe -> stream sync" if mapped else
                      "wab_vec_step_host_packed: pinned host actions -> H2D -> wab_step_kernel -> one D2H of grids/food/role/status/"

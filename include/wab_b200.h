@@ -161,6 +161,11 @@ int64_t wab_vec_num_envs(const WabVec *h);
 /* Lanes cooperating on one env (1, 4, 8, 16 or 32), chosen at create from the batch size so that a
  * small batch still covers every SM; results do not depend on it. */
 int wab_vec_lanes_per_env(const WabVec *h);
+/* 1 when a wab_vec_step_many launch of n_steps steps runs as the two-warp pipeline (wab_step_pipe_kernel: one warp of a
+ * pair runs the rules, the other publishes observations and scalars), 0 when it runs wab_step_kernel. The pipeline serves
+ * lanes-per-env batches of up to 8 rule warps per SM and launches of >= 4 steps; WAB_PIPE=0 / 2 in the environment
+ * forces never / always. Results are identical. */
+int wab_vec_step_many_pipelined(const WabVec *h, int32_t n_steps);
 /* Which kernels serve this handle: 0 = the specialised 11 x 11 / spawn-margin-1 kernels (a 121-bit window sliding in
  * registers), 1 = the warp-per-env kernels for every other odd viewport up to 31 x 31 and margins 1, 2 (wab_generic.cuh;
  * WAB_GENERIC=1 in the environment forces them onto the default geometry, for tests). Results are identical. */

@@ -55,3 +55,30 @@ def test_async_reducer_without_process_group_returns_local_stats():
     assert red.result() is None
     red.submit(lambda: torch.arange(8, dtype=torch.int64))
     assert red.result()["steps"] == 1 and red.submitted == 1
+
+
+def test_numa_binding_follows_the_gpus_sysfs_entry(tmp_path):
+    """bind_to_gpu_numa reads the GPU's NUMA node and local CPUs from sysfs, narrows the CPU affinity to the local CPUs
+    this process may use and prefers that node's memory; platforms without the information are left alone."""
+    import subprocess
+    import sys
+    from wab_gym_b200.sharding import gpu_numa_info, parse_cpulist
+    assert parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11} and parse_cpulist("") == set()
+    allowed = sorted(os.sched_getaffinity(0))
+    dev = tmp_path / "bus" / "pci" / "devices" / "0000:1b:00.0"
+    dev.mkdir(parents=True)
+    (dev / "numa_node").write_text("0\n")
+    (dev / "local_cpulist").write_text("%d,100000\n" % allowed[0])
+    info = gpu_numa_info("0000:1B:00.0", sysfs=str(tmp_path))
+    assert info["numa_node"] == 0 and info["local_cpus"] == {allowed[0], 100000}
+    assert gpu_numa_info("0000:ff:00.0", sysfs=str(tmp_path))["numa_node"] == -1
+    # in a child process: the affinity change must not leak into the test runner
+    code = ("import os, json, sys; sys.path.insert(0, %r); from wab_gym_b200.sharding import bind_to_gpu_numa; "
+            "r = bind_to_gpu_numa(0, pci_bus_id='0000:1b:00.0', sysfs=%r); r['now'] = sorted(os.sched_getaffinity(0)); "
+            "r2 = bind_to_gpu_numa(0, pci_bus_id='0000:ff:00.0', sysfs=%r); print(json.dumps([r, r2]))"
+            % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(tmp_path), str(tmp_path)))
+    import json
+    r, r2 = json.loads(subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, check=True, text=True).stdout)
+    assert r["numa_node"] == 0 and r["now"] == [allowed[0]]
+    assert r["cpu_bound"] == (len(allowed) > 1) and r["cpus_after"] == 1
+    assert r2["numa_node"] == -1 and not r2["cpu_bound"] and not r2["mem_bound"]

@@ -612,3 +612,47 @@ def test_time_chunked_kernel_equals_single_steps(lpe, name, monkeypatch):
             assert np.array_equal(sa[k], sb[k]), (lpe, name, T, k)
     assert a.stats() == b.stats() and a.stats()["bad_actions"] == 7 * 1
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("lpe", [4, 8, 16, 32])
+@pytest.mark.parametrize("name", ["defaults", "dense", "six_actions_random_start", "restrict_view", "tiny_bushes"])
+def test_two_warp_pipeline_equals_single_steps(lpe, name, monkeypatch):
+    """Multi-step launches of the lanes-per-env geometries run as a pair of warps per env group: one runs the rules and
+    parks each step's planes and scalars in a ring of shared-memory slots, the other publishes them (wab_step_pipe_kernel).
+    Every output of launches of 4, 5, 23, 64 and 131 steps on a ragged batch — observations, features, reward, done, info,
+    the position history, the hidden state and the statistics — equals what single-step launches give, and so does the
+    same launch with the pipeline switched off."""
+    monkeypatch.setenv("WAB_LPE", str(lpe))
+    monkeypatch.setenv("WAB_PIPE", "2")             # always (the default uses it only while the batch leaves issue slots free)
+    monkeypatch.delenv("WAB_CHUNK", raising=False)
+    overrides, _ = OPTION_SETS[name]
+    n, seed = 45, 321
+    a = _vec(n, overrides, seed=seed, features=True, wolf_cap=64, ego=True)
+    b = _vec(n, overrides, seed=seed, features=True, wolf_cap=64, ego=True)
+    c = _vec(n, overrides, seed=seed, features=True, wolf_cap=64, ego=True)
+    assert a.lanes_per_env == lpe
+    gen = torch.Generator(device="cuda").manual_seed(100 + lpe)
+    a.reset(); b.reset(); c.reset()
+    for T in (4, 5, 23, 64, 131):
+        acts = torch.randint(0, a.n_actions, (T, n), dtype=torch.uint8, device="cuda", generator=gen)
+        acts[T // 2, 3] = 77                                   # a bad action in the middle of the launch
+        oa, ra, da, ia = a.step_many(acts)
+        monkeypatch.setenv("WAB_PIPE", "0")
+        oc, rc, dc, ic = c.step_many(acts)
+        monkeypatch.setenv("WAB_PIPE", "2")
+        for x, y in zip(oa, oc):
+            assert torch.equal(x, y), (lpe, name, T)
+        assert torch.equal(ra, rc) and torch.equal(da, dc) and torch.equal(ia["info"], ic["info"])
+        assert torch.equal(ia["features"], ic["features"])
+        for t in range(T):
+            ob, rb, db, ib = b.step(acts[t])
+            for x, y in zip(oa, ob):
+                assert torch.equal(x[t], y), (lpe, name, T, t)
+            assert torch.equal(ra[t], rb) and torch.equal(da[t], db) and torch.equal(ia["info"][t], ib["info"]), (lpe, name, T, t)
+            assert torch.equal(ia["features"][t], ib["features"]), (lpe, name, T, t)
+        assert torch.equal(a.ego_proximities(), b.ego_proximities()), (lpe, name, T)
+        sa, sb, sc = a.export_state(), b.export_state(), c.export_state()
+        for k in sa:
+            assert np.array_equal(sa[k], sb[k]) and np.array_equal(sa[k], sc[k]), (lpe, name, T, k)
+    assert a.stats() == b.stats() == c.stats() and a.stats()["bad_actions"] == 5
+    a.close(); b.close(); c.close()

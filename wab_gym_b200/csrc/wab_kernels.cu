@@ -44,6 +44,9 @@ constexpr int kFlushUnroll = WAB_FLUSH_UNROLL;
 #ifndef WAB_MIN_BLOCKS_LPEN
 #define WAB_MIN_BLOCKS_LPEN 1         // lanes-per-env kernels: no register cap (one wave of few CTAs anyway)
 #endif
+#ifndef WAB_PIPE_PAIRS
+#define WAB_PIPE_PAIRS 4              // rule/publisher warp pairs per CTA of the pipelined multi-step kernel
+#endif
 #ifndef WAB_THREADS_LPE1
 #define WAB_THREADS_LPE1 32           // thread-per-env kernel: one warp per CTA (no intra-CTA imbalance over a T-step launch:
                                       // 1.32e10 vs 1.29e10 env-steps/s at 1M envs with 128-thread CTAs, profiles/r1f_wave_quantization.txt)
@@ -235,7 +238,7 @@ __device__ __forceinline__ void write_features(uint8_t* features, int64_t o, con
     for (int k = 0; k < 7; ++k) dst[k] = f[k];
 }
 
-__device__ __forceinline__ void flush_stats(unsigned long long* wstats, const uint32_t c[8]) {
+__device__ __forceinline__ void flush_stats_row(unsigned long long* wstats, int64_t row, const uint32_t c[8]) {
     // warp redux, then lane k adds total k to the warp's own row (one 64-byte read-modify-write, exclusive to this warp)
     const int lane = threadIdx.x & 31;
     uint32_t mine = 0u;
@@ -244,8 +247,10 @@ __device__ __forceinline__ void flush_stats(unsigned long long* wstats, const ui
         const uint32_t s = __reduce_add_sync(FULL, c[k]);
         mine = lane == k ? s : mine;
     }
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (lane < 8 && mine) wstats[warp * 8 + lane] += (unsigned long long)mine;
+    if (lane < 8 && mine) wstats[row * 8 + lane] += (unsigned long long)mine;
+}
+__device__ __forceinline__ void flush_stats(unsigned long long* wstats, const uint32_t c[8]) {
+    flush_stats_row(wstats, ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, c);
 }
 
 // totals[k] = sum over warps of wstats[warp][k]; one block per counter
@@ -577,6 +582,176 @@ wab_step_chunk_kernel(const __grid_constant__ Params P, const StatePtrs st, cons
         cnt[WAB_STAT_OVERFLOWS] = (uint32_t)(acc_misc >> 32) & 0xFFFFu;
     }
     flush_stats(st.wstats, cnt);
+}
+
+// ---- the multi-step kernel of the lanes-per-env geometries as a two-warp pipeline --------------------------------------
+// A small batch is bound by the length of one step's dependent instruction chain, and a third of that chain is not rules
+// at all: composing the 363-bit strings, expanding them to bytes, the 16-byte stores and the scalar outputs. Here a CTA is
+// one PAIR of warps that owns EPW = 32 / LPE envs: warp 0 runs the rules (exactly the code of wab_step_kernel) and parks
+// each step's planes and scalars in a ring of shared-memory slots; warp 1 publishes them — bit stream, byte expansion,
+// stores, scalars, features — while warp 0 is already on the next steps. The two meet only at mbarriers in shared memory
+// (one "full" and one "empty" barrier per ring slot; an arrive never blocks, a wait spins on the barrier's phase parity).
+// Results are identical to wab_step_kernel's (same functions in the same order per env); WAB_PIPE=0 selects that kernel.
+template <int LPE> struct PipeGeo {
+    static constexpr int EPW = 32 / LPE;
+    static constexpr int DEPTH = 4;                        // ring slots, each with a full and an empty mbarrier
+    static constexpr int RES = 12;                         // words parked per (env, step): 2 x 4 planes, scalars, info, reward
+    static constexpr int RING = DEPTH * EPW * RES;
+    static constexpr int SW = (WarpStream<EPW>::WORDS + 3) & ~3;
+    // Warp w of a CTA sits on scheduler w % 4 of its SM. A CTA is therefore FOUR pairs — warps 0..3 run the rules,
+    // warps 4..7 publish — so every scheduler gets the same mix of both roles; with one pair per CTA the rule warps of an
+    // SM all land on two of its four schedulers and the pipeline gains nothing (profiles/r2j_pipe_ab.txt).
+    static constexpr int PAIRS = WAB_PIPE_PAIRS;
+    static constexpr int THREADS = 64 * PAIRS;
+    static __host__ __device__ int pair_words(int wolf_cap) { return ((wolf_cap * EPW + 3) & ~3) + RING + SW + 4 * DEPTH; }
+};
+// Shared-memory mbarriers rather than named hardware barriers: the SM's pool of named barriers caps resident CTAs
+// (2 * DEPTH + 1 of them per CTA left room for ~4 CTAs per SM; a 4,096-env batch needs 7 to be one wave).
+__device__ __forceinline__ uint32_t pipe_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pipe_mbar_init(uint64_t* b) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pipe_smem_addr(b)), "r"(1u) : "memory");
+}
+// one elected lane arrives for its warp (after __syncwarp: the warp's shared-memory accesses are ordered before it; the
+// arrive has release, the wait acquire semantics at CTA scope)
+__device__ __forceinline__ void pipe_mbar_arrive(uint64_t* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pipe_smem_addr(b)) : "memory");
+}
+__device__ __forceinline__ void pipe_mbar_wait(uint64_t* b, uint32_t parity) {
+    const uint32_t a = pipe_smem_addr(b);
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+template <bool F64, int LPE>
+__global__ void __launch_bounds__(PipeGeo<LPE>::THREADS, 1)
+wab_step_pipe_kernel(const __grid_constant__ Params P, const StatePtrs st, const uint8_t* __restrict__ actions,
+                     const int n_steps, const OutPtrs out) {
+    extern __shared__ uint32_t smem[];
+    constexpr int EPW = PipeGeo<LPE>::EPW, D = PipeGeo<LPE>::DEPTH, RES = PipeGeo<LPE>::RES;
+    const int64_t n = st.n;
+    const int lane = threadIdx.x & 31;
+    constexpr int PAIRS = PipeGeo<LPE>::PAIRS;
+    const int warp = threadIdx.x >> 5, pair = warp % PAIRS;
+    const int64_t group = (int64_t)blockIdx.x * PAIRS + pair;
+    const int64_t warp_first = group * EPW;
+    uint32_t* pbase = smem + pair * PipeGeo<LPE>::pair_words(P.wolf_cap);
+    uint32_t* ring = pbase + ((P.wolf_cap * EPW + 3) & ~3); // [DEPTH][EPW][RES], 16-byte aligned
+    uint32_t* stream = ring + PipeGeo<LPE>::RING;
+    uint64_t* full = reinterpret_cast<uint64_t*>(stream + PipeGeo<LPE>::SW);   // [DEPTH] step t is in slot t % DEPTH
+    uint64_t* empty = full + D;                                                // [DEPTH] the slot has been read
+    pdl_launch_dependents();
+    if (warp >= PAIRS && lane < 2 * D) pipe_mbar_init(full + lane);
+    __syncthreads();
+    pdl_wait();
+    if (warp < PAIRS) {
+        // ---------------------------------------------------------------- warp 0: the rules
+        Ctx c;
+        c.lane = lane; c.sub = lane % LPE; c.slot = lane / LPE; c.env_local = c.slot;
+        c.idx = warp_first + c.slot; c.warp_first = warp_first;
+        c.active = c.idx < n; c.writer = c.active && c.sub == 0;
+        c.n_valid = 0;
+        uint32_t* wolves_s = pbase + c.env_local;          // [wolf_cap][EPW]
+        Coop<LPE> coop;
+        coop.sub = (uint32_t)c.sub;
+        coop.gmask = LPE == 32 ? FULL : (((1u << (LPE & 31)) - 1u) << (c.lane - c.sub));
+        Env E;
+        Slots S;
+        S.wolves = wolves_s; S.wstride = EPW;
+        S.logcell = st.logcell + (c.active ? c.idx : 0); S.logcnt = st.logcnt + (c.active ? c.idx : 0); S.lstride = n;
+        if (c.active) load_env<F64>(P, st, c.idx, E, wolves_s, EPW);
+        else { E = Env(); }
+        unsigned long long acc_outcome = 0ull, acc_misc = 0ull;
+        const uint8_t* ap = actions + (c.active ? c.idx : 0);
+        uint32_t a_next = c.active ? *ap : 0u;
+        for (int t = 0; t < n_steps; ++t) {
+            StepOut O;
+            bool need_reset = false;
+            const uint32_t a = a_next;
+            ap += n;
+            if (c.active && t + 1 < n_steps) a_next = *ap;
+            if (c.active) {
+                env_step<F64, LPE>(P, E, S, a, O, coop);
+                if (st.hist && c.writer && E.turn < (uint32_t)st.hist_len) st.hist[(int64_t)E.turn * n + c.idx] = pack_xy(E.x, E.y);
+                need_reset = O.done && P.auto_reset;
+                acc_outcome += 1ull << (16u * O.outcome);
+                acc_misc += (unsigned long long)O.ate | ((unsigned long long)O.bad_action << 16);
+            } else {
+                O = StepOut();
+            }
+            if (__any_sync(FULL, need_reset)) {
+                warp_reset<F64, LPE>(P, E, S, need_reset, c.lane, O.wm, O.bm, O.overflow);
+                if (need_reset) {
+                    O.food_obs = food_observation(P, E, F64);
+                    O.role = E.role; O.status = E.status;
+                }
+            }
+            apply_view_mask(P, O.role, O.wm, O.bm);
+            const int s = t & (D - 1);
+            __syncwarp();
+            if (t >= D) pipe_mbar_wait(empty + s, ((uint32_t)(t / D) - 1u) & 1u);   // the publisher has taken step t - D out of this slot
+            if (c.writer) {
+                acc_misc += (unsigned long long)O.overflow << 32;
+                uint32_t* r = ring + (s * EPW + c.slot) * RES;
+                *reinterpret_cast<uint4*>(r) = make_uint4(O.wm[0], O.wm[1], O.wm[2], O.wm[3]);
+                *reinterpret_cast<uint4*>(r + 4) = make_uint4(O.bm[0], O.bm[1], O.bm[2], O.bm[3]);
+                *reinterpret_cast<uint4*>(r + 8) = make_uint4(O.food_obs | (O.role << 8) | (O.status << 16) | (O.done << 24),
+                                                              O.info, __float_as_uint(O.reward), 0u);
+            }
+            __syncwarp();
+            if (lane == 0) pipe_mbar_arrive(full + s);      // step t is in the slot
+        }
+        if (c.writer) store_env<F64>(st, c.idx, E, wolves_s, EPW);
+        uint32_t cnt[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        if (c.writer) {
+            const uint32_t fin = (uint32_t)(acc_outcome >> 16) & 0xFFFFu, sta = (uint32_t)(acc_outcome >> 32) & 0xFFFFu,
+                           kil = (uint32_t)(acc_outcome >> 48) & 0xFFFFu;
+            cnt[WAB_STAT_EPISODES] = fin + sta + kil;
+            cnt[WAB_STAT_STEPS] = (uint32_t)n_steps;
+            cnt[WAB_STAT_FINISHED] = fin; cnt[WAB_STAT_STARVED] = sta; cnt[WAB_STAT_KILLED] = kil;
+            cnt[WAB_STAT_EATS] = (uint32_t)acc_misc & 0xFFFFu;
+            cnt[WAB_STAT_BAD_ACTIONS] = (uint32_t)(acc_misc >> 16) & 0xFFFFu;
+            cnt[WAB_STAT_OVERFLOWS] = (uint32_t)(acc_misc >> 32) & 0xFFFFu;
+        }
+        flush_stats_row(st.wstats, group, cnt);
+    } else {
+        // ---------------------------------------------------------------- warp 1: the publisher (lane l < EPW: env l)
+        const int64_t idx = warp_first + lane;
+        const bool mine = lane < EPW && idx < n;
+        const int64_t left = n - warp_first;
+        const int n_valid = (int)(left < EPW ? (left > 0 ? left : 0) : EPW);
+        int64_t o = idx;
+        int64_t first_byte = warp_first * OBS_BYTES;
+        for (int t = 0; t < n_steps; ++t, o += n, first_byte += n * OBS_BYTES) {
+            const int s = t & (D - 1);
+            pipe_mbar_wait(full + s, (uint32_t)(t / D) & 1u);   // step t is in the slot
+            const int off = (int)(first_byte & 15);
+            uint4 sc = make_uint4(0u, 0u, 0u, 0u);
+            StepOut O;
+            if (lane < EPW) {
+                const uint32_t* r = ring + (s * EPW + lane) * RES;
+                const uint4 w = *reinterpret_cast<const uint4*>(r), b = *reinterpret_cast<const uint4*>(r + 4);
+                sc = *reinterpret_cast<const uint4*>(r + 8);
+                O.wm[0] = w.x; O.wm[1] = w.y; O.wm[2] = w.z; O.wm[3] = w.w;
+                O.bm[0] = b.x; O.bm[1] = b.y; O.bm[2] = b.z; O.bm[3] = b.w;
+                stream_put(stream, off + OBS_BYTES * lane, lane == EPW - 1, off + EPW * OBS_BYTES, O.wm, O.bm, mine);
+            }
+            __syncwarp();                                   // every read of the slot has landed in registers or the stream
+            if (lane == 0) pipe_mbar_arrive(empty + s);     // the slot is free for step t + D
+            if (mine) {
+                O.food_obs = sc.x & 0xFFu; O.role = (sc.x >> 8) & 0xFFu; O.status = (sc.x >> 16) & 0xFFu;
+                O.done = sc.x >> 24; O.info = sc.y; O.reward = __uint_as_float(sc.z);
+                write_scalars(out, o, O);
+                if (out.features) write_features(out.features, o, O);
+            }
+#ifndef WAB_EXP_NOEMIT
+            stream_flush<false>(stream, nullptr, out.grids + (first_byte - off), off, off + OBS_BYTES * n_valid, lane);
+#endif
+            __syncwarp();
+        }
+    }
 }
 
 // reset(mask) + fresh observation of every env
@@ -977,6 +1152,7 @@ struct WabVec {
     int64_t obs_bytes; // 3 * width * height
     int lpe;          // lanes per env chosen at create (see pick_lpe)
     int mb;           // CTAs per SM the thread-per-env kernel is built for (see pick_mb)
+    int n_sm;         // multiprocessors of the device
     uint8_t* d_features;   // bound feature output, or null
     // host-buffer step as one CUDA graph (H2D actions -> step kernel -> D2H block), rebuilt when the pointers change
     cudaStream_t host_stream;
@@ -1026,6 +1202,13 @@ void launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t sm
 // 4,096 envs (1.77e9 vs 1.79e9 env-steps/s; profiles/r2e_*): the draws it makes ahead are ~15 % of a step's instructions,
 // and parking / re-reading every step's planes costs about as much.
 bool chunk_enabled() { const char* e = getenv("WAB_CHUNK"); return e && atoi(e) != 0; }
+// // WAB_PIPE: 0 = never, 1 (default) = where it pays (see launch_step_t), 2 = always (tests, A/B runs).
+int pipe_mode() { const char* e = getenv("WAB_PIPE"); return e ? atoi(e) : 1; }
+bool use_pipeline(const WabVec* h, int lpe, int T) {
+    if (h->generic || lpe <= 1 || T < 4 || pipe_mode() == 0 || (chunk_enabled() && (lpe == 8 || lpe == 16))) return false;
+    const int64_t epw = 32 / lpe, rule_warps = (h->n + epw - 1) / epw;
+    return pipe_mode() == 2 || rule_warps <= 8 * (int64_t)h->n_sm;
+}
 template <bool F64, int LPE>
 void launch_step_t(const WabVec* h, const uint8_t* a, int T, const OutPtrs& out, cudaStream_t s) {
     const unsigned grid = (unsigned)((h->n + Geo<LPE>::EPB - 1) / Geo<LPE>::EPB);
@@ -1034,6 +1217,18 @@ void launch_step_t(const WabVec* h, const uint8_t* a, int T, const OutPtrs& out,
             const size_t smem = sizeof(uint32_t) * ((size_t)h->P.wolf_cap * Geo<LPE>::EPB +
                                                     (size_t)(Geo<LPE>::THREADS / 32) * ChunkGeo<LPE>::WARP_WORDS);
             launch_pdl(wab_step_chunk_kernel<F64, LPE>, grid, Geo<LPE>::THREADS, smem, s, h->P, h->st, a, T, out);
+            return;
+        }
+    }
+    if constexpr (LPE > 1) {
+        // two-warp pipeline (rules in one warp, publication in the other) while the batch leaves issue slots free: up to
+        // 8 rule warps per SM. Same-box A/B (profiles/r2j_pipe_ab.txt): 4,096 envs at LPE 8 (6.9 rule warps per SM)
+        // 1.76e9 -> 1.97e9 env-steps/s, 2,048 at LPE 16 1.05e9 -> 1.21e9; 8,192 at LPE 8 (13.8 per SM) 2.74e9 -> 2.06e9.
+        if (use_pipeline(h, LPE, T)) {
+            const size_t smem = sizeof(uint32_t) * (size_t)PipeGeo<LPE>::PAIRS * (size_t)PipeGeo<LPE>::pair_words(h->P.wolf_cap);
+            const int64_t groups = (h->n + PipeGeo<LPE>::EPW - 1) / PipeGeo<LPE>::EPW;
+            const unsigned pgrid = (unsigned)((groups + PipeGeo<LPE>::PAIRS - 1) / PipeGeo<LPE>::PAIRS);
+            launch_pdl(wab_step_pipe_kernel<F64, LPE>, pgrid, PipeGeo<LPE>::THREADS, smem, s, h->P, h->st, a, T, out);
             return;
         }
     }
@@ -1197,6 +1392,8 @@ int wab_vec_create(const WabConfig* cfg, const uint32_t* bush_thr, int32_t n_bus
     const size_t o_stats = o; o = align_up(o + 64, 256);
     // one statistics row per warp of the largest grid this handle launches: its lanes-per-env variant, or thread per
     // env (which the mapped host path uses whatever the handle's variant is)
+    h->n_sm = 148;
+    cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device);
     h->lpe = pick_lpe(h);
     h->mb = pick_mb(h);
     auto warps_of = [n](size_t lpe) {
@@ -1243,6 +1440,7 @@ void wab_vec_destroy(WabVec* h) {
 int64_t wab_vec_num_envs(const WabVec* h) { return h ? h->n : 0; }
 int wab_vec_kernel_kind(const WabVec* h) { return h && h->generic ? 1 : 0; }
 int wab_vec_lanes_per_env(const WabVec* h) { return h ? (h->generic ? 32 : h->lpe) : 0; }
+int wab_vec_step_many_pipelined(const WabVec* h, int32_t n_steps) { return h && use_pipeline(h, h->lpe, n_steps) ? 1 : 0; }
 
 int wab_vec_reset(WabVec* h, const uint8_t* d_mask, WabObs obs, void* stream) {
     if (!h || !obs.d_grids || !obs.d_food || !obs.d_role || !obs.d_status) return fail(WAB_E_NULL, "null argument");

@@ -156,6 +156,14 @@ class VecEnv:
         return (ObsBatch(b["grids"], b["food"], b["role"], b["status"]), b["reward"], b["done"].view(torch.bool),
                 self._info(b))
 
+    def step_kernel_name(self, n_steps=1):
+        """The kernel a launch of `n_steps` lockstep steps runs (benchmarks and profiles name it)."""
+        if self.generic_kernels:
+            return "wab_generic_step_kernel"
+        if self.lib.wab_vec_step_many_pipelined(self._h, int(n_steps)):
+            return "wab_step_pipe_kernel<false, LPE=%d> (rule warp + publisher warp per env group)" % self.lanes_per_env
+        return "wab_step_kernel<false, LPE=%d>" % self.lanes_per_env
+
     def step_many(self, actions: torch.Tensor, out: Optional[dict] = None):
         """T lockstep steps in one launch; ``actions`` u8[T, N]. Every step's observation, reward and
         done are materialised ([T, N, ...]); state stays in registers between steps."""
