@@ -77,7 +77,7 @@ def parse_args():
     ap.add_argument("--legs", default="all", help="all | none | comma list of " + ",".join(ALL_LEGS))
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--numa", default="auto", choices=["auto", "off"],
+    ap.add_argument("--host-numa", dest="numa", default="auto", choices=["auto", "off"],
                     help="auto: every rank binds its threads and pinned memory to its GPU's NUMA node (sharding.bind_to_gpu_numa)")
     ap.add_argument("--skip-e2e", action="store_true", help="sweeps only: skip the host-buffer leg")
     ap.add_argument("--skip-cpu", action="store_true", help="sweeps only: skip the cpu_baseline leg")
