@@ -87,7 +87,7 @@ __global__ void wab2_turn_kernel(const __grid_constant__ Params2 P, const State2
         const int64_t o = (int64_t)a * n + idx;                       // [A][N] outputs
         if (acting && (out.planes || out.internal)) {
             const int64_t first_byte = ((int64_t)a * n + warp_first) * obs_bytes;   // the warp's 32 windows are contiguous
-            const int off = (int)(first_byte & 15);
+            const int off = out.planes ? obs_align_off(out.planes + first_byte) : 0;
             int32_t internal[5] = {0, 0, 0, 0, 0};
             if (out.planes) {
                 for (int k = lane; k < stream_words; k += 32) stream[k] = 0u;
@@ -191,7 +191,7 @@ int wab2_create(const Wab2Config* cfg, int64_t n_envs, uint64_t seed, uint64_t e
     // every window fits the world once -> occupancy-plane kernel, one warp per world
     h->grid = cfg->window_radius >= rmax && cfg->width >= S && cfg->height >= S && cfg->width <= 64 && cfg->height <= 64 &&
               (E > 96 || getenv("WAB2_GRID") != nullptr) && getenv("WAB2_NO_GRID") == nullptr;   // small worlds: thread per world is faster
-    h->stream_words = h->grid ? (3 * S * S + 15 + 31) / 32 + 1 : (32 * 3 * S * S + 15 + 31) / 32 + 1;
+    h->stream_words = h->grid ? (3 * S * S + 15 + 31) / 32 + 1 : (32 * 3 * S * S + 31 + 31) / 32 + 1;   // thread per world: 32-byte store grid
     // threads per block: as many as shared memory allows (3E state words + one bit stream per thread)
     int max_smem = 48 * 1024;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);

@@ -162,7 +162,7 @@ __device__ __forceinline__ uint32_t nibble_to_bytes(uint32_t n) { return (n * 0x
 // 60 bits of every env's string are zero, so a word shared by two envs is written by the later one.
 template <int EPW>
 struct WarpStream {
-    static constexpr int WORDS = (EPW * OBS_BYTES + 15 + 31) / 32 + 1;
+    static constexpr int WORDS = (EPW * OBS_BYTES + 31 + 31) / 32 + 1;   // the slab may start at any of 32 bit offsets
 };
 
 __device__ __forceinline__ void stream_put(uint32_t* stream, int bit0, bool last, int total_bits,
@@ -186,36 +186,76 @@ __device__ __forceinline__ void stream_put(uint32_t* stream, int bit0, bool last
     if (nown > 12) stream[fw + 12] = 0u;
 }
 
-// gA = 16-byte aligned address of stream bit 0; valid bits are [off, end).
+// 256-bit global stores (st.global.v8.b32, new with sm_100: SASS STG.E.EF.ENL2.256): a lane turns 32 stream bits into 32
+// bytes and issues ONE store — half the store instructions, loop iterations and stream loads of the 16-byte version.
+// Measured SLOWER on B200 (same box, bench.py legs, profiles/r2p_ab_wide_stores.txt): 131,072 envs 1.116e10 -> 1.035e10
+// env-steps/s, 1M envs 1.200e10 -> 1.167e10, v2 config 3 3.21e8 -> 2.98e8 world turns/s, 4,096 envs 1.974e9 -> 1.924e9 —
+// so the default stays the 16-byte store (STG.E.EF.128); -DWAB_WIDE_STORES=1 builds this version (bit-identical outputs:
+// the whole GPU suite passes with it).
+#ifndef WAB_WIDE_STORES
+#define WAB_WIDE_STORES 0
+#endif
+constexpr bool kWideStores = WAB_WIDE_STORES != 0;
+constexpr int kObsAlign = kWideStores ? 32 : 16;     // the store grid the warp's bit stream is aligned to
+__device__ __forceinline__ void st_cs_256(void* p, uint2 a, uint2 b, uint2 c, uint2 d) {
+    asm volatile("st.global.cs.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(b.x), "r"(b.y),
+                 "r"(c.x), "r"(c.y), "r"(d.x), "r"(d.y) : "memory");
+}
+// byte offset of an output address inside its store-grid cell (the address minus this is kObsAlign-aligned)
+__device__ __forceinline__ int obs_align_off(const uint8_t* p) { return (int)(reinterpret_cast<uintptr_t>(p) & (uintptr_t)(kObsAlign - 1)); }
+
+// gA = kObsAlign-aligned address of stream bit 0; valid bits are [off, end).
 // `lut` = 256 x uint2 in shared memory: byte value -> its 8 bits as 8 bytes (built once per CTA).
 // USE_LUT = false expands with two multiplies per 8 bytes instead (the lanes-per-env kernels: few chunks per step, and no
 // table means no CTA barrier anywhere in a single-step launch).
-template <bool USE_LUT = true>
+template <bool USE_LUT = true, bool WIDE = kWideStores>
 __device__ __forceinline__ void stream_flush(const uint32_t* stream, const uint2* lut, uint8_t* gA, int off, int end,
                                              int lane, bool lut_built = true) {
-    const uint16_t* hs = reinterpret_cast<const uint16_t*>(stream);
-    const int c_lo = (off + 15) >> 4, c_hi = end >> 4;            // chunks entirely inside [off, end)
+    constexpr int SH = WIDE ? 5 : 4, CH = 1 << SH;               // chunk = one store of CH bytes
+    const int c_lo = (off + CH - 1) >> SH, c_hi = end >> SH;     // chunks entirely inside [off, end)
+    if (WIDE) {
 #pragma unroll kFlushUnroll
-    for (int c = c_lo + lane; c < c_hi; c += 32) {
-        const uint32_t h = hs[c];
-        uint2 lo, hi;
-        if (USE_LUT && lut_built) {
-            lo = lut[h & 0xFFu]; hi = lut[h >> 8];
-        } else {
-            lo = make_uint2(nibble_to_bytes(h & 15u), nibble_to_bytes((h >> 4) & 15u));
-            hi = make_uint2(nibble_to_bytes((h >> 8) & 15u), nibble_to_bytes(h >> 12));
-        }
+        for (int c = c_lo + lane; c < c_hi; c += 32) {
+            const uint32_t w = stream[c];
+            uint2 q0, q1, q2, q3;
+            if (USE_LUT && lut_built) {
+                q0 = lut[w & 0xFFu]; q1 = lut[(w >> 8) & 0xFFu]; q2 = lut[(w >> 16) & 0xFFu]; q3 = lut[w >> 24];
+            } else {
+                q0 = make_uint2(nibble_to_bytes(w & 15u), nibble_to_bytes((w >> 4) & 15u));
+                q1 = make_uint2(nibble_to_bytes((w >> 8) & 15u), nibble_to_bytes((w >> 12) & 15u));
+                q2 = make_uint2(nibble_to_bytes((w >> 16) & 15u), nibble_to_bytes((w >> 20) & 15u));
+                q3 = make_uint2(nibble_to_bytes((w >> 24) & 15u), nibble_to_bytes(w >> 28));
+            }
 #ifndef WAB_EXP_NOSTORE
-        __stcs(reinterpret_cast<uint4*>(gA) + c, make_uint4(lo.x, lo.y, hi.x, hi.y));
+            st_cs_256(gA + 32 * c, q0, q1, q2, q3);
 #else
-        if (lo.x == 0xdeadbeefu) gA[0] = (uint8_t)hi.y;
+            if (q0.x == 0xdeadbeefu) gA[0] = (uint8_t)q3.y;
 #endif
+        }
+    } else {
+        const uint16_t* hs = reinterpret_cast<const uint16_t*>(stream);
+#pragma unroll kFlushUnroll
+        for (int c = c_lo + lane; c < c_hi; c += 32) {
+            const uint32_t h = hs[c];
+            uint2 lo, hi;
+            if (USE_LUT && lut_built) {
+                lo = lut[h & 0xFFu]; hi = lut[h >> 8];
+            } else {
+                lo = make_uint2(nibble_to_bytes(h & 15u), nibble_to_bytes((h >> 4) & 15u));
+                hi = make_uint2(nibble_to_bytes((h >> 8) & 15u), nibble_to_bytes(h >> 12));
+            }
+#ifndef WAB_EXP_NOSTORE
+            __stcs(reinterpret_cast<uint4*>(gA) + c, make_uint4(lo.x, lo.y, hi.x, hi.y));
+#else
+            if (lo.x == 0xdeadbeefu) gA[0] = (uint8_t)hi.y;
+#endif
+        }
     }
-    if (lane < 16) {                                              // ragged head and tail, one byte per lane
-        const int head_end = min(c_lo << 4, end);
+    if (lane < CH) {                                              // ragged head and tail, one byte per lane
+        const int head_end = min(c_lo << SH, end);
         const int hb = off + lane;
         if (hb < head_end) gA[hb] = (uint8_t)((stream[hb >> 5] >> (hb & 31)) & 1u);
-        const int tb = max(c_hi << 4, head_end) + lane;
+        const int tb = max(c_hi << SH, head_end) + lane;
         if (tb < end) gA[tb] = (uint8_t)((stream[tb >> 5] >> (tb & 31)) & 1u);
     }
 }
@@ -321,7 +361,7 @@ template <int LPE>
 __device__ __forceinline__ void emit_obs(uint32_t* stream, const uint2* lut, const Ctx& c, uint8_t* grids,
                                          int64_t first_byte, const uint32_t wm[4], const uint32_t bm[4], bool lut_built = true) {
     constexpr int EPW = Geo<LPE>::EPW;
-    const int off = (int)(first_byte & 15);
+    const int off = obs_align_off(grids + first_byte);
     const int total = off + EPW * OBS_BYTES;
     if (c.sub == 0)
         stream_put(stream, off + OBS_BYTES * c.slot, c.slot == EPW - 1, total, wm, bm, c.active);
@@ -564,7 +604,7 @@ wab_step_chunk_kernel(const __grid_constant__ Params P, const StatePtrs st, cons
             for (int sf = 0; sf < Sn; ++sf) {
                 const int64_t fbs = ((int64_t)(t0 + sf) * n + c.warp_first) * OBS_BYTES;
                 const int offs = (int)(fbs & 15);
-                stream_flush<false>(streams + sf * SW, nullptr, out.grids + (fbs - offs), offs, offs + OBS_BYTES * c.n_valid, c.lane);
+                stream_flush<false, false>(streams + sf * SW, nullptr, out.grids + (fbs - offs), offs, offs + OBS_BYTES * c.n_valid, c.lane);
             }
             __syncwarp();
         }
@@ -727,7 +767,7 @@ wab_step_pipe_kernel(const __grid_constant__ Params P, const StatePtrs st, const
         for (int t = 0; t < n_steps; ++t, o += n, first_byte += n * OBS_BYTES) {
             const int s = t & (D - 1);
             pipe_mbar_wait(full + s, (uint32_t)(t / D) & 1u);   // step t is in the slot
-            const int off = (int)(first_byte & 15);
+            const int off = obs_align_off(out.grids + first_byte);
             uint4 sc = make_uint4(0u, 0u, 0u, 0u);
             StepOut O;
             if (lane < EPW) {
