@@ -270,6 +270,23 @@ WAB_HD uint32_t alive_after(const Params& P, uint32_t word, uint32_t eats) {
     return word >= P.bush_thr[eats] ? 1u : 0u;
 #endif
 }
+// The eat path's form of alive_after: the threshold of `eats` eats is settled on the HIGH half-word of the eaten cell's draw
+// (one Philox2x32 call, in line) unless it ties with the threshold's high half (2^-16 per eat: the second call, which
+// supplies the low half-word, then runs out of line). Same result as alive_after(P, bush_word(...), eats).
+WAB_HD uint32_t eaten_bush_alive(const Params& P, const Env& E, int32_t x, int32_t y, uint32_t eats) {
+    if (eats >= P.n_bush_thr) return 0u;
+#if defined(__CUDA_ARCH__)
+    const uint32_t thr = eats == 1u ? P.thr_bush2 : __ldg(P.bush_thr + eats);
+#else
+    const uint32_t thr = eats == 1u ? P.thr_bush2 : P.bush_thr[eats];
+#endif
+    const uint32_t c0 = pack_xy(x >> 1, y >> 1) ^ E.bk_a, lane = bush_lane(x, y);
+    uint32_t p[2];
+    philox2(P, c0, E.bk_b, p);
+    const uint32_t hi = half_of((lane & 2u) ? p[1] : p[0], half_sel(lane & 1u)), thi = thr >> 16;
+    if (hi != thi) return hi > thi ? 1u : 0u;
+    return bush_word_rare(c0, E.bk_b, P.rk2[0], lane) >= thr ? 1u : 0u;
+}
 // bush at (x, y) — known to exist at first reveal — still has food? (rare path: only when something was eaten empty)
 WAB_HD uint32_t bush_alive(const Params& P, const Env& E, const Slots& S, int32_t x, int32_t y) {
     if (!E.dep) return 1u;                      // nothing has been eaten empty this episode
@@ -635,12 +652,12 @@ WAB_HD void env_step_impl(const Params& P, Env& E, const Slots& S, uint32_t acti
         } else {
             eats = 1u; O.overflow = 1u;            // counted, never silent (WAB_STAT_OVERFLOWS)
         }
-#ifdef WAB_EAT_RARE   /* tuning A/B only */
-        const uint32_t eaten_word = bush_word(P, E, E.x, E.y);
+#ifdef WAB_EAT_FULLWORD   /* tuning A/B only: both Philox2x32 calls of the cell in line, then the full compare */
+        const uint32_t still = alive_after(P, bush_word_inline(P, E, E.x, E.y), eats);
 #else
-        const uint32_t eaten_word = bush_word_inline(P, E, E.x, E.y);
+        const uint32_t still = eaten_bush_alive(P, E, E.x, E.y, eats);
 #endif
-        if (!alive_after(P, eaten_word, eats)) { E.m[1] &= ~(1u << 28); E.dep = 1u; E.stale = 1u; }
+        if (!still) { E.m[1] &= ~(1u << 28); E.dep = 1u; E.stale = 1u; }
     }
 
     // ---- :316-322 hunger, starvation (overrides killed)

@@ -432,10 +432,14 @@ wab_affine1_tc_kernel(const __grid_constant__ Params P, const uint8_t* __restric
         if (MODE == 2) {
             // ---- the tail: x = clamp(leaky_relu(z3)); the A + 1 head rows as two 64-term partial sums per row (the two threads
             // of a row meet in shared memory — the operand area is free now); softmax; inverse-CDF sample on one keyed uniform
-            float* wsm = reinterpret_cast<float*>(tc_smem);               // [A + 1][128]
-            float* partial = wsm + 9 * 128;                               // [128 rows][2 halves][9]
+            // head weights transposed and zero-padded to [128][12]: the 9 weights of an input are three 16-byte broadcast loads
+            float* wsm = reinterpret_cast<float*>(tc_smem);               // [128][12]
+            float* partial = wsm + 12 * 128;                              // [128 rows][2 halves][9]
             const int n_out = tw.n_actions + 1;
-            for (int k = tid; k < n_out * 128; k += 256) wsm[k] = tw.w_heads[k];
+            for (int k = tid; k < 12 * 128; k += 256) {
+                const int i = k / 12, o = k - 12 * i;
+                wsm[k] = o < n_out ? tw.w_heads[o * 128 + i] : 0.f;
+            }
             __syncthreads();
             float acc[9];
 #pragma unroll
@@ -445,9 +449,11 @@ wab_affine1_tc_kernel(const __grid_constant__ Params P, const uint8_t* __restric
                 float v = z3[i];
                 v = v > 0.f ? v : v * slope;                              // F.leaky_relu, :92
                 v = fminf(fmaxf(v, tw.clamp_lo), tw.clamp_hi);            // torch.clamp(x, -4, 4), :93
-#pragma unroll
-                for (int o = 0; o < 9; ++o)
-                    if (o < n_out) acc[o] = fmaf(v, wsm[o * 128 + h * 64 + i], acc[o]);
+                const float4* wrow = reinterpret_cast<const float4*>(wsm + (h * 64 + i) * 12);
+                const float4 w0 = wrow[0], w1 = wrow[1], w2 = wrow[2];
+                acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]); acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+                acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]); acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+                acc[8] = fmaf(v, w2.x, acc[8]);
             }
 #pragma unroll
             for (int o = 0; o < 9; ++o) partial[(r * 2 + h) * 9 + o] = acc[o];
