@@ -55,6 +55,14 @@ constexpr int T2_KC = 32;                                  // layers 2 and 3: K 
 constexpr int T2_A_PART = TC_TILE_M * T2_KC * 2;           // 8 KB: one part of a 128-row operand chunk
 constexpr int T2_B160_PART = 160 * T2_KC * 2;              // 10 KB: one part of a 160-row weight chunk
 
+// 16-byte asynchronous global -> shared copy (LDGSTS) and the wait for all of this thread's copies
+__device__ __forceinline__ void tc_cp_async16(uint32_t s_dst, const void* g_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s_dst), "l"(g_src) : "memory");
+}
+__device__ __forceinline__ void tc_cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
@@ -242,6 +250,15 @@ wab_affine1_tc_kernel(const __grid_constant__ Params P, const uint8_t* __restric
 #pragma unroll
             for (int s = 0; s < 4; ++s) x[s][e] = scale * (float)(w[s] >> 8);
         }
+        // The MMAs of the previous chunk (issued before this chunk's Philox calls started) have read both operand buffers by
+        // now: start the asynchronous copy of this chunk's weights — 48 KB already in operand layout, 12 copies of 16 bytes per
+        // thread, all in flight at once — and build the A operand's bf16 parts while it runs.
+        if (c > 0) { tc_mbar_wait(s_bar, parity); parity ^= 1u; }
+        {
+            const uint4* src = wpacked + (size_t)c * (3 * TC_PART_BYTES / 16);
+#pragma unroll
+            for (int k = tid; k < 3 * TC_PART_BYTES / 16; k += 256) tc_cp_async16(s_b + (uint32_t)k * 16u, src + k);
+        }
         uint32_t pk[3][4][4];                             // [part][s][word of the 16-byte vector]
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
@@ -257,20 +274,13 @@ wab_affine1_tc_kernel(const __grid_constant__ Params P, const uint8_t* __restric
                 pk[2][s][e2] = tc_pack_bf16x2(ra, rb);
             }
         }
-        if (c > 0) { tc_mbar_wait(s_bar, parity); parity ^= 1u; }    // the MMAs of the previous chunk have read the operands
 #pragma unroll
         for (int p = 0; p < 3; ++p)
 #pragma unroll
             for (int s = 0; s < 4; ++s)
                 asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(s_a + p * TC_PART_BYTES + a_row + (uint32_t)(h * 4 + s) * 128u),
                              "r"(pk[p][s][0]), "r"(pk[p][s][1]), "r"(pk[p][s][2]), "r"(pk[p][s][3]) : "memory");
-        // ---- B: the chunk's three weight parts, 48 KB already in operand layout
-        const uint4* src = wpacked + (size_t)c * (3 * TC_PART_BYTES / 16);
-#pragma unroll 4
-        for (int k = tid; k < 3 * TC_PART_BYTES / 16; k += 256) {
-            const uint4 v = src[k];
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(s_b + (uint32_t)k * 16u), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-        }
+        tc_cp_async_wait_all();                                        // the weight chunk has landed
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core's reads
         __syncthreads();
         if (tid == 0) {
@@ -340,11 +350,9 @@ wab_affine1_tc_kernel(const __grid_constant__ Params P, const uint8_t* __restric
             asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(dst + 2 * T2_A_PART), "r"(p2[0]), "r"(p2[1]), "r"(p2[2]), "r"(p2[3]) : "memory");
         };
         auto copy_b = [&](const uint4* src, int n16) {                   // the chunk's three weight parts, already in operand layout
-#pragma unroll 4
-            for (int k = tid; k < n16; k += 256) {
-                const uint4 v = src[k];
-                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(s_b2 + (uint32_t)k * 16u), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-            }
+#pragma unroll 8
+            for (int k = tid; k < n16; k += 256) tc_cp_async16(s_b2 + (uint32_t)k * 16u, src + k);
+            tc_cp_async_wait_all();
         };
         auto issue = [&](uint32_t b_part, uint32_t idesc, bool first) {  // one chunk: 2 K steps x 6 products, then commit
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
