@@ -140,6 +140,10 @@ int wab_vec_step_host(WabVec *h, const uint8_t *h_actions, uint8_t *h_grids, uin
  * (no staging copy); either way the block is complete when the call returns. */
 int wab_vec_host_block_layout(const WabVec *h, int64_t *offsets7, int64_t *total_bytes);
 int wab_vec_step_host_packed(WabVec *h, const uint8_t *h_actions, uint8_t *h_block, void *stream);
+/* The host-buffer entry points remember, by host address, what they resolved for the caller's buffers (the device
+ * aliases of pinned memory, the captured copy-step-copy graph). Call this before freeing or unregistering a buffer that
+ * was passed to them: a later allocation at the same address must not inherit a stale alias. */
+int wab_vec_forget_host_buffers(WabVec *h);
 int wab_vec_reset_host(WabVec *h, uint8_t *h_grids, uint8_t *h_food, uint8_t *h_role, uint8_t *h_status,
                        void *stream);
 

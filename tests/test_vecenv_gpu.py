@@ -288,6 +288,19 @@ def test_host_buffer_path_and_masked_reset(mapped, monkeypatch):
     a.step_host(loose)
     o, r, d, i = b.step(torch.from_numpy(acts).cuda())
     assert np.array_equal(loose["grids"].numpy(), o.grids.cpu().numpy()) and np.array_equal(loose["reward"].numpy(), r.cpu().numpy())
+    # buffers handed back (the library forgets its cached aliases / graph for their addresses), fresh ones — at an odd
+    # offset inside a pinned allocation, so the block is NOT 16-byte aligned and the mapped path must stand down — work too
+    from wab_gym_b200 import _lib
+    a.free_host_buffers(hb)
+    assert not hb
+    hb2 = a.alloc_host_buffers(pinned=True)
+    odd = torch.empty(hb2["block"].numel() + 64, dtype=torch.uint8).pin_memory()
+    for blk in (hb2["block"], odd[4:4 + hb2["block"].numel()]):
+        acts = rng.integers(0, 5, n).astype(np.uint8)
+        hb2["actions"].copy_(torch.from_numpy(acts))
+        _lib.check(a.lib.wab_vec_step_host_packed(a._h, hb2["actions"].data_ptr(), blk.data_ptr(), a._stream()))
+        o, r, d, i = b.step(torch.from_numpy(acts).cuda())
+        assert np.array_equal(blk[:o.grids.numel()].numpy().reshape(o.grids.shape), o.grids.cpu().numpy())
     # masked reset: only the selected envs start a new episode
     before = b.export_state()
     prev = [t.cpu().numpy().copy() for t in o]

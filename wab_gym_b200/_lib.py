@@ -17,7 +17,7 @@ EXPORTS = [
     "wab_vec_create", "wab_vec_reset", "wab_vec_step", "wab_vec_step_many", "wab_vec_step_host",
     "wab_vec_reset_host", "wab_vec_stats", "wab_vec_stats_device", "wab_vec_export_state", "wab_vec_num_envs", "wab_vec_lanes_per_env", "wab_vec_step_many_pipelined", "wab_vec_kernel_kind",
     "wab_vec_destroy", "wab_philox_device", "wab_vec_bind_features", "wab_pragmatic_features",
-    "wab_vec_flatten_features", "wab_vec_flatten_features_noisy", "wab_sample_categorical", "wab_policy_tail", "wab_vec_enable_ego", "wab_vec_ego_proximities", "wab_vec_flat_dim", "wab_vec_host_block_layout", "wab_vec_step_host_packed",
+    "wab_vec_flatten_features", "wab_vec_flatten_features_noisy", "wab_sample_categorical", "wab_policy_tail", "wab_vec_enable_ego", "wab_vec_ego_proximities", "wab_vec_flat_dim", "wab_vec_host_block_layout", "wab_vec_step_host_packed", "wab_vec_forget_host_buffers",
     "wab_policy_affine1_packed_bytes", "wab_policy_affine1_prepare", "wab_policy_affine1", "wab_policy_linear_packed_bytes", "wab_policy_linear_prepare", "wab_policy_trunk", "wab_policy_forward", "wab2_create", "wab2_kernel_kind", "wab2_output_layout", "wab2_reset", "wab2_turn", "wab2_export_state", "wab2_import_state", "wab2_destroy", "wab_last_error", "wab_abi_version",
 ]
 
@@ -59,6 +59,7 @@ def load():
     L.wab_vec_reset_host.argtypes = [vp] * 6
     L.wab_vec_host_block_layout.argtypes = [vp, vp, vp]
     L.wab_vec_step_host_packed.argtypes = [vp, vp, vp, vp]
+    L.wab_vec_forget_host_buffers.argtypes = [vp]
     L.wab_vec_stats.argtypes = [vp, vp, i32, vp]
     L.wab_vec_stats_device.argtypes = [vp, vp, vp]
     L.wab_vec_export_state.argtypes = [vp] * 14

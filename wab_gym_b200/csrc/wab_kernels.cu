@@ -1577,8 +1577,11 @@ int wab_vec_step_host_packed(WabVec* h, const uint8_t* h_actions, uint8_t* h_blo
         if (h->m_actions != h_actions || h->m_block != h_block) {      // resolve the device aliases once per buffer pair
             cudaPointerAttributes pa, pb;
             h->m_actions = h_actions; h->m_block = h_block; h->m_dactions = nullptr; h->m_dblock = nullptr;
+            // the kernel's 16-byte observation stores align themselves to any address, its f32 reward stores need the
+            // block's 256-byte-aligned offsets to stay 4-byte aligned: a block that is not 16-byte aligned takes the staged path
             if (cudaPointerGetAttributes(&pa, h_actions) == cudaSuccess && cudaPointerGetAttributes(&pb, h_block) == cudaSuccess &&
-                pa.type == cudaMemoryTypeHost && pb.type == cudaMemoryTypeHost && pa.devicePointer && pb.devicePointer) {
+                pa.type == cudaMemoryTypeHost && pb.type == cudaMemoryTypeHost && pa.devicePointer && pb.devicePointer &&
+                ((uintptr_t)pb.devicePointer & 15u) == 0) {
                 h->m_dactions = (const uint8_t*)pa.devicePointer; h->m_dblock = (uint8_t*)pb.devicePointer;
             } else {
                 cudaGetLastError();                // pageable memory: staged copies below
@@ -1626,6 +1629,18 @@ int wab_vec_step_host_packed(WabVec* h, const uint8_t* h_actions, uint8_t* h_blo
     if (int rc = launch_step(h, 1, b + L.actions, obs, (float*)(b + L.reward), b + L.done, b + L.info, s)) return rc;
     WAB_CUDA(cudaMemcpyAsync(h_block, b + L.grids, L.total - L.grids, cudaMemcpyDeviceToHost, s));   // one transfer
     WAB_CUDA(cudaStreamSynchronize(s));
+    return WAB_OK;
+}
+
+// The host-buffer entry points cache what they resolved for the caller's buffers (device aliases of pinned memory, the
+// captured copy-step-copy graph) by host address. A buffer that is freed or unregistered must be forgotten first: another
+// allocation at the same address would otherwise inherit a stale alias.
+int wab_vec_forget_host_buffers(WabVec* h) {
+    if (!h) return fail(WAB_E_NULL, "null handle");
+    DeviceGuard guard(h->device);
+    h->m_actions = nullptr; h->m_block = nullptr; h->m_dactions = nullptr; h->m_dblock = nullptr;
+    h->g_actions = nullptr; h->g_block = nullptr; h->g_features = nullptr;
+    if (h->host_graph) { cudaGraphExecDestroy(h->host_graph); h->host_graph = nullptr; }
     return WAB_OK;
 }
 

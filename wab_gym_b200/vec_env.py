@@ -279,6 +279,12 @@ class VecEnv:
                                                   _ptr(hb["done"]), _ptr(hb["info"]), self._stream()))
         return hb
 
+    def free_host_buffers(self, hb: dict):
+        """Drop host buffers from ``alloc_host_buffers``: the library forgets what it cached for their addresses (device
+        aliases of the pinned block, the captured host-step graph) before the memory goes back to the allocator."""
+        _lib.check(self.lib.wab_vec_forget_host_buffers(self._h))
+        hb.clear()
+
     def reset_host(self, hb: dict):
         self._bind({})
         _lib.check(self.lib.wab_vec_reset_host(self._h, _ptr(hb["grids"]), _ptr(hb["food"]), _ptr(hb["role"]),
