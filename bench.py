@@ -513,6 +513,22 @@ def rollout_leg(ctx, n, K, min_ms):
         ms2 = ctx.max_over_ranks(e0.elapsed_time(e1))
         lib = {"value": ctx.world * n * s2 / (ms2 * 1e-3), "ms_per_step": ms2 / s2, "steps": s2, "path": ro2.describe()}
         env2.close()
+    # and with FEATURES-ONLY stepping (VecEnv(emit_grids=False)): the policy consumes the 28 feature bytes, so the 363-byte
+    # one-hot grids need not be materialised in HBM at all — reported beside the headline, which writes them
+    fo = None
+    try:
+        env3 = VecEnv(n, seed=ctx.args.seed, device=ctx.dev, env_id_base=ctx.rank * n, features=True, emit_grids=False)
+        ro3 = Rollout(env3, Policy(env3.flat_dim, env3.n_actions), use_graph=True, dtype=torch.float32)
+        ro3.run(10)
+        ctx.barrier()
+        e0.record(); ro3.run(steps); e1.record()
+        ctx.barrier()
+        ms3 = ctx.max_over_ranks(e0.elapsed_time(e1))
+        fo = {"value": ctx.world * n * steps / (ms3 * 1e-3), "ms_per_step": ms3 / steps, "steps": steps,
+              "path": "same loop, wab_step_kernel with d_grids = NULL: features, scalars, reward, done, info only"}
+        env3.close()
+    except Exception as exc:
+        fo = {"error": "%s: %s" % (type(exc).__name__, exc)}
     flops = 2.0 * (env.flat_dim * 128 + 128 * 150 + 150 * 128 + 128 * (env.n_actions + 1))
     v = n * steps / (ms * 1e-3)
     return {"workload": "configs[4]: actor_critic.py rollout, policy %d-128-150-128-{%d,1} fp32 in the loop, %d v1 envs per GPU" % (
@@ -520,7 +536,7 @@ def rollout_leg(ctx, n, K, min_ms):
             "value": ctx.world * v, "unit": "env-steps/s", "ms_per_step": ms / steps, "window_ms": ms, "steps": steps,
             "dtype": ("fp32 policy (fp32-accurate on the tensor cores: bf16 x 3 operand splits, fp32 accumulation; "
                       "tests/test_rollout_gpu.py holds it to 3e-6 of the fp64 result)") if tc else "fp32 policy",
-            "num_envs_per_gpu": n, "global_envs": ctx.world * n, "path": desc, "library_path": lib,
+            "num_envs_per_gpu": n, "global_envs": ctx.world * n, "path": desc, "library_path": lib, "features_only": fo,
             "policy_flops_per_env_step": flops, "policy_tflops": v * flops / 1e12,
             "mean_episode_length": st["steps"] / max(st["episodes"], 1)}
 

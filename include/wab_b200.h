@@ -82,7 +82,10 @@ typedef struct WabConfig {
 /* Observation batch: the first six elements of the reference's tuple (wab_env.py:374-385) for N
  * envs. The seventh (view_mask) is a function of role and options only. */
 typedef struct WabObs {
-    uint8_t *d_grids;  /* [N][3][11][11] u8: wolves, bushes, ostriches; cell [i][j] = [5-dx][5-dy] */
+    uint8_t *d_grids;  /* [N][3][11][11] u8: wolves, bushes, ostriches; cell [i][j] = [5-dx][5-dy]. May be NULL in
+                        * wab_vec_reset / wab_vec_step / wab_vec_step_many while a feature buffer is bound
+                        * (wab_vec_bind_features): FEATURES-ONLY stepping — the 28 PragmaticObsWrapper bytes per env, the
+                        * scalars, reward, done and info are written, the one-hot grids are not materialised. */
     uint8_t *d_food;   /* [N] ceil(food * turns_to_empty_food)                     wab_env.py:452  */
     uint8_t *d_role;   /* [N]                                                      wab_env.py:390  */
     uint8_t *d_status; /* [N] 0 alive, 1 starved, 2 killed                         wab_env.py:387  */

@@ -669,3 +669,36 @@ def test_two_warp_pipeline_equals_single_steps(lpe, name, monkeypatch):
             assert np.array_equal(sa[k], sb[k]) and np.array_equal(sa[k], sc[k]), (lpe, name, T, k)
     assert a.stats() == b.stats() == c.stats() and a.stats()["bad_actions"] == 5
     a.close(); b.close(); c.close()
+
+
+@pytest.mark.parametrize("lpe", [1, 8, 32])
+def test_features_only_stepping_equals_full_stepping(lpe, monkeypatch):
+    """VecEnv(emit_grids=False): the kernels get d_grids = NULL and never materialise the one-hot grids; the 28 feature
+    bytes, scalars, reward, done, info, the statistics and the hidden state equal those of a batch that writes them —
+    single-step launches, multi-step launches (pipeline kernel included) and resets."""
+    monkeypatch.setenv("WAB_LPE", str(lpe))
+    n, seed = 77, 5
+    full = _vec(n, OPTION_SETS["dense"][0], seed=seed, features=True, wolf_cap=64)
+    lean = _vec(n, OPTION_SETS["dense"][0], seed=seed, features=True, wolf_cap=64, emit_grids=False)
+    of, ol = full.reset(), lean.reset()
+    assert ol.grids is None and torch.equal(full.last_features, lean.last_features)
+    for x, y in zip(of[1:], ol[1:]):
+        assert torch.equal(x, y)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    for t in range(30):
+        a = torch.randint(0, full.n_actions, (n,), dtype=torch.uint8, device="cuda", generator=gen)
+        (of, rf, df, jf), (ol, rl, dl, jl) = full.step(a), lean.step(a)
+        assert torch.equal(jf["features"], jl["features"]) and torch.equal(rf, rl) and torch.equal(df, dl) and torch.equal(jf["info"], jl["info"])
+        assert torch.equal(of.food, ol.food) and torch.equal(of.role, ol.role) and torch.equal(of.status, ol.status)
+    for T in (3, 24):
+        acts = torch.randint(0, full.n_actions, (T, n), dtype=torch.uint8, device="cuda", generator=gen)
+        (of, rf, df, jf), (ol, rl, dl, jl) = full.step_many(acts), lean.step_many(acts)
+        assert ol.grids is None
+        assert torch.equal(jf["features"], jl["features"]) and torch.equal(rf, rl) and torch.equal(df, dl) and torch.equal(jf["info"], jl["info"])
+    sf, sl = full.export_state(), lean.export_state()
+    for k in sf:
+        assert np.array_equal(sf[k], sl[k]), k
+    assert full.stats() == lean.stats()
+    with pytest.raises(ValueError):
+        _vec(8, seed=1, emit_grids=False)               # no feature buffer to write instead
+    full.close(); lean.close()

@@ -438,7 +438,7 @@ wab_step_kernel(const __grid_constant__ Params P, const StatePtrs st, const uint
             if (out.features) write_features(out.features, o, O);
         }
 #ifndef WAB_EXP_NOEMIT
-        emit_obs<LPE>(stream, lut, c, out.grids, first_byte, O.wm, O.bm, lut_built);
+        if (out.grids) emit_obs<LPE>(stream, lut, c, out.grids, first_byte, O.wm, O.bm, lut_built);   // null: features-only stepping
 #endif
     }
     if (c.writer) store_env<F64>(st, c.idx, E, wolves_s, EPB);
@@ -581,7 +581,7 @@ wab_step_chunk_kernel(const __grid_constant__ Params P, const StatePtrs st, cons
                 const uint4* r = reinterpret_cast<const uint4*>(res + me * RES);
                 const uint4 w4 = r[0], b4 = r[1], sc = r[2];
                 const uint32_t wm[4] = {w4.x, w4.y, w4.z, w4.w}, bm[4] = {b4.x, b4.y, b4.z, b4.w};
-                stream_put(streams + s3 * SW, off3 + OBS_BYTES * c.slot, c.slot == EPW - 1, off3 + EPW * OBS_BYTES, wm, bm, c.active);
+                if (out.grids) stream_put(streams + s3 * SW, off3 + OBS_BYTES * c.slot, c.slot == EPW - 1, off3 + EPW * OBS_BYTES, wm, bm, c.active);
                 if (c.active) {
                     const int64_t o3 = (int64_t)(t0 + s3) * n + c.idx;
                     out.food[o3] = (uint8_t)(sc.x & 0xFFu);
@@ -601,7 +601,7 @@ wab_step_chunk_kernel(const __grid_constant__ Params P, const StatePtrs st, cons
             }
             __syncwarp();
 #pragma unroll 1
-            for (int sf = 0; sf < Sn; ++sf) {
+            for (int sf = 0; sf < (out.grids ? Sn : 0); ++sf) {
                 const int64_t fbs = ((int64_t)(t0 + sf) * n + c.warp_first) * OBS_BYTES;
                 const int offs = (int)(fbs & 15);
                 stream_flush<false, false>(streams + sf * SW, nullptr, out.grids + (fbs - offs), offs, offs + OBS_BYTES * c.n_valid, c.lane);
@@ -776,7 +776,7 @@ wab_step_pipe_kernel(const __grid_constant__ Params P, const StatePtrs st, const
                 sc = *reinterpret_cast<const uint4*>(r + 8);
                 O.wm[0] = w.x; O.wm[1] = w.y; O.wm[2] = w.z; O.wm[3] = w.w;
                 O.bm[0] = b.x; O.bm[1] = b.y; O.bm[2] = b.z; O.bm[3] = b.w;
-                stream_put(stream, off + OBS_BYTES * lane, lane == EPW - 1, off + EPW * OBS_BYTES, O.wm, O.bm, mine);
+                if (out.grids) stream_put(stream, off + OBS_BYTES * lane, lane == EPW - 1, off + EPW * OBS_BYTES, O.wm, O.bm, mine);
             }
             __syncwarp();                                   // every read of the slot has landed in registers or the stream
             if (lane == 0) pipe_mbar_arrive(empty + s);     // the slot is free for step t + D
@@ -787,7 +787,7 @@ wab_step_pipe_kernel(const __grid_constant__ Params P, const StatePtrs st, const
                 if (out.features) write_features(out.features, o, O);
             }
 #ifndef WAB_EXP_NOEMIT
-            stream_flush<false>(stream, nullptr, out.grids + (first_byte - off), off, off + OBS_BYTES * n_valid, lane);
+            if (out.grids) stream_flush<false>(stream, nullptr, out.grids + (first_byte - off), off, off + OBS_BYTES * n_valid, lane);
 #endif
             __syncwarp();
         }
@@ -835,7 +835,7 @@ wab_reset_kernel(const __grid_constant__ Params P, const StatePtrs st, const uin
         cnt[WAB_STAT_OVERFLOWS] += O.overflow;
         store_env<F64>(st, c.idx, E, wolves_s, EPB);
     }
-    emit_obs<LPE>(stream, lut, c, out.grids, c.warp_first * OBS_BYTES, O.wm, O.bm, lut_built);
+    if (out.grids) emit_obs<LPE>(stream, lut, c, out.grids, c.warp_first * OBS_BYTES, O.wm, O.bm, lut_built);
     flush_stats(st.wstats, cnt);
 }
 
@@ -1342,6 +1342,17 @@ int pick_mb(const WabVec* h) {
         }                                                                                      \
     } while (0)
 
+// d_grids may be NULL for FEATURES-ONLY stepping: a PragmaticObsWrapper feature buffer is bound (wab_vec_bind_features) and
+// the caller — the reference's actor-critic consumes nothing else (actor_critic.py:42, :188) — does not want the 363-byte
+// one-hot grids materialised in HBM. Specialised 11 x 11 kernels only.
+int check_grids(const WabVec* h, const uint8_t* d_grids) {
+    if (!d_grids) {
+        if (h->generic || !h->d_features) return fail(WAB_E_NULL, "d_grids may only be null with a bound feature buffer (wab_vec_bind_features)");
+        return WAB_OK;
+    }
+    return check_ptr_align(d_grids, "d_grids");
+}
+
 int launch_step(WabVec* h, int n_steps, const uint8_t* d_actions, const WabObs& obs, float* d_reward,
                 uint8_t* d_done, uint8_t* d_info, cudaStream_t s, int lpe = 0) {
     OutPtrs out{obs.d_grids, obs.d_food, obs.d_role, obs.d_status, d_reward, d_done, d_info, h->d_features};
@@ -1483,8 +1494,8 @@ int wab_vec_lanes_per_env(const WabVec* h) { return h ? (h->generic ? 32 : h->lp
 int wab_vec_step_many_pipelined(const WabVec* h, int32_t n_steps) { return h && use_pipeline(h, h->lpe, n_steps) ? 1 : 0; }
 
 int wab_vec_reset(WabVec* h, const uint8_t* d_mask, WabObs obs, void* stream) {
-    if (!h || !obs.d_grids || !obs.d_food || !obs.d_role || !obs.d_status) return fail(WAB_E_NULL, "null argument");
-    if (int rc = check_ptr_align(obs.d_grids, "d_grids")) return rc;
+    if (!h || !obs.d_food || !obs.d_role || !obs.d_status) return fail(WAB_E_NULL, "null argument");
+    if (int rc = check_grids(h, obs.d_grids)) return rc;
     DeviceGuard guard(h->device);
     OutPtrs out{obs.d_grids, obs.d_food, obs.d_role, obs.d_status, nullptr, nullptr, nullptr, h->d_features};
     cudaStream_t s = (cudaStream_t)stream;
@@ -1505,19 +1516,19 @@ int wab_vec_reset(WabVec* h, const uint8_t* d_mask, WabObs obs, void* stream) {
 
 int wab_vec_step(WabVec* h, const uint8_t* d_actions, WabObs obs, float* d_reward, uint8_t* d_done,
                  uint8_t* d_info, void* stream) {
-    if (!h || !d_actions || !obs.d_grids || !obs.d_food || !obs.d_role || !obs.d_status || !d_reward || !d_done)
+    if (!h || !d_actions || !obs.d_food || !obs.d_role || !obs.d_status || !d_reward || !d_done)
         return fail(WAB_E_NULL, "null argument");
-    if (int rc = check_ptr_align(obs.d_grids, "d_grids")) return rc;
+    if (int rc = check_grids(h, obs.d_grids)) return rc;
     DeviceGuard guard(h->device);
     return launch_step(h, 1, d_actions, obs, d_reward, d_done, d_info, (cudaStream_t)stream);
 }
 
 int wab_vec_step_many(WabVec* h, int32_t n_steps, const uint8_t* d_actions, WabObs obs, float* d_reward,
                       uint8_t* d_done, uint8_t* d_info, void* stream) {
-    if (!h || !d_actions || !obs.d_grids || !obs.d_food || !obs.d_role || !obs.d_status || !d_reward || !d_done)
+    if (!h || !d_actions || !obs.d_food || !obs.d_role || !obs.d_status || !d_reward || !d_done)
         return fail(WAB_E_NULL, "null argument");
     if (n_steps < 1 || n_steps > 65535) return fail(WAB_E_CONFIG, "n_steps must be in [1, 65535]");
-    if (int rc = check_ptr_align(obs.d_grids, "d_grids")) return rc;
+    if (int rc = check_grids(h, obs.d_grids)) return rc;
     DeviceGuard guard(h->device);
     return launch_step(h, n_steps, d_actions, obs, d_reward, d_done, d_info, (cudaStream_t)stream);
 }

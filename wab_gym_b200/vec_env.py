@@ -45,7 +45,7 @@ def _ptr(t: Optional[torch.Tensor]):
 class VecEnv:
     def __init__(self, num_envs: int, game_options: Optional[dict] = None, device="cuda", seed: int = 0,
                  env_id_base: int = 0, auto_reset: bool = True, wolf_cap: int = 16, log_cap: Optional[int] = None,
-                 force_f64_food: bool = False, features: bool = False, ego: bool = False):
+                 force_f64_food: bool = False, features: bool = False, ego: bool = False, emit_grids: bool = True):
         self._h = None
         self._bound = None     # feature buffer currently bound in the handle
         self.lib = _lib.load()  # raises if the CUDA library is unavailable — no fallback
@@ -77,6 +77,12 @@ class VecEnv:
         if ego:      # egocentric observation family: the kernels keep every episode's position history
             _lib.check(self.lib.wab_vec_enable_ego(self._h))
         self.with_features = bool(features)
+        #: emit_grids=False (needs features=True): FEATURES-ONLY stepping — the kernels write the 28 PragmaticObsWrapper bytes,
+        #: scalars, reward, done and info per env and never materialise the 363-byte one-hot grids (ObsBatch.grids is None):
+        #: what the reference's actor-critic consumes (actor_critic.py:42, :188) at a thirteenth of the output traffic
+        self.emit_grids = bool(emit_grids)
+        if not self.emit_grids and (not self.with_features or self.generic_kernels):
+            raise ValueError("emit_grids=False needs features=True and the default 11 x 11 viewport")
         self.flat_dim = int(self.lib.wab_vec_flat_dim(self._h))
         self._out = self._alloc(None)
         self._many: Dict[int, dict] = {}
@@ -89,7 +95,7 @@ class VecEnv:
         extra = {"features": torch.empty(lead + (28,), **u8)} if self.with_features else {}
         return {
             **extra,
-            "grids": torch.empty(lead + (3,) + self.view, **u8), "food": torch.empty(lead, **u8),
+            "grids": torch.empty(lead + (3,) + self.view, **u8) if self.emit_grids else None, "food": torch.empty(lead, **u8),
             "role": torch.empty(lead, **u8), "status": torch.empty(lead, **u8),
             "reward": torch.empty(lead, dtype=torch.float32, device=dev), "done": torch.empty(lead, **u8),
             "info": torch.empty(lead, **u8),
@@ -97,8 +103,8 @@ class VecEnv:
 
     @staticmethod
     def _obs_struct(buf) -> _lib.WabObs:
-        return _lib.WabObs(buf["grids"].data_ptr(), buf["food"].data_ptr(), buf["role"].data_ptr(),
-                           buf["status"].data_ptr())
+        return _lib.WabObs(buf["grids"].data_ptr() if buf.get("grids") is not None else 0, buf["food"].data_ptr(),
+                           buf["role"].data_ptr(), buf["status"].data_ptr())
 
     def _bind(self, buf):
         """Point the fused PragmaticObsWrapper feature output at this call's buffer (or switch it off)."""
