@@ -195,8 +195,11 @@ int wab2_create(const Wab2Config* cfg, int64_t n_envs, uint64_t seed, uint64_t e
     // threads per block: as many as shared memory allows (3E state words + one bit stream per thread)
     int max_smem = 48 * 1024;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-    int bs = 128;
+    // 64-thread CTAs: a 65,536-world batch is 1,024 CTAs = 6.9 per SM (12 or 14 warps), where 128-thread CTAs gave 3 or 4
+    // per SM (12 or 16 warps) and the fuller SMs set the launch time: 3.19e8 -> 3.35e8 world turns/s (profiles/r2v_v2_bs.txt)
+    int bs = 64;
     auto need = [&](int b) { return sizeof(uint32_t) * ((size_t)2 * E * b + (size_t)(((b >> 5) * h->stream_words + 1) & ~1) + 512); };
+    if (const char* eb = getenv("WAB2_BS")) { const int v = atoi(eb); if (v == 32 || v == 64 || v == 128) bs = v; }   // A/B runs
     while (bs > 32 && need(bs) > (size_t)max_smem / 2) bs >>= 1;
     if (need(bs) > (size_t)max_smem) { delete h; return fail(WAB_E_UNSUPPORTED, "too many entities for the shared-memory staging"); }
     h->bs = bs; h->smem_turn = need(bs); h->smem_init = sizeof(uint32_t) * (size_t)2 * E * bs;
