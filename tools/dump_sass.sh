@@ -15,6 +15,9 @@ for f in re.split(r'\n\s*Function : ', txt)[1:]:
                      ('wab2_grid_turn_kernelILb1ELb0E', 'v2_grid_turn')):
         if key in name:
             body = 'Function : ' + f
+            # keep the instruction text only: drop the hex encodings (and the encoding-only second line of every instruction)
+            body = '\n'.join(re.sub(r'\s*/\* 0x[0-9a-f]{16} \*/\s*$', '', ln) for ln in body.split('\n')
+                             if not re.match(r'^\s*/\* 0x[0-9a-f]{16} \*/\s*$', ln))
             n = len(re.findall(r'^\s+/\*[0-9a-f]{4,5}\*/', body, flags=re.M))
             ops = {}
             for m in re.finditer(r'^\s+/\*[0-9a-f]{4,5}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)', body, flags=re.M):
