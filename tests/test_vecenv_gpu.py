@@ -262,10 +262,11 @@ def test_million_env_checksum_against_oracle():
     env.close()
 
 
-@pytest.mark.parametrize("mapped", ["0", "1", "2"])
+@pytest.mark.parametrize("mapped", ["0", "1", "2", "3"])
 def test_host_buffer_path_and_masked_reset(mapped, monkeypatch):
     """Host entry points: staged copies (0), the kernel writing the pinned block directly (1), the same with the
-    thread-per-env kernel (2, the default for small batches) — all equal to the device path."""
+    thread-per-env kernel (2, the default for small batches), the 16-envs-per-CTA kernel whose every store is a full
+    16-byte one (3, opt-in) — all equal to the device path."""
     monkeypatch.setenv("WAB_HOST_MAPPED", mapped)
     n = 300
     a, b = _vec(n, seed=9), _vec(n, seed=9)

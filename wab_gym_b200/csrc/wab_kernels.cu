@@ -208,14 +208,15 @@ __device__ __forceinline__ int obs_align_off(const uint8_t* p) { return (int)(re
 // `lut` = 256 x uint2 in shared memory: byte value -> its 8 bits as 8 bytes (built once per CTA).
 // USE_LUT = false expands with two multiplies per 8 bytes instead (the lanes-per-env kernels: few chunks per step, and no
 // table means no CTA barrier anywhere in a single-step launch).
-template <bool USE_LUT = true, bool WIDE = kWideStores>
+// `lane` / STRIDE: the flushing thread's index among STRIDE cooperating threads (a warp: 32; a whole CTA: its size).
+template <bool USE_LUT = true, bool WIDE = kWideStores, int STRIDE = 32>
 __device__ __forceinline__ void stream_flush(const uint32_t* stream, const uint2* lut, uint8_t* gA, int off, int end,
                                              int lane, bool lut_built = true) {
     constexpr int SH = WIDE ? 5 : 4, CH = 1 << SH;               // chunk = one store of CH bytes
     const int c_lo = (off + CH - 1) >> SH, c_hi = end >> SH;     // chunks entirely inside [off, end)
     if (WIDE) {
 #pragma unroll kFlushUnroll
-        for (int c = c_lo + lane; c < c_hi; c += 32) {
+        for (int c = c_lo + lane; c < c_hi; c += STRIDE) {
             const uint32_t w = stream[c];
             uint2 q0, q1, q2, q3;
             if (USE_LUT && lut_built) {
@@ -235,7 +236,7 @@ __device__ __forceinline__ void stream_flush(const uint32_t* stream, const uint2
     } else {
         const uint16_t* hs = reinterpret_cast<const uint16_t*>(stream);
 #pragma unroll kFlushUnroll
-        for (int c = c_lo + lane; c < c_hi; c += 32) {
+        for (int c = c_lo + lane; c < c_hi; c += STRIDE) {
             const uint32_t h = hs[c];
             uint2 lo, hi;
             if (USE_LUT && lut_built) {
@@ -620,6 +621,90 @@ wab_step_chunk_kernel(const __grid_constant__ Params P, const StatePtrs st, cons
         cnt[WAB_STAT_EATS] = (uint32_t)acc_misc & 0xFFFFu;
         cnt[WAB_STAT_BAD_ACTIONS] = (uint32_t)(acc_misc >> 16) & 0xFFFFu;
         cnt[WAB_STAT_OVERFLOWS] = (uint32_t)(acc_misc >> 32) & 0xFFFFu;
+    }
+    flush_stats(st.wstats, cnt);
+}
+
+// ---- single-step kernel for the mapped host path: 8 lanes per env, 16 envs per CTA, CTA-wide emission ----------------
+// wab_vec_step_host_packed lets the kernel write the caller's pinned host block directly, so the step's compute time sits
+// in front of a PCIe-bound burst of stores. The thread-per-env kernel only issues whole 16-byte stores (its warps own
+// 16-byte-aligned slabs) but needs ~8 us for one step of a small batch; the lanes-per-env kernels need ~2.5 us, but
+// their warps own 4 x 363 bytes at arbitrary alignment and finish with up to 30 single-byte stores each — a separate PCIe
+// write per byte. Sixteen consecutive envs are 5,808 bytes = 363 x 16: a CTA of 128 threads (8 lanes per env) builds ONE
+// bit stream for its 16 envs and every store it issues is a full, aligned 16-byte one (a batch that is not a multiple of
+// 16 pays single bytes at its very end only). One CTA barrier per step — acceptable for a single-step launch.
+// Measured (profiles/r1f_e2e_paths.txt, round 2): bit-identical, but the host step does not wait for the compute —
+// 4,096 envs 50.0 -> 52.8 us, 16,384 envs 142 -> 158 us, only 1,024 envs gain (27.7 -> 26.8 us) — so it is opt-in
+// (WAB_HOST_MAPPED=3) and the thread-per-env kernel stays the default of the mapped path.
+constexpr int kCta16Envs = 16, kCta16Threads = 128;
+constexpr int kCta16Stream = (kCta16Envs * OBS_BYTES + 31 + 31) / 32 + 1;
+
+template <bool F64>
+__global__ void __launch_bounds__(kCta16Threads)
+wab_step_cta16_kernel(const __grid_constant__ Params P, const StatePtrs st, const uint8_t* __restrict__ actions, const OutPtrs out) {
+    extern __shared__ uint32_t smem[];
+    constexpr int LPE = 8, EPB = kCta16Envs;
+    const int64_t n = st.n;
+    Ctx c;
+    c.lane = threadIdx.x & 31; c.sub = c.lane % LPE; c.slot = c.lane / LPE;
+    c.env_local = threadIdx.x / LPE;
+    c.idx = (int64_t)blockIdx.x * EPB + c.env_local;
+    c.warp_first = c.idx - c.slot;
+    c.active = c.idx < n; c.writer = c.active && c.sub == 0;
+    c.n_valid = 0;
+    uint32_t* wolves_s = smem + c.env_local;                                  // [wolf_cap][EPB]
+    uint32_t* stream = smem + P.wolf_cap * EPB;                               // one bit stream for the CTA's 16 envs
+    pdl_launch_dependents();
+    pdl_wait();
+    Coop<LPE> coop;
+    coop.sub = (uint32_t)c.sub;
+    coop.gmask = ((1u << LPE) - 1u) << (c.lane - c.sub);
+    Env E;
+    Slots S;
+    S.wolves = wolves_s; S.wstride = EPB;
+    S.logcell = st.logcell + (c.active ? c.idx : 0); S.logcnt = st.logcnt + (c.active ? c.idx : 0); S.lstride = n;
+    if (c.active) load_env<F64>(P, st, c.idx, E, wolves_s, EPB);
+    else { E = Env(); }
+    StepOut O;
+    bool need_reset = false;
+    uint32_t cnt[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    if (c.active) {
+        env_step<F64, LPE>(P, E, S, (uint32_t)actions[c.idx], O, coop);
+        if (st.hist && c.writer && E.turn < (uint32_t)st.hist_len) st.hist[(int64_t)E.turn * n + c.idx] = pack_xy(E.x, E.y);
+        need_reset = O.done && P.auto_reset;
+    } else {
+        O = StepOut();
+    }
+    if (c.writer) {
+        cnt[WAB_STAT_STEPS] = 1u;
+        cnt[WAB_STAT_EPISODES] = O.outcome != 0u; cnt[WAB_STAT_FINISHED] = O.outcome == 1u;
+        cnt[WAB_STAT_STARVED] = O.outcome == 2u; cnt[WAB_STAT_KILLED] = O.outcome == 3u;
+        cnt[WAB_STAT_EATS] = O.ate; cnt[WAB_STAT_BAD_ACTIONS] = O.bad_action;
+    }
+    if (__any_sync(FULL, need_reset)) {
+        warp_reset<F64, LPE>(P, E, S, need_reset, c.lane, O.wm, O.bm, O.overflow);
+        if (need_reset) {
+            O.food_obs = food_observation(P, E, F64);
+            O.role = E.role; O.status = E.status;
+        }
+    }
+    apply_view_mask(P, O.role, O.wm, O.bm);
+    if (c.writer) {
+        cnt[WAB_STAT_OVERFLOWS] = O.overflow;
+        write_scalars(out, c.idx, O);
+        if (out.features) write_features(out.features, c.idx, O);
+        store_env<F64>(st, c.idx, E, wolves_s, EPB);
+    }
+    if (out.grids) {
+        const int64_t first_byte = (int64_t)blockIdx.x * EPB * OBS_BYTES;
+        const int off = obs_align_off(out.grids + first_byte);
+        const int64_t left = n - (int64_t)blockIdx.x * EPB;
+        const int n_valid = (int)(left < EPB ? left : EPB);
+        if (c.sub == 0)
+            stream_put(stream, off + OBS_BYTES * c.env_local, c.env_local == EPB - 1, off + EPB * OBS_BYTES, O.wm, O.bm, c.active);
+        __syncthreads();
+        stream_flush<false, kWideStores, kCta16Threads>(stream, nullptr, out.grids + (first_byte - off), off, off + OBS_BYTES * n_valid,
+                                                        (int)threadIdx.x);
     }
     flush_stats(st.wstats, cnt);
 }
@@ -1451,8 +1536,10 @@ int wab_vec_create(const WabConfig* cfg, const uint32_t* bush_thr, int32_t n_bus
         const size_t threads = lpe == 1 ? (size_t)WAB_THREADS_LPE1 : (size_t)WAB_THREADS_LPEN, epb = threads / lpe;
         return (n + epb - 1) / epb * (threads / 32);
     };
-    const size_t stat_rows = h->generic ? (n + GEN_WARPS - 1) / GEN_WARPS * GEN_WARPS
-                                        : (warps_of(1) > warps_of((size_t)h->lpe) ? warps_of(1) : warps_of((size_t)h->lpe));
+    const size_t cta16_rows = (n + kCta16Envs - 1) / kCta16Envs * (kCta16Threads / 32);   // the mapped host path's kernel
+    size_t stat_rows = h->generic ? (n + GEN_WARPS - 1) / GEN_WARPS * GEN_WARPS
+                                  : (warps_of(1) > warps_of((size_t)h->lpe) ? warps_of(1) : warps_of((size_t)h->lpe));
+    if (!h->generic && cta16_rows > stat_rows) stat_rows = cta16_rows;
     const size_t o_wstats = o; o = align_up(o + 64 * stat_rows, 256);
     cudaError_t e = cudaMalloc(&h->slab, o);
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaMalloc(state)"); }
@@ -1578,7 +1665,7 @@ int wab_vec_step_host_packed(WabVec* h, const uint8_t* h_actions, uint8_t* h_blo
     // thread-per-env kernel — whose warps own 16-byte-aligned slabs, so every store is a full 16-byte one — reads the
     // actions from, and streams its outputs into, the caller's pinned (hence device-mapped) host buffers; no staging
     // copy, and the transfer overlaps the step. Measured (profiles/r1_e2e_paths.txt): 52.7 vs 60.2 us per step at
-    // 4,096 envs; the copy engine wins from 32k envs up. WAB_HOST_MAPPED=0/1/2 forces staged / mapped / mapped with
+    // 4,096 envs; the copy engine wins from 32k envs up. WAB_HOST_MAPPED=0/1/2/3 forces staged / mapped / mapped with
     // the thread-per-env kernel.
     if (h->host_mapped < 0) {
         const char* e = getenv("WAB_HOST_MAPPED");
@@ -1601,8 +1688,17 @@ int wab_vec_step_host_packed(WabVec* h, const uint8_t* h_actions, uint8_t* h_blo
         if (h->m_dblock) {
             uint8_t* m = h->m_dblock - L.grids;                        // block offsets are relative to L.grids
             WabObs mo{m + L.grids, m + L.food, m + L.role, m + L.status};
-            if (int rc = launch_step(h, 1, h->m_dactions, mo, (float*)(m + L.reward), m + L.done, m + L.info, s,
-                                     h->host_mapped == 2 ? 1 : 0)) return rc;
+            if (h->host_mapped == 3 && !h->generic) {          // 16 envs per CTA, every store a full 16-byte one
+                OutPtrs mout{mo.d_grids, mo.d_food, mo.d_role, mo.d_status, (float*)(m + L.reward), m + L.done, m + L.info, h->d_features};
+                const unsigned grid = (unsigned)((h->n + kCta16Envs - 1) / kCta16Envs);
+                const size_t smem = sizeof(uint32_t) * ((size_t)h->P.wolf_cap * kCta16Envs + (size_t)kCta16Stream);
+                if (h->cfg.food_mode == WAB_FOOD_F64)
+                    launch_pdl(wab_step_cta16_kernel<true>, grid, kCta16Threads, smem, s, h->P, h->st, h->m_dactions, mout);
+                else
+                    launch_pdl(wab_step_cta16_kernel<false>, grid, kCta16Threads, smem, s, h->P, h->st, h->m_dactions, mout);
+                WAB_CUDA(cudaGetLastError());
+            } else if (int rc = launch_step(h, 1, h->m_dactions, mo, (float*)(m + L.reward), m + L.done, m + L.info, s,
+                                            h->host_mapped == 2 ? 1 : 0)) return rc;
             WAB_CUDA(cudaStreamSynchronize(s));
             return WAB_OK;
         }
