@@ -601,9 +601,9 @@ def run_ours(args):
     percall = v1_percall_leg(ctx, n, K, W, args.leg_window_ms)
 
     legs = {}
-    # the big-batch legs bound their output buffer: <= 64 steps per launch at 131,072 envs (3.1 GB), <= 24 at 1M envs (9.4 GB)
+    # the big-batch legs bound their output buffer: <= 128 steps per launch at 131,072 envs (6.2 GB), <= 24 at 1M envs (9.4 GB)
     plan = {
-        "large_batch": lambda: v1_fused_leg(ctx, 131072, min(K, 64), W, 64, args.leg_window_ms, with_collective=False),
+        "large_batch": lambda: v1_fused_leg(ctx, 131072, min(K, 128), W, 128, args.leg_window_ms, with_collective=False),
         "batch_1m": lambda: v1_fused_leg(ctx, 1048576, min(K, 24), W, 24, args.leg_window_ms, with_collective=False),
         "v2_config3": lambda: v2_leg(ctx, 65536, (20, 20, 10, 3, 20), args.leg_window_ms, "configs[2]"),
         "v2_config4": lambda: v2_leg(ctx, 131072, (64, 64, 8, 64, 256), args.leg_window_ms, "configs[3] (8-GPU share of 1,048,576)"),
